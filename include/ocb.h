@@ -1,0 +1,193 @@
+/*
+ * ocb.h — C ABI of the B200-native batched Overcooked / Balance-Beam simulator.
+ *
+ * This is the drop-in boundary under the reference's batched multi-agent env API
+ * (pantheonrl_extension/vectorenv.py:26-255, VectorMultiAgentEnv.n_step / n_reset).
+ * In the reference the same role is played by the nanobind class
+ * `SimplecookedSimulator` (src/overcooked2_env/bindings.cpp:27-96; tensor exports
+ * src/overcooked2_env/mgr.cpp:213-272) and `BalanceBeamSimulator`
+ * (src/balance_beam_env/bindings.cpp, mgr.cpp:191-233).  Each entry point below cites
+ * the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no torch / C++ types cross this boundary;
+ *   - return 0 on success, a negative OCB_ERR_* otherwise; never abort();
+ *     ocb_last_error() returns a thread-local human readable message;
+ *   - the library owns only the world state (structure-of-arrays in HBM);
+ *     every input / output buffer is owned by the caller (e.g. torch tensors);
+ *   - pointers are DEVICE pointers unless the function name ends in `_host`;
+ *   - all launches are asynchronous on the caller supplied `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream); the
+ *     library never synchronises except in the `_host`, get/set_state calls;
+ *   - one handle is single-threaded; different handles / GPUs are independent.
+ *
+ * Tensor layouts (N worlds, P players, W x H grid, C = 5P + 10 channels):
+ *   actions  [P, N]            int32 (or see ocb_step_ex), values 0..5
+ *                              (N,S,E,W,STAY,INTERACT; envs/overcooked2_reimplement.py:35-43);
+ *                              out-of-range values are treated as STAY
+ *   obs      [P, N, W, H, C]   int8, lossless state encoding
+ *                              (envs/overcooked2_reimplement.py:173-259, axis order
+ *                              envs/overcooked2_env.py:322-325)
+ *   reward   [P, N]            int32, team reward replicated per player
+ *                              (envs/overcooked2_env.py:336-339; mgr.cpp:244-248)
+ *   done     [N]               int32 0/1 (mgr.cpp:213-217); on a done step the world
+ *                              is reset and obs is the post-reset observation
+ *                              (pantheonrl_extension/vectorenv.py:369-370)
+ *   K-step rollouts prepend a [K] axis to every tensor.
+ */
+#ifndef OCB_H_
+#define OCB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCB_ABI_VERSION 1
+#define OCB_MAX_PLAYERS 4
+#define OCB_MAX_CELLS 256
+#define OCB_NUM_RECIPES 16 /* (MAX_NUM_INGREDIENTS+1)^2, index 4*onions+tomatoes */
+#define OCB_MAX_COOK_TIME 120 /* cooking tick must fit the int8 observation */
+
+/* error codes */
+#define OCB_OK 0
+#define OCB_ERR_INVALID_ARG (-1)
+#define OCB_ERR_BAD_LAYOUT (-2)
+#define OCB_ERR_CUDA (-3)
+#define OCB_ERR_NO_DEVICE (-4)
+#define OCB_ERR_BAD_STATE (-5)
+#define OCB_ERR_UNSUPPORTED (-6)
+
+/* action dtypes accepted by ocb_step_ex / ocb_rollout_actions */
+#define OCB_ACT_I32 0
+#define OCB_ACT_I64 1
+#define OCB_ACT_F32 2
+#define OCB_ACT_U8 3
+
+/*
+ * Flat POD layout description == the keyword arguments the reference passes to
+ * SimplecookedSimulator / DummyMDP (envs/overcooked2_env.py:171-291,
+ * envs/overcooked2_reimplement.py:121-151).
+ */
+typedef struct ocb_config {
+    uint32_t struct_size; /* sizeof(ocb_config): versioning */
+    int32_t width;
+    int32_t height;
+    int32_t num_players; /* 1..OCB_MAX_PLAYERS */
+    int32_t horizon;     /* episode length, done = timestep >= horizon */
+    int32_t placement_in_pot_rew;
+    int32_t dish_pickup_rew;
+    int32_t soup_pickup_rew;
+    int32_t recipe_values[OCB_NUM_RECIPES];
+    int32_t recipe_times[OCB_NUM_RECIPES];
+    int32_t start_player_x[OCB_MAX_PLAYERS];
+    int32_t start_player_y[OCB_MAX_PLAYERS];
+    /* terrain codes, row-major (pos = y*width + x):
+     * 0 AIR, 1 POT, 2 COUNTER, 3 ONION_SOURCE, 4 DISH_SOURCE, 5 SERVING, 6 TOMATO_SOURCE */
+    uint8_t terrain[OCB_MAX_CELLS];
+} ocb_config;
+
+typedef struct ocb_env ocb_env; /* opaque Overcooked handle */
+typedef struct bb_env bb_env;   /* opaque Balance-Beam handle */
+
+/* ------------------------------------------------------------------ misc */
+int ocb_abi_version(void);
+/* thread-local message describing the last error on this thread */
+const char* ocb_last_error(void);
+/* number of visible CUDA devices, or a negative error */
+int ocb_device_count(void);
+
+/* ------------------------------------------------------- Overcooked: life-cycle */
+/* replaces SimplecookedSimulator.__init__ (bindings.cpp:27-60, mgr.cpp:128-200);
+ * all worlds start in the standard start state (reimplement.py:387-391). */
+int ocb_create(const ocb_config* cfg, int device, uint32_t num_worlds, uint64_t seed, ocb_env** out);
+int ocb_destroy(ocb_env* env);
+
+/* shape queries */
+int ocb_num_worlds(const ocb_env* env);
+int ocb_num_players(const ocb_env* env);
+int ocb_obs_channels(const ocb_env* env);         /* C = 5P + 10 */
+int ocb_obs_bytes_per_agent(const ocb_env* env);  /* W*H*C */
+int ocb_state_ints_per_world(const ocb_env* env); /* length of one packed world state */
+
+/* kernel tuning knobs: lanes_per_world in {1,2,4} (0 = default), use_tma in {0,1} */
+int ocb_set_tuning(ocb_env* env, int lanes_per_world, int use_tma);
+
+/* ------------------------------------------------------- Overcooked: hot path */
+/* VectorMultiAgentEnv.n_reset (vectorenv.py:241-252 / SyncVectorEnv.n_reset 398-425):
+ * reset every world, optionally write obs [P,N,W,H,C] (obs may be NULL). */
+int ocb_reset(ocb_env* env, int8_t* obs, void* stream);
+
+/* observation of the current state, no stepping (OvercookedMadrona.get_obs,
+ * envs/overcooked2_env.py:103-114). */
+int ocb_observe(ocb_env* env, int8_t* obs, void* stream);
+
+/* VectorMultiAgentEnv.n_step (vectorenv.py:220-239; OvercookedMadrona.n_step
+ * envs/overcooked2_env.py:116-125 == sim.step() + scatter glue). One fused kernel:
+ * interact -> movement/collision -> cook tick -> reward -> done/auto-reset -> obs.
+ * obs / reward / done may each be NULL to skip that output. */
+int ocb_step(ocb_env* env, const int32_t* actions, int8_t* obs, int32_t* reward, int32_t* done, void* stream);
+/* same, actions given in another dtype (trainers pass float32, envs/overcooked2_env.py:119) */
+int ocb_step_ex(ocb_env* env, const void* actions, int act_dtype, int8_t* obs, int32_t* reward, int32_t* done,
+                void* stream);
+
+/* K fused steps in one launch with caller supplied actions [K,P,N]; outputs get a
+ * leading [K] axis (obs_slab [K,P,N,W,H,C]); any output may be NULL. */
+int ocb_rollout_actions(ocb_env* env, int K, const void* actions, int act_dtype, int8_t* obs_slab,
+                        int32_t* reward, int32_t* done, void* stream);
+
+/* K fused steps with uniform random actions drawn on the device from the
+ * counter-based RNG (Philox4x32-10 keyed by seed, indexed by (world, step));
+ * actions_out [K,P,N] uint8 (may be NULL) records what was played so the
+ * trajectory can be replayed through the oracle. */
+int ocb_rollout_random(ocb_env* env, int K, int8_t* obs_slab, int32_t* reward, int32_t* done,
+                       uint8_t* actions_out, void* stream);
+
+/* host-buffer variant of ocb_step: copies actions H2D, steps, copies outputs D2H
+ * and synchronises.  Pointers are HOST pointers (pinned memory recommended);
+ * h_obs / h_reward / h_done may be NULL. */
+int ocb_step_host(ocb_env* env, const int32_t* h_actions, int8_t* h_obs, int32_t* h_reward, int32_t* h_done);
+
+/* ------------------------------------------------------- Overcooked: state I/O */
+/* Packed world state, int32 [N, L], L = ocb_state_ints_per_world():
+ *   [0]            timestep
+ *   per player i:  pos, orientation, held_name, held_onions, held_tomatoes, held_cooking_tick
+ *   per cell c:    obj_name, obj_onions, obj_tomatoes, obj_cooking_tick   (name 0 = NONE)
+ * mirrors OvercookedState / PlayerState / ObjectState (reimplement.py:46-117).
+ * HOST pointers; these calls synchronise. */
+int ocb_get_state(ocb_env* env, int32_t* h_state, size_t n_ints);
+int ocb_set_state(ocb_env* env, const int32_t* h_state, size_t n_ints);
+
+/* per-world episode statistics kept on the device: sum of returns of completed
+ * episodes, number of completed episodes (replaces the host-side
+ * running_score bookkeeping, train/MAPPO/main_player.py:256-261).
+ * DEVICE pointers, each may be NULL. */
+int ocb_read_episode_stats(ocb_env* env, int64_t* return_sum, int32_t* episodes, void* stream);
+int ocb_clear_episode_stats(ocb_env* env, void* stream);
+
+/* global step counter that indexes the action RNG (incremented by every step) */
+uint64_t ocb_step_count(const ocb_env* env);
+
+/* ------------------------------------------------------- Balance-Beam */
+/* replaces BalanceBeamSimulator (src/balance_beam_env/mgr.cpp:191-233) behind
+ * MadronaEnv.n_step / n_reset (vectorenv.py:306-343).
+ *   actions [2,N] int32 in 0..3 (moves -2,-1,+1,+2; envs/balance_beam_env.py:14)
+ *   obs     [2,N,7] int32, reward [2,N] float32, done [N] int32. */
+int bb_create(int device, uint32_t num_worlds, uint64_t seed, bb_env** out);
+int bb_destroy(bb_env* env);
+int bb_num_worlds(const bb_env* env);
+int bb_reset(bb_env* env, int32_t* obs, void* stream);
+int bb_observe(bb_env* env, int32_t* obs, void* stream);
+int bb_step(bb_env* env, const int32_t* actions, int32_t* obs, float* reward, int32_t* done, void* stream);
+int bb_rollout_random(bb_env* env, int K, int32_t* obs_slab, float* reward, int32_t* done, uint8_t* actions_out,
+                      void* stream);
+/* packed state int32 [N,8]: loc0, loc1, time, hist0[t-1], hist0[t-2], hist1[t-1], hist1[t-2], episode */
+int bb_get_state(bb_env* env, int32_t* h_state, size_t n_ints);
+int bb_set_state(bb_env* env, const int32_t* h_state, size_t n_ints);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCB_H_ */
