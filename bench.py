@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path
+
+Workload (BASELINE.json configs[2], the one the metric's target is quoted on):
+Overcooked cramped_room, 2 agents, horizon 400, 16,384 worlds per GPU, uniform random
+actions drawn on the device, env step + observation encode only.
+
+A "step" is one environment step of every world of the job.  The device-timed `value`
+runs `--steps` steps as fused launches of `--steps-per-launch` steps each
+(ocb_rollout_random); every launch writes a [spl, P, N, W, H, C] observation slab
+(1.3 GB at the defaults, >> the 126 MB L2, so no flush is needed between launches).
+`e2e` runs the reference-facing single-step call with HOST buffers (ocb_step_host:
+pinned actions H2D, kernel, obs + rewards + dones D2H, sync) — one launch per step.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LAYOUT = "simple"  # cramped_room
+HORIZON = 400
+WORLDS_PER_GPU = 16384
+METRIC = "agent-steps/sec (env+obs)"
+UNIT = "agent-steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--warmup", type=int, default=400)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--steps-per-launch", type=int, default=100)
+    ap.add_argument("--worlds", type=int, default=WORLDS_PER_GPU)
+    ap.add_argument("--layout", default=LAYOUT)
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per world (kernel tuning), 0 = library default")
+    ap.add_argument("--tma", type=int, default=-1, help="1/0 force the TMA bulk-store path, -1 = library default")
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "overcooked cramped_room (simple.layout), 2 agents, horizon %d, %d worlds/GPU, "
+                        "random actions, env step + obs encode" % (HORIZON, args.worlds),
+            "layout": args.layout, "worlds_per_gpu": args.worlds, "n_worlds": args.worlds * n_gpus,
+            "horizon": HORIZON, "steps_per_launch": args.steps_per_launch,
+            "l2_policy": "outputs larger than L2 (obs slab per launch >> 126 MB); no flush needed",
+            "parallelism": "worlds sharded, %d per GPU, no data-path collective" % args.worlds}
+
+
+# ----------------------------------------------------------------------------- CPU baselines
+def _py_port_worker(job):
+    """one process: the Python port of the reference env on `n` worlds for `steps` steps"""
+    layout, horizon, n, steps, seed = job
+    import numpy as np
+    from diverse_conventions_b200 import layouts
+    from oracle.overcooked_oracle import OvercookedOracle
+    lp = layouts.load_layout(layout, horizon)
+    orc = OvercookedOracle(lp, n)
+    acts = np.random.default_rng(seed).integers(0, 6, size=(steps, lp.num_players, n))
+    t0 = time.perf_counter()
+    for k in range(steps):
+        orc.step(acts[k])
+    return n * steps, time.perf_counter() - t0
+
+
+def cpu_port_throughput(layout, steps, budget_s, cores):
+    """agent-steps/s of the Python port (the reference's CPU path is per-world Python too,
+    envs/overcooked2_reimplement.py + pantheonrl_extension/vectorenv.py:362-396), all cores."""
+    import concurrent.futures as cf
+    ws, dt = _py_port_worker((layout, HORIZON, 2, 50, 0))  # calibrate: seconds per world-step
+    per_ws = dt / ws
+    n_per_core = int(max(1, min(256, budget_s / (per_ws * steps))))
+    jobs = [(layout, HORIZON, n_per_core, steps, 100 + i) for i in range(cores)]
+    with cf.ProcessPoolExecutor(max_workers=cores) as ex:
+        res = list(ex.map(_py_port_worker, jobs))
+    total_ws = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return 2 * total_ws / wall, n_per_core * cores, steps
+
+
+def c_port_throughput(layout, budget_s, threads):
+    """agent-steps/s of the C restatement (oracle/ocb_oracle.c), `threads` host threads"""
+    import concurrent.futures as cf
+    import numpy as np
+    from diverse_conventions_b200 import layouts
+    from oracle.c_oracle import COracle
+    lp = layouts.load_layout(layout, HORIZON)
+    n, K = 2048, 50
+    acts = np.random.default_rng(0).integers(0, 6, size=(K, 2, n)).astype(np.uint8)
+
+    def work(_):
+        orc = COracle(lp, n)
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < budget_s:
+            orc.rollout(acts)
+            reps += 1
+        return reps * n * K, time.perf_counter() - t0
+
+    with cf.ThreadPoolExecutor(max_workers=threads) as ex:  # ctypes releases the GIL
+        res = list(ex.map(work, range(threads)))
+    return 2 * sum(r[0] for r in res) / max(r[1] for r in res)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    c_oracle.build()
+    cores = host_cores()
+    t0 = time.perf_counter()
+    steps = max(args.steps, 1)
+    # warm-up: a short run of the same worker (process pool start, imports)
+    _py_port_worker((args.layout, HORIZON, 2, max(min(args.warmup, 50), 3), 1))
+    value, n_worlds, steps_done = cpu_port_throughput(args.layout, min(steps, 2000), 20.0, cores)
+    c_value = c_port_throughput(args.layout, 3.0, cores)
+    cfg = workload_config(args, args.gpus)
+    sample = "%d worlds x %d steps over %d processes (python port of the reference env, 1 process per core)" % (
+        n_worlds, steps_done, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 2 * n_worlds / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "c_port_value": c_value,
+                             "c_port_note": "oracle/ocb_oracle.c (C restatement, -O2), %d threads" % cores},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t_begin - 0.05 <= t <= t_end + 0.15] or [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from diverse_conventions_b200 import layouts
+    from diverse_conventions_b200.overcooked_env import B200Overcooked
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    N, K, W, spl = args.worlds, args.steps, args.warmup, args.steps_per_launch
+    lp = layouts.load_layout(args.layout, HORIZON)
+    P = lp.num_players
+    env = B200Overcooked(args.layout, N, local, horizon=HORIZON, seed=0, world_offset=rank * N)
+    if args.lanes or args.tma >= 0:
+        env.set_tuning(args.lanes, bool(max(args.tma, 0)))
+    out = env.alloc_rollout(spl, obs=True, actions=False)
+    bytes_ws = layouts.io_bytes_per_world_step(lp)
+
+    def run_steps(n_steps, events=None):
+        launches, done_steps = 0, 0
+        while done_steps < n_steps:
+            k = min(spl, n_steps - done_steps)
+            if events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            env.rollout_random(k, out)
+            if events is not None:
+                e1.record()
+                events.append((k, e0, e1))
+            done_steps += k
+            launches += 1
+        return launches
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    run_steps(max(W, 3))
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_begin = time.perf_counter()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    events = []
+    start.record()
+    launches = run_steps(K, events)
+    stop.record()
+    barrier()
+    t_end = time.perf_counter()
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
+    ms = torch.tensor([start.elapsed_time(stop)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = P * N * world * K / (ms_total * 1e-3)
+
+    # per-launch duration of the dominant kernel (full launches only) -> roofline
+    full = [e0.elapsed_time(e1) for k, e0, e1 in events if k == spl]
+    launch_ms = statistics.mean(full) if full else ms_total / max(launches, 1)
+    k_launch = spl if full else K
+    achieved = bytes_ws * N * k_launch / (launch_ms * 1e-3) / 1e9
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f)["hbm_gbs"])
+            peak_src = "MEASURED_PEAKS.json hbm_gbs (sustained copy)"
+    except Exception:
+        pass
+
+    # end-to-end: the reference-facing single-step call with host buffers
+    E = max(args.e2e_steps, 1)
+    h_act = torch.randint(0, 6, (P, N), dtype=torch.int32).pin_memory()
+    h_obs = torch.empty((P, N, lp.width, lp.height, lp.channels), dtype=torch.int8).pin_memory()
+    h_rew = torch.empty((P, N), dtype=torch.int32).pin_memory()
+    h_done = torch.empty((N,), dtype=torch.int32).pin_memory()
+    for _ in range(5):
+        env.step_host(h_act, h_obs, h_rew, h_done)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(E):
+        env.step_host(h_act, h_obs, h_rew, h_done)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = P * N * world * E / float(e2e_s.item())
+    h2d = 4 * P * N
+    d2h = P * N * lp.size * lp.channels + 4 * P * N + 4 * N
+    # same call without shipping the observation planes over PCIe (they normally stay on the device)
+    t0 = time.perf_counter()
+    for _ in range(E):
+        env.step_host(h_act, None, h_rew, h_done)
+    torch.cuda.synchronize()
+    e2e_noobs = P * N * E / (time.perf_counter() - t0)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": "oc_rollout_kernel<2,%d>" % (args.lanes or 4),
+                             "bytes_per_world_step": bytes_ws, "world_steps_per_launch": N * k_launch,
+                             "launch_ms": launch_ms, "peak_source": peak_src},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "call": "ocb_step_host (1 launch / step, obs+reward+done to pinned host memory)",
+                        "steps": E, "value_without_obs_d2h_rank0": e2e_noobs},
+                "gpu_launches": launches, "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle import c_oracle
+                c_oracle.build()
+                cores = host_cores()
+                v, n_worlds, steps_done = cpu_port_throughput(args.layout, 400, args.cpu_seconds, cores)
+                line["cpu_baseline"] = {
+                    "value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": "%d worlds x %d steps, python port of the reference env, 1 process per core" % (
+                        n_worlds, steps_done),
+                    "c_port_value": c_port_throughput(args.layout, 2.0, cores),
+                    "c_port_note": "oracle/ocb_oracle.c (C restatement), %d threads" % cores}
+            except Exception as exc:  # the baseline must never take the GPU line down
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % exc}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,108 @@
+"""ctypes binding of the C ABI (include/ocb.h) — the only way Python reaches the kernels.
+
+There is deliberately no fallback: if ``libocb.so`` is missing or a call fails, an
+exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from typing import List
+
+from . import build as _build
+from .layouts import ocb_config
+
+OCB_OK = 0
+ACT_I32, ACT_I64, ACT_F32, ACT_U8 = 0, 1, 2, 3
+
+_lib = None
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_u32 = ctypes.c_uint32
+_u64 = ctypes.c_uint64
+_sz = ctypes.c_size_t
+_pp = ctypes.POINTER(ctypes.c_void_p)
+
+# name -> (restype, argtypes); must list every function declared in include/ocb.h
+PROTOTYPES = {
+    "ocb_abi_version": (_i, []),
+    "ocb_last_error": (ctypes.c_char_p, []),
+    "ocb_device_count": (_i, []),
+    "ocb_create": (_i, [ctypes.POINTER(ocb_config), _i, _u32, _u64, _pp]),
+    "ocb_destroy": (_i, [_vp]),
+    "ocb_num_worlds": (_i, [_vp]),
+    "ocb_num_players": (_i, [_vp]),
+    "ocb_obs_channels": (_i, [_vp]),
+    "ocb_obs_bytes_per_agent": (_i, [_vp]),
+    "ocb_state_ints_per_world": (_i, [_vp]),
+    "ocb_set_tuning": (_i, [_vp, _i, _i]),
+    "ocb_reset": (_i, [_vp, _vp, _vp]),
+    "ocb_observe": (_i, [_vp, _vp, _vp]),
+    "ocb_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "ocb_step_ex": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "ocb_rollout_actions": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "ocb_rollout_random": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "ocb_step_host": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "ocb_get_state": (_i, [_vp, _vp, _sz]),
+    "ocb_set_state": (_i, [_vp, _vp, _sz]),
+    "ocb_read_episode_stats": (_i, [_vp, _vp, _vp, _vp]),
+    "ocb_clear_episode_stats": (_i, [_vp, _vp]),
+    "ocb_step_count": (_u64, [_vp]),
+    "ocb_set_world_offset": (_i, [_vp, _u32]),
+    "bb_create": (_i, [_i, _u32, _u64, _pp]),
+    "bb_destroy": (_i, [_vp]),
+    "bb_num_worlds": (_i, [_vp]),
+    "bb_reset": (_i, [_vp, _vp, _vp]),
+    "bb_observe": (_i, [_vp, _vp, _vp]),
+    "bb_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "bb_rollout_random": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "bb_get_state": (_i, [_vp, _vp, _sz]),
+    "bb_set_state": (_i, [_vp, _vp, _sz]),
+}
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__("libocb error %d: %s" % (code, message))
+        self.code = code
+
+
+def header_path() -> str:
+    return os.path.join(os.path.dirname(_build.HERE), "include", "ocb.h")
+
+
+def declared_symbols() -> List[str]:
+    """Function names declared in include/ocb.h (parsed, so the header stays the source of truth)."""
+    with open(header_path()) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    names = re.findall(r"\b((?:ocb|bb)_[a-z0-9_]+)\s*\(", text)
+    return sorted(set(names))
+
+
+def lib(build_if_missing: bool = True):
+    """Load (building first if the sources are newer) and return the ctypes library."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB_PATH
+        if build_if_missing and _build.is_stale() and _build.find_nvcc() is not None:
+            _build.build_native()
+        if not os.path.exists(path):
+            raise ImportError(
+                "%s is missing: build it with `python -m diverse_conventions_b200.build` "
+                "(there is no CPU fallback)" % path)
+        L = ctypes.CDLL(path)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)  # AttributeError if the .so lacks a declared symbol
+            fn.restype, fn.argtypes = res, args
+        if L.ocb_abi_version() != 1:
+            raise ImportError("libocb.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(code: int) -> int:
+    if code < 0:
+        raise NativeError(code, lib().ocb_last_error().decode("utf-8", "replace"))
+    return code

@@ -1,0 +1,26 @@
+// api_common.h — helpers shared by the C-ABI translation units
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ocb {
+
+extern thread_local char g_err[512];
+// records a printf-style message for ocb_last_error() and returns `code`
+int fail(int code, const char* fmt, ...);
+
+// makes `device` current for the scope of one ABI call and restores the caller's device
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) {
+            cudaSetDevice(device);
+            switched = true;
+        }
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace ocb

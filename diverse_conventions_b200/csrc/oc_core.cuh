@@ -1,0 +1,385 @@
+// oc_core.cuh — per-world Overcooked logic shared by the sm_100a kernels
+// (oc_kernels.cu) and by the host-side emulation harness used in the CPU tests
+// (tests/emu/oc_emu.cpp).  Everything here is a pure function of registers and of
+// a few small shared-memory tables; no global memory, no synchronisation.
+//
+// Semantics follow the reference's Python MDP (envs/overcooked2_reimplement.py,
+// "R:" below) — not its Madrona ECS systems.  The design differs from both:
+//   * world state is packed: one 32-bit word per player, one 16-bit word per cell;
+//   * the pot / dish bookkeeping needed by the shaped reward is kept incrementally
+//     (dishes lying on counters) instead of re-scanning the grid;
+//   * the observation is not re-encoded from scratch: each world keeps its
+//     (W,H,C) planes resident in shared memory and only the bytes touched by the
+//     transition are rewritten before the planes are streamed out.
+#pragma once
+#include <stdint.h>
+
+#include "ocb.h"
+
+#if defined(__CUDACC__)
+#define OCB_HD __host__ __device__ __forceinline__
+#define OCB_HDM __host__ __device__ __forceinline__
+#else
+#define OCB_HD static inline
+#define OCB_HDM inline
+#endif
+
+namespace ocb {
+
+constexpr int kMaxCells = OCB_MAX_CELLS;
+constexpr int kMaxPlayers = OCB_MAX_PLAYERS;
+constexpr int kMaxPots = 32;
+
+// terrain (R:12-19), objects (R:5-9), actions (R:35-43)
+enum : int { T_AIR = 0, T_POT = 1, T_COUNTER = 2, T_ONION_SRC = 3, T_DISH_SRC = 4, T_SERVING = 5, T_TOMATO_SRC = 6 };
+enum : int { O_NONE = 0, O_TOMATO = 1, O_ONION = 2, O_DISH = 3, O_SOUP = 4 };
+enum : int { A_NORTH = 0, A_SOUTH = 1, A_EAST = 2, A_WEST = 3, A_STAY = 4, A_INTERACT = 5 };
+
+// Static per-layout tables, built on the host (ocb_api.cu: build_tables) and staged
+// into shared memory by every CTA.
+struct alignas(16) Tables {
+    int32_t W, H, S, P, C, SC; // SC = S*C bytes of one agent's observation
+    int32_t horizon, n_pots, n_objcells;
+    int32_t rew_place, rew_dish, rew_soup;
+    int32_t start_pos[kMaxPlayers];
+    int32_t rvalue[OCB_NUM_RECIPES];
+    uint8_t rtime[OCB_NUM_RECIPES];
+    uint8_t terrain[kMaxCells];
+    uint16_t slot_off[kMaxCells];  // byte offset of a cell inside a (W,H,C) plane: (x*H+y)*C
+    uint16_t pot_cells[kMaxPots];  // cells with POT terrain
+    uint16_t objcells[kMaxCells];  // cells that can hold an object: counters, then pots
+};
+
+// ---------------------------------------------------------------- packed objects
+// bits 0-2 name | 3-4 tomatoes | 5-6 onions | 8-15 cooking_tick+1 ; NONE == 0.
+// (ObjectState, R:46-57; recipe index 4*onions+tomatoes == bits 3..6)
+OCB_HD uint32_t obj_make(int name, int onions, int tomatoes, int tick) {
+    return (uint32_t)name | ((uint32_t)tomatoes << 3) | ((uint32_t)onions << 5) | ((uint32_t)(tick + 1) << 8);
+}
+OCB_HD int obj_name(uint32_t o) { return (int)(o & 7u); }
+OCB_HD int obj_tomatoes(uint32_t o) { return (int)((o >> 3) & 3u); }
+OCB_HD int obj_onions(uint32_t o) { return (int)((o >> 5) & 3u); }
+OCB_HD int obj_recipe(uint32_t o) { return (int)((o >> 3) & 15u); }
+OCB_HD int obj_tickp1(uint32_t o) { return (int)((o >> 8) & 0xFFu); }
+OCB_HD int obj_ingredients(uint32_t o) { return obj_onions(o) + obj_tomatoes(o); }
+
+// player word: bits 0-11 pos | 12-13 orientation | 16-31 held object
+OCB_HD uint32_t player_pack(int pos, int orient, uint32_t held) {
+    return (uint32_t)pos | ((uint32_t)orient << 12) | (held << 16);
+}
+
+template <int P>
+struct World {
+    int pos[P];
+    int orient[P];
+    uint32_t held[P];
+    int timestep;
+    int counter_dishes;  // number of DISH objects lying on COUNTER cells
+};
+
+template <int P>
+OCB_HD int sel(const int (&a)[P], int idx) {
+    int r = a[0];
+#pragma unroll
+    for (int q = 1; q < P; ++q) r = (idx == q) ? a[q] : r;
+    return r;
+}
+template <int P>
+OCB_HD uint32_t selu(const uint32_t (&a)[P], int idx) {
+    uint32_t r = a[0];
+#pragma unroll
+    for (int q = 1; q < P; ++q) r = (idx == q) ? a[q] : r;
+    return r;
+}
+
+OCB_HD int dir_delta(int d, int W) {  // R:22-32
+    return d == A_NORTH ? -W : d == A_SOUTH ? W : d == A_EAST ? 1 : d == A_WEST ? -1 : 0;
+}
+
+// is_cooking / is_ready, R:159-163 (tick = tickp1-1, time = rtime[recipe])
+OCB_HD bool soup_cooking(const Tables& tb, uint32_t o) {
+    const int tp1 = obj_tickp1(o);
+    return tp1 >= 1 && tp1 <= (int)tb.rtime[obj_recipe(o)];
+}
+OCB_HD bool soup_ready(const Tables& tb, uint32_t o) {
+    const int tp1 = obj_tickp1(o);
+    return tp1 >= 1 && tp1 > (int)tb.rtime[obj_recipe(o)];
+}
+
+// One world transition (R:381-385): resolve_interacts -> resolve_movement ->
+// step_environment_effects.  `objs[cell*ostride]` is this world's object on `cell`.
+// dirty[i] receives the counter / pot cell touched by player i's interact (or -1).
+// Returns the team reward (sum over players; envs/overcooked2_env.py:336).
+template <int P>
+OCB_HD int step_world(const Tables& tb, World<P>& w, uint16_t* objs, int ostride, const int (&act)[P], int (&dirty)[P]) {
+    int reward = 0;
+    bool any_interact = false;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        dirty[i] = -1;
+        any_interact |= (act[i] == A_INTERACT);
+    }
+
+    if (any_interact) {
+        // pot snapshot taken once before the player loop (R:302, get_pot_states R:272-281)
+        int non_empty_pots = 0;
+        for (int q = 0; q < tb.n_pots; ++q) {
+            const uint32_t o = objs[(int)tb.pot_cells[q] * ostride];
+            non_empty_pots += (o != 0u && (obj_tickp1(o) >= 1 || obj_ingredients(o) < 3)) ? 1 : 0;
+        }
+        // players in index order on live state (R:305-353)
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            if (act[i] != A_INTERACT) continue;
+            const int tgt = w.pos[i] + dir_delta(w.orient[i], tb.W);  // pre-move pose, R:309-310
+            const int t = tb.terrain[tgt];
+            const uint32_t h = w.held[i];
+            if (t == T_COUNTER) {  // R:313-319
+                const uint32_t o = objs[tgt * ostride];
+                if (h != 0u && o == 0u) {
+                    objs[tgt * ostride] = (uint16_t)h;
+                    w.held[i] = 0u;
+                    w.counter_dishes += (obj_name(h) == O_DISH);
+                } else if (h == 0u && o != 0u) {
+                    w.held[i] = o;
+                    objs[tgt * ostride] = 0;
+                    w.counter_dishes -= (obj_name(o) == O_DISH);
+                }
+                dirty[i] = tgt;
+            } else if (t == T_ONION_SRC) {  // R:320-321
+                if (h == 0u) w.held[i] = obj_make(O_ONION, 0, 0, -1);
+            } else if (t == T_TOMATO_SRC) {  // R:322-323
+                if (h == 0u) w.held[i] = obj_make(O_TOMATO, 0, 0, -1);
+            } else if (t == T_DISH_SRC) {  // R:324-327, is_dish_pickup_useful R:261-270
+                if (h == 0u) {
+                    if (P == 2) {
+                        int held_dishes = 0;
+#pragma unroll
+                        for (int j = 0; j < P; ++j) held_dishes += (obj_name(w.held[j]) == O_DISH);
+                        if (w.counter_dishes == 0 && held_dishes < non_empty_pots) reward += tb.rew_dish;
+                    }
+                    w.held[i] = obj_make(O_DISH, 0, 0, -1);
+                }
+            } else if (t == T_POT) {  // R:331-349
+                if (h != 0u) {
+                    uint32_t o = objs[tgt * ostride];
+                    const int hn = obj_name(h);
+                    if (hn == O_DISH && o != 0u && soup_ready(tb, o)) {  // R:332-336
+                        w.held[i] = o;
+                        objs[tgt * ostride] = 0;
+                        reward += tb.rew_soup;
+                    } else if (hn == O_ONION || hn == O_TOMATO) {  // R:337-349
+                        if (o == 0u) o = obj_make(O_SOUP, 0, 0, -1);
+                        if (!(obj_tickp1(o) >= 1 || obj_ingredients(o) == 3)) {
+                            o += (hn == O_ONION) ? (1u << 5) : (1u << 3);
+                            w.held[i] = 0u;
+                            reward += tb.rew_place;
+                        }
+                        // soup_to_be_cooked_at_location (R:287-296) and full -> auto start
+                        if (obj_name(o) == O_SOUP && !soup_cooking(tb, o) && !soup_ready(tb, o) &&
+                            obj_ingredients(o) == 3)
+                            o = (o & 0xFFu) | (1u << 8);
+                        objs[tgt * ostride] = (uint16_t)o;
+                    }
+                    dirty[i] = tgt;
+                }
+            } else if (t == T_SERVING) {  // R:350-353, deliver_soup R:283-285
+                if (h != 0u && obj_name(h) == O_SOUP) {
+                    reward += tb.rvalue[obj_recipe(h)];
+                    w.held[i] = 0u;
+                }
+            }
+        }
+    }
+
+    // resolve_movement R:368-371, _move_if_direction R:393-399
+    int np[P], no[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const int a = act[i];
+        const int cand = w.pos[i] + dir_delta(a, tb.W);  // INTERACT/STAY -> delta 0
+        const bool walk = (a < A_STAY) && (tb.terrain[cand] == T_AIR);
+        np[i] = walk ? cand : w.pos[i];
+        no[i] = (a < A_STAY) ? a : w.orient[i];
+    }
+    // _handle_collisions R:356-366: any colliding pair freezes every position
+    bool blocked = false;
+#pragma unroll
+    for (int i = 0; i < P; ++i)
+#pragma unroll
+        for (int j = i + 1; j < P; ++j)
+            blocked |= (np[i] == np[j]) || (np[i] == w.pos[j] && w.pos[i] == np[j]);
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        w.pos[i] = blocked ? w.pos[i] : np[i];
+        w.orient[i] = no[i];
+    }
+
+    // step_environment_effects R:373-379 (cooking soups only ever sit in pots)
+    w.timestep += 1;
+    for (int q = 0; q < tb.n_pots; ++q) {
+        const int cell = tb.pot_cells[q];
+        const uint32_t o = objs[cell * ostride];
+        if (obj_name(o) == O_SOUP && soup_cooking(tb, o)) objs[cell * ostride] = (uint16_t)(o + 0x100u);
+    }
+    return reward;
+}
+
+template <int P>
+OCB_HD void reset_world(const Tables& tb, World<P>& w) {  // R:387-391
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        w.pos[i] = tb.start_pos[i];
+        w.orient[i] = 0;
+        w.held[i] = 0u;
+    }
+    w.timestep = 0;
+    w.counter_dishes = 0;
+}
+
+// ---------------------------------------------------------------- observation bytes
+// lossless_state_encoding, R:173-259; plane layout (W,H,C) as delivered by the env
+// adapter (envs/overcooked2_env.py:322-325).  shift = 5P.
+
+// the five dynamic channels shift+5..shift+9 of a counter / pot cell (R:177-211)
+template <int P>
+OCB_HD void encode_cell(const Tables& tb, uint8_t* plane, int cell, uint32_t o) {
+    uint8_t* px = plane + tb.slot_off[cell] + 5 * P + 5;
+    const int name = obj_name(o);
+    const bool soup_in_pot = (name == O_SOUP) && (tb.terrain[cell] == T_POT);
+    const int tp1 = obj_tickp1(o);
+    px[0] = soup_in_pot ? (uint8_t)obj_onions(o) : (uint8_t)0;
+    px[1] = (soup_in_pot && tp1 >= 1) ? (uint8_t)(tp1 - 1) : (uint8_t)0;
+    px[2] = (name == O_SOUP && !soup_in_pot) ? 1 : 0;
+    px[3] = (name == O_DISH) ? 1 : 0;
+    px[4] = (name == O_ONION) ? 1 : 0;
+}
+
+// player i as seen by `viewer` (R:221-257): position one-hot, orientation one-hot of
+// the relative player index, held object drawn on the holder's cell
+template <int P>
+OCB_HD void poke_player(const Tables& tb, uint8_t* plane, int viewer, int i, int pos, int orient, uint32_t held) {
+    uint8_t* px = plane + tb.slot_off[pos];
+    const int rel = (i == viewer) ? 0 : (i < viewer ? i + 1 : i);
+    px[rel] = 1;
+    px[P + 4 * rel + orient] = 1;
+    const int name = obj_name(held);
+    if (name == O_SOUP) px[5 * P + 7] = 1;
+    else if (name == O_DISH) px[5 * P + 8] = 1;
+    else if (name == O_ONION) px[5 * P + 9] = 1;
+}
+
+// a cell a player has left: players only stand on AIR, whose static bytes are all 0
+template <int P>
+OCB_HD void clear_cell(const Tables& tb, uint8_t* plane, int pos) {
+    constexpr int C = 5 * P + 10;
+    uint8_t* px = plane + tb.slot_off[pos];
+    if (C % 4 == 0) {
+        uint32_t* p4 = reinterpret_cast<uint32_t*>(px);
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q) p4[q] = 0u;
+    } else {
+#pragma unroll
+        for (int q = 0; q < C; ++q) px[q] = 0;
+    }
+}
+
+// Role-split plane maintenance.  A world is served by G lanes (g = 0..G-1); the
+// caller separates phase 1 and phase 2 with a warp barrier.
+//   full == true : rebuild from the static template (launch start, episode reset)
+//   full == false: rewrite only what the transition touched.
+// planes: this world's plane of view v is at planes + v*view_stride.
+template <int P, int G>
+OCB_HD void obs_phase1(const Tables& tb, uint8_t* planes, int view_stride, const uint8_t* tmpl, bool full, int g,
+                       const int (&oldpos)[P]) {
+    if (full) {
+        if (tb.SC % 4 == 0) {
+            const uint32_t* t4 = reinterpret_cast<const uint32_t*>(tmpl);
+            const int n4 = tb.SC >> 2;
+            for (int v = 0; v < P; ++v) {
+                uint32_t* d4 = reinterpret_cast<uint32_t*>(planes + v * view_stride);
+                for (int j = g; j < n4; j += G) d4[j] = t4[j];
+            }
+        } else {
+            for (int v = 0; v < P; ++v)
+                for (int j = g; j < tb.SC; j += G) planes[v * view_stride + j] = tmpl[j];
+        }
+    } else {
+#pragma unroll
+        for (int j0 = 0; j0 < P * P; j0 += G) {
+            const int j = j0 + g;
+            if (j < P * P) clear_cell<P>(tb, planes + (j / P) * view_stride, sel<P>(oldpos, j % P));
+        }
+    }
+}
+
+template <int P, int G>
+OCB_HD void obs_phase2(const Tables& tb, uint8_t* planes, int view_stride, const uint16_t* objs, int ostride,
+                       bool full, int g, const World<P>& w, const int (&dirty)[P]) {
+    if (full) {
+        for (int idx = g; idx < tb.n_objcells; idx += G) {
+            const int cell = tb.objcells[idx];
+            const uint32_t o = objs[cell * ostride];
+            if (o != 0u)
+                for (int v = 0; v < P; ++v) encode_cell<P>(tb, planes + v * view_stride, cell, o);
+        }
+    } else {
+        const int n = (P + tb.n_pots) * P;  // (interact targets + pots) x views
+        for (int j = g; j < n; j += G) {
+            const int v = j % P, d = j / P;
+            const int cell = (d < P) ? sel<P>(dirty, d) : (int)tb.pot_cells[d - P];
+            if (cell >= 0) encode_cell<P>(tb, planes + v * view_stride, cell, objs[cell * ostride]);
+        }
+    }
+#pragma unroll
+    for (int j0 = 0; j0 < P * P; j0 += G) {
+        const int j = j0 + g;
+        if (j < P * P) {
+            const int v = j / P, i = j % P;
+            poke_player<P>(tb, planes + v * view_stride, v, i, sel<P>(w.pos, i), sel<P>(w.orient, i), selu<P>(w.held, i));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- action RNG
+// Philox4x32-10 (Salmon et al., SC'11), counter = (world, block_lo, block_hi, 0),
+// key = (seed_lo, seed_hi).  One block serves 8/P_pad consecutive steps.
+OCB_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+OCB_HD void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0, c[1] = lo1, c[2] = n2, c[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+template <int P>
+struct ActionRng {
+    static constexpr int kPad = P <= 2 ? 2 : 4;
+    static constexpr int kStepsPerBlock = 8 / kPad;
+    uint32_t r[4];
+    OCB_HDM void refill(uint64_t seed, uint32_t world, uint64_t step) {
+        const uint64_t block = step / kStepsPerBlock;
+        r[0] = world, r[1] = (uint32_t)block, r[2] = (uint32_t)(block >> 32), r[3] = 0u;
+        philox4x32_10(r, (uint32_t)seed, (uint32_t)(seed >> 32));
+    }
+    // 16-bit slice number sub*kPad + player, mapped to 0..num_actions-1
+    OCB_HDM int action(uint64_t step, int player, int num_actions) const {
+        const int h = (int)(step % kStepsPerBlock) * kPad + player;
+        const int wsel = h >> 1;
+        const uint32_t word = wsel == 0 ? r[0] : wsel == 1 ? r[1] : wsel == 2 ? r[2] : r[3];
+        const uint32_t half = (h & 1) ? (word >> 16) : (word & 0xFFFFu);
+        return (int)((half * (uint32_t)num_actions) >> 16);
+    }
+};
+
+}  // namespace ocb

@@ -1,0 +1,442 @@
+// oc_kernels.cu — sm_100a kernels of the batched Overcooked simulator.
+//
+// oc_rollout_kernel<P,G>: K fused environment steps per launch.
+//   * a warp owns a tile of WPW = 32/G consecutive worlds for the whole launch;
+//     every world is served by G lanes that execute the (sequential, branchy)
+//     transition redundantly in registers and split the observation byte pokes;
+//   * world state lives in registers (players) and shared memory (cell objects)
+//     for all K steps; HBM is touched only for the mandatory I/O:
+//     actions in, observation planes / reward / done out;
+//   * each tile keeps its P x WPW observation planes resident in shared memory,
+//     laid out exactly like the [P, N, W, H, C] output so that one view of the
+//     tile is one contiguous run of WPW*S*C bytes in HBM.  After the few bytes
+//     touched by a transition are rewritten the run is streamed out either with
+//     16-byte coalesced streaming stores or with one TMA bulk copy
+//     (cp.async.bulk.global.shared::cta) per view.
+// See DESIGN.md for the byte accounting and the roofline.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "oc_core.cuh"
+#include "oc_kernels.h"
+
+namespace ocb {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+__device__ __forceinline__ int load_action(const void* a, int dtype, size_t idx) {
+    int v;
+    switch (dtype) {
+        case OCB_ACT_I64: v = (int)static_cast<const long long*>(a)[idx]; break;
+        case OCB_ACT_F32: v = (int)static_cast<const float*>(a)[idx]; break;
+        case OCB_ACT_U8: v = (int)static_cast<const uint8_t*>(a)[idx]; break;
+        default: v = static_cast<const int*>(a)[idx]; break;
+    }
+    return (v >= 0 && v <= 5) ? v : A_STAY;
+}
+
+// streams `nbytes` of shared memory to global memory with the widest aligned stores
+__device__ __forceinline__ void warp_copy_out(int8_t* __restrict__ dst, const uint8_t* __restrict__ src, int nbytes,
+                                              int lane) {
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        const int n16 = nbytes >> 4;
+        const uint4* s16 = reinterpret_cast<const uint4*>(src);
+        uint4* d16 = reinterpret_cast<uint4*>(dst);
+        for (int c = lane; c < n16; c += 32) __stcs(d16 + c, s16[c]);
+        for (int b = (n16 << 4) + lane; b < nbytes; b += 32) dst[b] = (int8_t)src[b];
+    } else if ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
+        const int n4 = nbytes >> 2;
+        const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src);
+        uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
+        for (int c = lane; c < n4; c += 32) __stcs(d4 + c, s4[c]);
+        for (int b = (n4 << 2) + lane; b < nbytes; b += 32) dst[b] = (int8_t)src[b];
+    } else {
+        for (int b = lane; b < nbytes; b += 32) dst[b] = (int8_t)src[b];
+    }
+}
+
+template <int P, int G>
+__global__ void __launch_bounds__(kThreadsPerCta) oc_rollout_kernel(const RolloutParams prm) {
+    constexpr int WPW = 32 / G;
+    extern __shared__ __align__(16) uint8_t smem[];
+
+    // ---- stage the static tables and the observation template
+    Tables& tb = *reinterpret_cast<Tables*>(smem);
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int SC = tb.SC, S = tb.S;
+    uint8_t* tmpl = smem + align16(sizeof(Tables));
+    for (int i = threadIdx.x; i < SC; i += blockDim.x) tmpl[i] = prm.tmpl[i];
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wi = lane / G, g = lane % G;
+    const int view_stride = align16(WPW * SC);  // one view of the tile
+    const size_t warp_bytes = (size_t)P * view_stride + align16(S * WPW * 2);
+    uint8_t* wbase = smem + align16(sizeof(Tables)) + align16(SC) + warp * warp_bytes;
+    uint8_t* planes = wbase;                                                       // [P][WPW][SC]
+    uint16_t* objs = reinterpret_cast<uint16_t*>(wbase + (size_t)P * view_stride);  // [S][WPW]
+    uint16_t* myobjs = objs + wi;
+    uint8_t* myplanes = planes + wi * SC;  // + v*view_stride
+
+    const int N = prm.N;
+    const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int n0 = tile * WPW;
+    if (n0 >= N) return;  // whole warp idle (no block-level sync below)
+    const int nvalid = min(WPW, N - n0);
+    const int n = n0 + wi;
+    const bool valid = n < N;
+    const int nl = valid ? n : N - 1;
+
+    // ---- load world state: HBM -> registers / shared memory
+    World<P> w;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const uint32_t pw = prm.players[(size_t)i * N + nl];
+        w.pos[i] = (int)(pw & 0xFFFu);
+        w.orient[i] = (int)((pw >> 12) & 3u);
+        w.held[i] = pw >> 16;
+    }
+    w.timestep = prm.timestep[nl];
+    for (int c = g; c < S; c += G) myobjs[c * WPW] = prm.objs[(size_t)c * N + nl];
+    __syncwarp();
+    {
+        int cd = 0;
+        for (int idx = g; idx < tb.n_objcells; idx += G) {
+            const int cell = tb.objcells[idx];
+            cd += (tb.terrain[cell] == T_COUNTER && obj_name(myobjs[cell * WPW]) == O_DISH);
+        }
+#pragma unroll
+        for (int m = 1; m < G; m <<= 1) cd += __shfl_xor_sync(0xffffffffu, cd, m);
+        w.counter_dishes = cd;
+    }
+    int cur_return = prm.cur_return[nl];
+    long long ret_add = 0;
+    int ep_add = 0;
+
+    const bool use_rng = prm.actions == nullptr;
+    const bool want_obs = prm.obs != nullptr;
+    ActionRng<P> rng;
+    unsigned long long t = prm.step0;
+    if (use_rng && (t % ActionRng<P>::kStepsPerBlock) != 0) rng.refill(prm.seed, (uint32_t)(prm.world0 + nl), t);
+    bool tma_pending = false;
+
+    for (int k = 0; k < prm.K; ++k, ++t) {
+        // ---- joint action
+        int act[P];
+        if (use_rng) {
+            if ((t % ActionRng<P>::kStepsPerBlock) == 0) rng.refill(prm.seed, (uint32_t)(prm.world0 + nl), t);
+#pragma unroll
+            for (int i = 0; i < P; ++i) act[i] = rng.action(t, i, 6);
+        } else {
+#pragma unroll
+            for (int i = 0; i < P; ++i) act[i] = load_action(prm.actions, prm.act_dtype, ((size_t)k * P + i) * N + nl);
+        }
+        if (prm.actions_out != nullptr && valid) {
+#pragma unroll
+            for (int i = 0; i < P; ++i)
+                if (i % G == g) prm.actions_out[((size_t)k * P + i) * N + n] = (uint8_t)act[i];
+        }
+
+        // ---- transition (registers + shared memory only)
+        int oldpos[P], dirty[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) oldpos[i] = w.pos[i];
+        const int r = step_world<P>(tb, w, myobjs, WPW, act, dirty);
+        const bool done = w.timestep >= tb.horizon;  // envs/overcooked2_env.py:334
+        cur_return += r;
+        if (done) {  // auto-reset, pantheonrl_extension/vectorenv.py:369-370
+            ret_add += cur_return;
+            ep_add += 1;
+            cur_return = 0;
+            reset_world<P>(tb, w);
+            for (int idx = g; idx < tb.n_objcells; idx += G) myobjs[(int)tb.objcells[idx] * WPW] = 0;
+        }
+        __syncwarp();  // cleared cells are read by the sibling lanes of the world
+        if (valid) {
+            if (prm.rew != nullptr) {
+#pragma unroll
+                for (int i = 0; i < P; ++i)
+                    if (i % G == g) prm.rew[((size_t)k * P + i) * N + n] = r;
+            }
+            if (prm.done != nullptr && g == G - 1) prm.done[(size_t)k * N + n] = done ? 1 : 0;
+        }
+
+        // ---- observation planes: rewrite touched bytes, stream the tile out
+        if (want_obs) {
+            const bool full = (k == 0) || done;
+            if (tma_pending) {  // the previous bulk copy must have finished reading the planes
+                if (lane == 0) bulk_wait_read_all();
+                tma_pending = false;
+            }
+            __syncwarp();
+            obs_phase1<P, G>(tb, myplanes, view_stride, tmpl, full, g, oldpos);
+            __syncwarp();
+            obs_phase2<P, G>(tb, myplanes, view_stride, myobjs, WPW, full, g, w, dirty);
+            const int nbytes = nvalid * SC;
+            int8_t* dst0 = prm.obs + (((size_t)k * P) * N + n0) * SC;
+            const size_t dst_view_stride = (size_t)N * SC;
+            const bool tma_ok = prm.use_tma && ((nbytes & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst0) & 15u) == 0) &&
+                                ((dst_view_stride & 15u) == 0);
+            if (tma_ok) {
+                fence_proxy_async_smem();  // generic-proxy pokes -> visible to the async proxy
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int v = 0; v < P; ++v)
+                        bulk_store_s2g(dst0 + v * dst_view_stride, planes + v * view_stride, (uint32_t)nbytes);
+                    bulk_commit();
+                }
+                tma_pending = true;
+            } else {
+                __syncwarp();
+#pragma unroll
+                for (int v = 0; v < P; ++v) warp_copy_out(dst0 + v * dst_view_stride, planes + v * view_stride, nbytes, lane);
+            }
+        }
+    }
+    if (tma_pending && lane == 0) bulk_wait_read_all();
+
+    // ---- store world state back
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < P; ++i)
+            if (i % G == g) prm.players[(size_t)i * N + n] = player_pack(w.pos[i], w.orient[i], w.held[i]);
+        for (int c = g; c < S; c += G) prm.objs[(size_t)c * N + n] = myobjs[c * WPW];
+        if (g == 0) {
+            prm.timestep[n] = w.timestep;
+            prm.cur_return[n] = cur_return;
+            if (ep_add) {
+                prm.ret_sum[n] += ret_add;
+                prm.episodes[n] += ep_add;
+            }
+        }
+    }
+}
+
+// observation of the current state (no step): full rebuild + stream out
+template <int P, int G>
+__global__ void __launch_bounds__(kThreadsPerCta) oc_observe_kernel(const RolloutParams prm) {
+    constexpr int WPW = 32 / G;
+    extern __shared__ __align__(16) uint8_t smem[];
+    Tables& tb = *reinterpret_cast<Tables*>(smem);
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int SC = tb.SC, S = tb.S;
+    uint8_t* tmpl = smem + align16(sizeof(Tables));
+    for (int i = threadIdx.x; i < SC; i += blockDim.x) tmpl[i] = prm.tmpl[i];
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wi = lane / G, g = lane % G;
+    const int view_stride = align16(WPW * SC);
+    const size_t warp_bytes = (size_t)P * view_stride + align16(S * WPW * 2);
+    uint8_t* wbase = smem + align16(sizeof(Tables)) + align16(SC) + warp * warp_bytes;
+    uint8_t* planes = wbase;
+    uint16_t* myobjs = reinterpret_cast<uint16_t*>(wbase + (size_t)P * view_stride) + wi;
+    uint8_t* myplanes = planes + wi * SC;
+
+    const int N = prm.N;
+    const int n0 = (blockIdx.x * (blockDim.x >> 5) + warp) * WPW;
+    if (n0 >= N) return;
+    const int nvalid = min(WPW, N - n0);
+    const int nl = min(n0 + wi, N - 1);
+
+    World<P> w;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const uint32_t pw = prm.players[(size_t)i * N + nl];
+        w.pos[i] = (int)(pw & 0xFFFu);
+        w.orient[i] = (int)((pw >> 12) & 3u);
+        w.held[i] = pw >> 16;
+    }
+    w.timestep = 0;
+    w.counter_dishes = 0;
+    for (int c = g; c < S; c += G) myobjs[c * WPW] = prm.objs[(size_t)c * N + nl];
+    int none[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) none[i] = -1;
+    __syncwarp();
+    obs_phase1<P, G>(tb, myplanes, view_stride, tmpl, true, g, none);
+    __syncwarp();
+    obs_phase2<P, G>(tb, myplanes, view_stride, myobjs, WPW, true, g, w, none);
+    __syncwarp();
+    const int nbytes = nvalid * SC;
+#pragma unroll
+    for (int v = 0; v < P; ++v)
+        warp_copy_out(prm.obs + ((size_t)v * N + n0) * SC, planes + v * view_stride, nbytes, lane);
+}
+
+__global__ void oc_reset_kernel(const Tables* __restrict__ tables, uint32_t* players, uint16_t* objs, int32_t* timestep,
+                                int32_t* cur_return, int N) {
+    const int P = tables->P, S = tables->S;
+    const size_t total = (size_t)N * (size_t)(S > P ? S : P);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int n = (int)(idx % (size_t)N), row = (int)(idx / (size_t)N);
+        if (row < P) players[(size_t)row * N + n] = player_pack(tables->start_pos[row], 0, 0u);
+        if (row < S) objs[(size_t)row * N + n] = 0;
+        if (row == 0) {
+            timestep[n] = 0;
+            cur_return[n] = 0;
+        }
+    }
+}
+
+// packed ABI state (int32 [N, L], include/ocb.h) <-> device structure-of-arrays
+__global__ void oc_export_state_kernel(const Tables* __restrict__ tables, const uint32_t* players, const uint16_t* objs,
+                                       const int32_t* timestep, int32_t* out, int N) {
+    const int P = tables->P, S = tables->S, L = 1 + 6 * P + 4 * S;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        int32_t* row = out + (size_t)n * L;
+        row[0] = timestep[n];
+        for (int i = 0; i < P; ++i) {
+            const uint32_t pw = players[(size_t)i * N + n];
+            const uint32_t h = pw >> 16;
+            int32_t* pl = row + 1 + 6 * i;
+            pl[0] = (int)(pw & 0xFFFu);
+            pl[1] = (int)((pw >> 12) & 3u);
+            pl[2] = obj_name(h);
+            pl[3] = obj_onions(h);
+            pl[4] = obj_tomatoes(h);
+            pl[5] = h ? obj_tickp1(h) - 1 : 0;
+        }
+        for (int c = 0; c < S; ++c) {
+            const uint32_t o = objs[(size_t)c * N + n];
+            int32_t* oc = row + 1 + 6 * P + 4 * c;
+            oc[0] = obj_name(o);
+            oc[1] = obj_onions(o);
+            oc[2] = obj_tomatoes(o);
+            oc[3] = o ? obj_tickp1(o) - 1 : 0;
+        }
+    }
+}
+
+// returns (through *bad) the number of worlds holding a state the CUDA path does not
+// represent: out-of-range fields, objects on cells that cannot hold one, a pot
+// holding anything but a soup, a cooking soup outside a pot, a player off the AIR cells.
+__global__ void oc_import_state_kernel(const Tables* __restrict__ tables, const int32_t* in, uint32_t* players,
+                                       uint16_t* objs, int32_t* timestep, int32_t* cur_return, int N, int* bad) {
+    const int P = tables->P, S = tables->S, L = 1 + 6 * P + 4 * S;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        const int32_t* row = in + (size_t)n * L;
+        bool ok = row[0] >= 0;
+        auto check_obj = [&](const int32_t* o) {
+            if (o[0] == O_NONE) return o[1] == 0 && o[2] == 0 && o[3] == 0;
+            bool g = o[0] >= O_TOMATO && o[0] <= O_SOUP && o[1] >= 0 && o[2] >= 0 && o[1] + o[2] <= 3 && o[3] >= -1 &&
+                     o[3] <= OCB_MAX_COOK_TIME + 1;
+            if (g && o[0] != O_SOUP) g = (o[1] == 0 && o[2] == 0 && o[3] == -1);
+            return g;
+        };
+        for (int i = 0; i < P; ++i) {
+            const int32_t* pl = row + 1 + 6 * i;
+            ok = ok && pl[0] >= 0 && pl[0] < S && pl[1] >= 0 && pl[1] <= 3 && check_obj(pl + 2);
+            if (ok) ok = tables->terrain[pl[0]] == T_AIR;
+            if (ok) {
+                const uint32_t h = pl[2] ? obj_make(pl[2], pl[3], pl[4], pl[5]) : 0u;
+                players[(size_t)i * N + n] = player_pack(pl[0], pl[1], h);
+            }
+        }
+        for (int c = 0; c < S; ++c) {
+            const int32_t* oc = row + 1 + 6 * P + 4 * c;
+            ok = ok && check_obj(oc);
+            uint32_t o = 0u;
+            if (ok && oc[0] != O_NONE) {
+                const int t = tables->terrain[c];
+                o = obj_make(oc[0], oc[1], oc[2], oc[3]);
+                ok = (t == T_POT && oc[0] == O_SOUP) || (t == T_COUNTER && !(oc[0] == O_SOUP && soup_cooking(*tables, o)));
+            }
+            objs[(size_t)c * N + n] = (uint16_t)o;
+        }
+        timestep[n] = row[0];
+        cur_return[n] = 0;
+        if (!ok) atomicAdd(bad, 1);
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+template <int P, int G>
+static cudaError_t launch_pg(const RolloutParams& prm, int warps_per_cta, size_t smem_bytes, bool observe_only,
+                             cudaStream_t stream) {
+    constexpr int WPW = 32 / G;
+    const int tiles = (prm.N + WPW - 1) / WPW;
+    const int ctas = (tiles + warps_per_cta - 1) / warps_per_cta;
+    auto kern = observe_only ? oc_observe_kernel<P, G> : oc_rollout_kernel<P, G>;
+    if (smem_bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<ctas, warps_per_cta * 32, smem_bytes, stream>>>(prm);
+    return cudaGetLastError();
+}
+
+size_t rollout_smem_bytes(int P, int S, int C, int G, int warps_per_cta) {
+    const int WPW = 32 / G;
+    const size_t SC = (size_t)S * C;
+    const size_t per_warp = (size_t)P * align16(WPW * SC) + align16(S * WPW * 2);
+    return align16(sizeof(Tables)) + align16(SC) + warps_per_cta * per_warp;
+}
+
+template <int P>
+static cudaError_t launch_p(const RolloutParams& prm, int G, int warps_per_cta, size_t smem_bytes, bool observe_only,
+                            cudaStream_t stream) {
+    switch (G) {
+        case 1: return launch_pg<P, 1>(prm, warps_per_cta, smem_bytes, observe_only, stream);
+        case 2: return launch_pg<P, 2>(prm, warps_per_cta, smem_bytes, observe_only, stream);
+        default: return launch_pg<P, 4>(prm, warps_per_cta, smem_bytes, observe_only, stream);
+    }
+}
+
+cudaError_t launch_rollout(const RolloutParams& prm, int P, int G, int warps_per_cta, size_t smem_bytes,
+                           bool observe_only, cudaStream_t stream) {
+    switch (P) {
+        case 1: return launch_p<1>(prm, G, warps_per_cta, smem_bytes, observe_only, stream);
+        case 2: return launch_p<2>(prm, G, warps_per_cta, smem_bytes, observe_only, stream);
+        case 3: return launch_p<3>(prm, G, warps_per_cta, smem_bytes, observe_only, stream);
+        case 4: return launch_p<4>(prm, G, warps_per_cta, smem_bytes, observe_only, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_reset(const Tables* tables, uint32_t* players, uint16_t* objs, int32_t* timestep, int32_t* cur_return,
+                         int N, int rows, cudaStream_t stream) {
+    const size_t total = (size_t)N * rows;
+    const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    oc_reset_kernel<<<blocks, 256, 0, stream>>>(tables, players, objs, timestep, cur_return, N);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_export_state(const Tables* tables, const uint32_t* players, const uint16_t* objs,
+                                const int32_t* timestep, int32_t* out, int N, cudaStream_t stream) {
+    oc_export_state_kernel<<<(N + 127) / 128, 128, 0, stream>>>(tables, players, objs, timestep, out, N);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_import_state(const Tables* tables, const int32_t* in, uint32_t* players, uint16_t* objs,
+                                int32_t* timestep, int32_t* cur_return, int N, int* bad, cudaStream_t stream) {
+    oc_import_state_kernel<<<(N + 127) / 128, 128, 0, stream>>>(tables, in, players, objs, timestep, cur_return, N, bad);
+    return cudaGetLastError();
+}
+
+}  // namespace ocb

@@ -1,0 +1,390 @@
+// ocb_api.cu — the C ABI of include/ocb.h (Overcooked part).
+// Plain CUDA runtime; no torch, no C++ types in any signature.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "api_common.h"
+#include "oc_core.cuh"
+#include "oc_kernels.h"
+#include "oc_tables.h"
+#include "ocb.h"
+
+using namespace ocb;
+
+namespace ocb {
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+}  // namespace ocb
+
+struct ocb_env {
+    int device;
+    int N, P, S, C, SC, L;
+    uint64_t seed;
+    uint64_t step_count;
+    uint32_t world0;
+    int lanes_per_world;  // G
+    int use_tma;
+    Tables h_tables;
+    // device
+    Tables* d_tables;
+    uint8_t* d_tmpl;
+    uint32_t* d_players;
+    uint16_t* d_objs;
+    int32_t* d_timestep;
+    int32_t* d_cur_return;
+    long long* d_ret_sum;
+    int32_t* d_episodes;
+    // scratch for the host-buffer entry points
+    int32_t* d_h_actions;
+    int8_t* d_h_obs;
+    int32_t* d_h_rew;
+    int32_t* d_h_done;
+    cudaStream_t own_stream;
+};
+
+static int build_tables_or_fail(const ocb_config* cfg, Tables* tb, uint8_t* tmpl) {
+    char msg[400];
+    const int rc = build_tables(cfg, tb, tmpl, msg, sizeof(msg));
+    return rc == OCB_OK ? OCB_OK : fail(rc, "%s", msg);
+}
+
+static int pick_launch_shape(const ocb_env* e, int G, int* warps, size_t* smem) {
+    for (int w = 4; w >= 1; w >>= 1) {
+        const size_t b = rollout_smem_bytes(e->P, e->S, e->C, G, w);
+        if (b <= 200 * 1024) {
+            *warps = w, *smem = b;
+            return OCB_OK;
+        }
+    }
+    return fail(OCB_ERR_UNSUPPORTED, "layout needs more shared memory than one SM has (S=%d, P=%d, lanes_per_world=%d)",
+                e->S, e->P, G);
+}
+
+// ------------------------------------------------------------------ misc
+extern "C" int ocb_abi_version(void) { return OCB_ABI_VERSION; }
+extern "C" const char* ocb_last_error(void) { return g_err; }
+extern "C" int ocb_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OCB_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------ life-cycle
+extern "C" int ocb_destroy(ocb_env* e) {
+    if (e == nullptr) return OCB_OK;
+    DeviceGuard guard(e->device);
+    cudaFree(e->d_tables);
+    cudaFree(e->d_tmpl);
+    cudaFree(e->d_players);
+    cudaFree(e->d_objs);
+    cudaFree(e->d_timestep);
+    cudaFree(e->d_cur_return);
+    cudaFree(e->d_ret_sum);
+    cudaFree(e->d_episodes);
+    cudaFree(e->d_h_actions);
+    cudaFree(e->d_h_obs);
+    cudaFree(e->d_h_rew);
+    cudaFree(e->d_h_done);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+    return OCB_OK;
+}
+
+extern "C" int ocb_create(const ocb_config* cfg, int device, uint32_t num_worlds, uint64_t seed, ocb_env** out) {
+    if (out == nullptr) return fail(OCB_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (num_worlds < 1 || num_worlds > (1u << 30)) return fail(OCB_ERR_INVALID_ARG, "num_worlds out of range");
+    const int ndev = ocb_device_count();
+    if (ndev <= 0) return fail(OCB_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(OCB_ERR_INVALID_ARG, "device %d not in 0..%d", device, ndev - 1);
+
+    ocb_env* e = new (std::nothrow) ocb_env();
+    if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "out of host memory");
+    memset(e, 0, sizeof(*e));
+    uint8_t tmpl[OCB_MAX_CELLS * (5 * OCB_MAX_PLAYERS + 10)];
+    int rc = build_tables_or_fail(cfg, &e->h_tables, tmpl);
+    if (rc != OCB_OK) {
+        delete e;
+        return rc;
+    }
+    e->device = device;
+    e->N = (int)num_worlds;
+    e->P = e->h_tables.P, e->S = e->h_tables.S, e->C = e->h_tables.C, e->SC = e->h_tables.SC;
+    e->L = 1 + 6 * e->P + 4 * e->S;
+    e->seed = seed;
+    e->lanes_per_world = 4;
+    e->use_tma = 0;
+
+    DeviceGuard guard(device);
+    const size_t N = num_worlds;
+#define OCB_TRY(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t err__ = (call);                                                           \
+        if (err__ != cudaSuccess) {                                                           \
+            rc = fail(OCB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(err__));              \
+            cudaGetLastError();                                                               \
+            ocb_destroy(e);                                                                   \
+            return rc;                                                                        \
+        }                                                                                     \
+    } while (0)
+    OCB_TRY(cudaMalloc(&e->d_tables, sizeof(Tables)));
+    OCB_TRY(cudaMalloc(&e->d_tmpl, align16(e->SC)));
+    OCB_TRY(cudaMalloc(&e->d_players, sizeof(uint32_t) * e->P * N));
+    OCB_TRY(cudaMalloc(&e->d_objs, sizeof(uint16_t) * e->S * N));
+    OCB_TRY(cudaMalloc(&e->d_timestep, sizeof(int32_t) * N));
+    OCB_TRY(cudaMalloc(&e->d_cur_return, sizeof(int32_t) * N));
+    OCB_TRY(cudaMalloc(&e->d_ret_sum, sizeof(long long) * N));
+    OCB_TRY(cudaMalloc(&e->d_episodes, sizeof(int32_t) * N));
+    OCB_TRY(cudaMemcpy(e->d_tables, &e->h_tables, sizeof(Tables), cudaMemcpyHostToDevice));
+    OCB_TRY(cudaMemcpy(e->d_tmpl, tmpl, e->SC, cudaMemcpyHostToDevice));
+    OCB_TRY(cudaMemset(e->d_ret_sum, 0, sizeof(long long) * N));
+    OCB_TRY(cudaMemset(e->d_episodes, 0, sizeof(int32_t) * N));
+    OCB_TRY(launch_reset(e->d_tables, e->d_players, e->d_objs, e->d_timestep, e->d_cur_return, e->N,
+                         e->S > e->P ? e->S : e->P, 0));
+    OCB_TRY(cudaDeviceSynchronize());
+#undef OCB_TRY
+    int warps;
+    size_t smem;
+    rc = pick_launch_shape(e, e->lanes_per_world, &warps, &smem);
+    if (rc != OCB_OK) {
+        ocb_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return OCB_OK;
+}
+
+extern "C" int ocb_num_worlds(const ocb_env* e) { return e ? e->N : fail(OCB_ERR_INVALID_ARG, "env is NULL"); }
+extern "C" int ocb_num_players(const ocb_env* e) { return e ? e->P : fail(OCB_ERR_INVALID_ARG, "env is NULL"); }
+extern "C" int ocb_obs_channels(const ocb_env* e) { return e ? e->C : fail(OCB_ERR_INVALID_ARG, "env is NULL"); }
+extern "C" int ocb_obs_bytes_per_agent(const ocb_env* e) { return e ? e->SC : fail(OCB_ERR_INVALID_ARG, "env is NULL"); }
+extern "C" int ocb_state_ints_per_world(const ocb_env* e) { return e ? e->L : fail(OCB_ERR_INVALID_ARG, "env is NULL"); }
+extern "C" uint64_t ocb_step_count(const ocb_env* e) { return e ? e->step_count : 0; }
+
+extern "C" int ocb_set_tuning(ocb_env* e, int lanes_per_world, int use_tma) {
+    if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "env is NULL");
+    if (lanes_per_world == 0) lanes_per_world = 4;
+    if (lanes_per_world != 1 && lanes_per_world != 2 && lanes_per_world != 4)
+        return fail(OCB_ERR_INVALID_ARG, "lanes_per_world must be 1, 2 or 4");
+    int warps;
+    size_t smem;
+    int rc = pick_launch_shape(e, lanes_per_world, &warps, &smem);
+    if (rc != OCB_OK) return rc;
+    e->lanes_per_world = lanes_per_world;
+    e->use_tma = use_tma ? 1 : 0;
+    return OCB_OK;
+}
+
+// world offset used by the action RNG (multi-GPU shards use rank*N); not in the
+// reference API, exported for the sharded rollout driver
+extern "C" int ocb_set_world_offset(ocb_env* e, uint32_t world0) {
+    if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "env is NULL");
+    e->world0 = world0;
+    return OCB_OK;
+}
+
+// ------------------------------------------------------------------ hot path
+static RolloutParams base_params(ocb_env* e) {
+    RolloutParams p;
+    memset(&p, 0, sizeof(p));
+    p.tables = e->d_tables, p.tmpl = e->d_tmpl;
+    p.players = e->d_players, p.objs = e->d_objs, p.timestep = e->d_timestep;
+    p.cur_return = e->d_cur_return, p.ret_sum = e->d_ret_sum, p.episodes = e->d_episodes;
+    p.N = e->N, p.seed = e->seed, p.world0 = e->world0, p.step0 = e->step_count;
+    p.use_tma = e->use_tma;
+    return p;
+}
+
+static int run_rollout(ocb_env* e, int K, const void* actions, int act_dtype, int8_t* obs, int32_t* rew, int32_t* done,
+                       uint8_t* actions_out, bool observe_only, void* stream) {
+    if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "env is NULL");
+    if (K < 0) return fail(OCB_ERR_INVALID_ARG, "K must be >= 0");
+    if (act_dtype < OCB_ACT_I32 || act_dtype > OCB_ACT_U8) return fail(OCB_ERR_INVALID_ARG, "unknown action dtype %d", act_dtype);
+    DeviceGuard guard(e->device);
+    RolloutParams p = base_params(e);
+    p.K = K, p.actions = actions, p.act_dtype = act_dtype, p.actions_out = actions_out;
+    p.obs = obs, p.rew = rew, p.done = done;
+    int warps;
+    size_t smem;
+    int rc = pick_launch_shape(e, e->lanes_per_world, &warps, &smem);
+    if (rc != OCB_OK) return rc;
+    cudaError_t err = launch_rollout(p, e->P, e->lanes_per_world, warps, smem, observe_only, (cudaStream_t)stream);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OCB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
+    }
+    if (!observe_only) e->step_count += (uint64_t)K;
+    return OCB_OK;
+}
+
+extern "C" int ocb_observe(ocb_env* e, int8_t* obs, void* stream) {
+    if (obs == nullptr) return fail(OCB_ERR_INVALID_ARG, "obs is NULL");
+    return run_rollout(e, 0, nullptr, OCB_ACT_I32, obs, nullptr, nullptr, nullptr, true, stream);
+}
+
+extern "C" int ocb_reset(ocb_env* e, int8_t* obs, void* stream) {
+    if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "env is NULL");
+    {
+        DeviceGuard guard(e->device);
+        cudaError_t err = launch_reset(e->d_tables, e->d_players, e->d_objs, e->d_timestep, e->d_cur_return, e->N,
+                                       e->S > e->P ? e->S : e->P, (cudaStream_t)stream);
+        if (err != cudaSuccess) {
+            cudaGetLastError();
+            return fail(OCB_ERR_CUDA, "reset launch failed: %s", cudaGetErrorString(err));
+        }
+    }
+    return obs ? ocb_observe(e, obs, stream) : OCB_OK;
+}
+
+extern "C" int ocb_step_ex(ocb_env* e, const void* actions, int act_dtype, int8_t* obs, int32_t* reward, int32_t* done,
+                           void* stream) {
+    if (actions == nullptr) return fail(OCB_ERR_INVALID_ARG, "actions is NULL");
+    return run_rollout(e, 1, actions, act_dtype, obs, reward, done, nullptr, false, stream);
+}
+
+extern "C" int ocb_step(ocb_env* e, const int32_t* actions, int8_t* obs, int32_t* reward, int32_t* done, void* stream) {
+    return ocb_step_ex(e, actions, OCB_ACT_I32, obs, reward, done, stream);
+}
+
+extern "C" int ocb_rollout_actions(ocb_env* e, int K, const void* actions, int act_dtype, int8_t* obs_slab,
+                                   int32_t* reward, int32_t* done, void* stream) {
+    if (actions == nullptr) return fail(OCB_ERR_INVALID_ARG, "actions is NULL");
+    return run_rollout(e, K, actions, act_dtype, obs_slab, reward, done, nullptr, false, stream);
+}
+
+extern "C" int ocb_rollout_random(ocb_env* e, int K, int8_t* obs_slab, int32_t* reward, int32_t* done,
+                                  uint8_t* actions_out, void* stream) {
+    return run_rollout(e, K, nullptr, OCB_ACT_I32, obs_slab, reward, done, actions_out, false, stream);
+}
+
+extern "C" int ocb_step_host(ocb_env* e, const int32_t* h_actions, int8_t* h_obs, int32_t* h_reward, int32_t* h_done) {
+    if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "env is NULL");
+    if (h_actions == nullptr) return fail(OCB_ERR_INVALID_ARG, "actions is NULL");
+    DeviceGuard guard(e->device);
+    const size_t N = e->N, P = e->P;
+#define OCB_TRY(call)                                                            \
+    do {                                                                         \
+        cudaError_t err__ = (call);                                              \
+        if (err__ != cudaSuccess) {                                              \
+            cudaGetLastError();                                                  \
+            return fail(OCB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(err__)); \
+        }                                                                        \
+    } while (0)
+    if (e->d_h_actions == nullptr) OCB_TRY(cudaMalloc(&e->d_h_actions, sizeof(int32_t) * P * N));
+    if (h_obs && e->d_h_obs == nullptr) OCB_TRY(cudaMalloc(&e->d_h_obs, P * N * (size_t)e->SC));
+    if (h_reward && e->d_h_rew == nullptr) OCB_TRY(cudaMalloc(&e->d_h_rew, sizeof(int32_t) * P * N));
+    if (h_done && e->d_h_done == nullptr) OCB_TRY(cudaMalloc(&e->d_h_done, sizeof(int32_t) * N));
+    cudaStream_t s = 0;  // legacy default stream: ordered after earlier calls on it
+    OCB_TRY(cudaMemcpyAsync(e->d_h_actions, h_actions, sizeof(int32_t) * P * N, cudaMemcpyHostToDevice, s));
+    int rc = ocb_step(e, e->d_h_actions, h_obs ? e->d_h_obs : nullptr, h_reward ? e->d_h_rew : nullptr,
+                      h_done ? e->d_h_done : nullptr, s);
+    if (rc != OCB_OK) return rc;
+    if (h_reward) OCB_TRY(cudaMemcpyAsync(h_reward, e->d_h_rew, sizeof(int32_t) * P * N, cudaMemcpyDeviceToHost, s));
+    if (h_done) OCB_TRY(cudaMemcpyAsync(h_done, e->d_h_done, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, s));
+    if (h_obs) OCB_TRY(cudaMemcpyAsync(h_obs, e->d_h_obs, P * N * (size_t)e->SC, cudaMemcpyDeviceToHost, s));
+    OCB_TRY(cudaStreamSynchronize(s));
+#undef OCB_TRY
+    return OCB_OK;
+}
+
+// ------------------------------------------------------------------ state I/O
+extern "C" int ocb_get_state(ocb_env* e, int32_t* h_state, size_t n_ints) {
+    if (e == nullptr || h_state == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL argument");
+    const size_t need = (size_t)e->N * e->L;
+    if (n_ints != need) return fail(OCB_ERR_INVALID_ARG, "state buffer has %zu ints, expected %zu", n_ints, need);
+    DeviceGuard guard(e->device);
+    int32_t* d = nullptr;
+    cudaError_t err = cudaMalloc(&d, need * sizeof(int32_t));
+    if (err == cudaSuccess) err = cudaDeviceSynchronize();
+    if (err == cudaSuccess) err = launch_export_state(e->d_tables, e->d_players, e->d_objs, e->d_timestep, d, e->N, 0);
+    if (err == cudaSuccess) err = cudaMemcpy(h_state, d, need * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OCB_ERR_CUDA, "get_state: %s", cudaGetErrorString(err));
+    }
+    return OCB_OK;
+}
+
+extern "C" int ocb_set_state(ocb_env* e, const int32_t* h_state, size_t n_ints) {
+    if (e == nullptr || h_state == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL argument");
+    const size_t need = (size_t)e->N * e->L;
+    if (n_ints != need) return fail(OCB_ERR_INVALID_ARG, "state buffer has %zu ints, expected %zu", n_ints, need);
+    DeviceGuard guard(e->device);
+    int32_t* d = nullptr;
+    int* d_bad = nullptr;
+    int bad = 0;
+    // validate into scratch copies first so that a rejected state leaves the env untouched
+    uint32_t* t_players = nullptr;
+    uint16_t* t_objs = nullptr;
+    int32_t *t_time = nullptr, *t_ret = nullptr;
+    const size_t N = e->N;
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err == cudaSuccess) err = cudaMalloc(&d, need * sizeof(int32_t));
+    if (err == cudaSuccess) err = cudaMalloc(&d_bad, sizeof(int));
+    if (err == cudaSuccess) err = cudaMalloc(&t_players, sizeof(uint32_t) * e->P * N);
+    if (err == cudaSuccess) err = cudaMalloc(&t_objs, sizeof(uint16_t) * e->S * N);
+    if (err == cudaSuccess) err = cudaMalloc(&t_time, sizeof(int32_t) * N);
+    if (err == cudaSuccess) err = cudaMalloc(&t_ret, sizeof(int32_t) * N);
+    if (err == cudaSuccess) err = cudaMemset(d_bad, 0, sizeof(int));
+    if (err == cudaSuccess) err = cudaMemcpy(d, h_state, need * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = launch_import_state(e->d_tables, d, t_players, t_objs, t_time, t_ret, e->N, d_bad, 0);
+    if (err == cudaSuccess) err = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
+    if (err == cudaSuccess && bad == 0) {
+        err = cudaMemcpy(e->d_players, t_players, sizeof(uint32_t) * e->P * N, cudaMemcpyDeviceToDevice);
+        if (err == cudaSuccess) err = cudaMemcpy(e->d_objs, t_objs, sizeof(uint16_t) * e->S * N, cudaMemcpyDeviceToDevice);
+        if (err == cudaSuccess) err = cudaMemcpy(e->d_timestep, t_time, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice);
+        if (err == cudaSuccess) err = cudaMemcpy(e->d_cur_return, t_ret, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice);
+    }
+    cudaFree(d), cudaFree(d_bad), cudaFree(t_players), cudaFree(t_objs), cudaFree(t_time), cudaFree(t_ret);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OCB_ERR_CUDA, "set_state: %s", cudaGetErrorString(err));
+    }
+    if (bad) return fail(OCB_ERR_BAD_STATE, "%d world(s) hold a state the simulator cannot represent", bad);
+    return OCB_OK;
+}
+
+extern "C" int ocb_read_episode_stats(ocb_env* e, int64_t* return_sum, int32_t* episodes, void* stream) {
+    if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "env is NULL");
+    DeviceGuard guard(e->device);
+    cudaError_t err = cudaSuccess;
+    if (return_sum)
+        err = cudaMemcpyAsync(return_sum, e->d_ret_sum, sizeof(long long) * (size_t)e->N, cudaMemcpyDeviceToDevice,
+                              (cudaStream_t)stream);
+    if (err == cudaSuccess && episodes)
+        err = cudaMemcpyAsync(episodes, e->d_episodes, sizeof(int32_t) * (size_t)e->N, cudaMemcpyDeviceToDevice,
+                              (cudaStream_t)stream);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OCB_ERR_CUDA, "read_episode_stats: %s", cudaGetErrorString(err));
+    }
+    return OCB_OK;
+}
+
+extern "C" int ocb_clear_episode_stats(ocb_env* e, void* stream) {
+    if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "env is NULL");
+    DeviceGuard guard(e->device);
+    cudaError_t err = cudaMemsetAsync(e->d_ret_sum, 0, sizeof(long long) * (size_t)e->N, (cudaStream_t)stream);
+    if (err == cudaSuccess) err = cudaMemsetAsync(e->d_episodes, 0, sizeof(int32_t) * (size_t)e->N, (cudaStream_t)stream);
+    if (err == cudaSuccess) err = cudaMemsetAsync(e->d_cur_return, 0, sizeof(int32_t) * (size_t)e->N, (cudaStream_t)stream);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OCB_ERR_CUDA, "clear_episode_stats: %s", cudaGetErrorString(err));
+    }
+    return OCB_OK;
+}

@@ -169,6 +169,9 @@ int ocb_clear_episode_stats(ocb_env* env, void* stream);
 
 /* global step counter that indexes the action RNG (incremented by every step) */
 uint64_t ocb_step_count(const ocb_env* env);
+/* index of this handle's world 0 in the global world numbering used by the action RNG
+ * (a multi-GPU shard of rank r with N worlds per rank uses r*N); default 0 */
+int ocb_set_world_offset(ocb_env* env, uint32_t world0);
 
 /* ------------------------------------------------------- Balance-Beam */
 /* replaces BalanceBeamSimulator (src/balance_beam_env/mgr.cpp:191-233) behind

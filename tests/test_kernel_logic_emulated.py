@@ -1,0 +1,68 @@
+"""CPU check of the CUDA kernel's per-lane code (csrc/oc_core.cuh compiled with g++ and
+driven with the kernel's tile / lane-role / phase orchestration, tests/emu/oc_emu.cpp)
+against the oracle.  The real kernel is checked on the GPU in test_gpu_*.py."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from diverse_conventions_b200 import layouts
+from emu.build_emu import lib as emu_lib
+from oracle.c_oracle import COracle, random_actions
+from scripted_agent import ScriptedTeam
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def scripted_actions(lp, N, K, rng, noise=0.25):
+    team = ScriptedTeam(lp, rng, noise=noise)
+    shadow = COracle(lp, N)
+    acts = np.zeros((K, lp.num_players, N), np.uint8)
+    for k in range(K):
+        for n in range(N):
+            acts[k, :, n] = team.joint(shadow.state[n])
+        shadow.step(acts[k])
+    return acts
+
+
+@pytest.mark.parametrize("name", ["simple", "random0", "random1", "random3", "unident_s", "simple_tomato",
+                                  "multiplayer_schelling", "simple_single", "corridor"])
+@pytest.mark.parametrize("G", [1, 2, 4])
+def test_emulated_kernel_matches_oracle(name, G):
+    rng = np.random.default_rng(hash((name, G)) % 2**32)
+    lp = layouts.load_layout(name, 50)
+    P, N, K = lp.num_players, 11, 130
+    acts = scripted_actions(lp, N, K, rng)
+    orc = COracle(lp, N)
+    obs_ref, rew_ref, done_ref = orc.rollout(acts)
+    st = COracle(lp, N).state.copy()
+    k0, parts = 0, []
+    for kk in (1, 52, K - 53):  # several launches: state is stored / reloaded in between
+        obs = np.zeros((kk, P, N, lp.width, lp.height, lp.channels), np.int8)
+        rew = np.zeros((kk, P, N), np.int32)
+        done = np.zeros((kk, N), np.int32)
+        rc = emu_lib().ocemu_rollout(ctypes.byref(orc.cfg), G, _p(st), N, kk, _p(np.ascontiguousarray(acts[k0:k0 + kk])),
+                                     0, k0, 0, _p(obs), _p(rew), _p(done), None)
+        assert rc == 0
+        parts.append((obs, rew, done))
+        k0 += kk
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), rew_ref)
+    assert np.array_equal(np.concatenate([p[2] for p in parts]), done_ref)
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), obs_ref)
+    assert np.array_equal(st, orc.state)
+    assert rew_ref.sum() > 0 and done_ref.sum() == 2 * N
+
+
+def test_emulated_rng_stream_matches_oracle_stream():
+    lp = layouts.load_layout("simple", 400)
+    N, K = 40, 37
+    orc = COracle(lp, N)
+    st = orc.state.copy()
+    ao = np.zeros((K, 2, N), np.uint8)
+    obs = np.zeros((K, 2, N, 5, 4, 20), np.int8)
+    emu_lib().ocemu_rollout(ctypes.byref(orc.cfg), 4, _p(st), N, K, None, 77, 5, 100, _p(obs), None, None, _p(ao))
+    assert np.array_equal(ao, random_actions(77, 100, N, 5, K, 2))
+    o, _, _ = orc.rollout(ao)
+    assert np.array_equal(o, obs)
