@@ -8,12 +8,13 @@ Workload (BASELINE.json configs[2], the one the metric's target is quoted on):
 Overcooked cramped_room, 2 agents, horizon 400, 16,384 worlds per GPU, uniform random
 actions drawn on the device, env step + observation encode only.
 
-A "step" is one environment step of every world of the job.  The device-timed `value`
-runs `--steps` steps as fused launches of `--steps-per-launch` steps each
-(ocb_rollout_random); every launch writes a [spl, P, N, W, H, C] observation slab
-(1.3 GB at the defaults, >> the 126 MB L2, so no flush is needed between launches).
+A bench "step" is one pass of the hot path over one batch: ONE fused launch
+(ocb_rollout_random) that advances every world of the job by `--env-steps-per-pass`
+(default 100) environment steps and writes the [T, P, N, W, H, C] observation slab
+(1.3 GB per GPU at the defaults, >> the 126 MB L2, so no flush is needed between
+passes).  `value` = agent-steps (P x worlds x env steps) per second over all GPUs.
 `e2e` runs the reference-facing single-step call with HOST buffers (ocb_step_host:
-pinned actions H2D, kernel, obs + rewards + dones D2H, sync) — one launch per step.
+pinned actions H2D, kernel, obs + rewards + dones D2H, sync), T calls per pass.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -38,15 +39,15 @@ UNIT = "agent-steps/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20000)
-    ap.add_argument("--warmup", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=3000, help="timed passes (fused launches)")
+    ap.add_argument("--warmup", type=int, default=30, help="untimed warm-up passes")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--steps-per-launch", type=int, default=100)
+    ap.add_argument("--env-steps-per-pass", type=int, default=100)
     ap.add_argument("--worlds", type=int, default=WORLDS_PER_GPU)
     ap.add_argument("--layout", default=LAYOUT)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per world (kernel tuning), 0 = library default")
     ap.add_argument("--tma", type=int, default=-1, help="1/0 force the TMA bulk-store path, -1 = library default")
-    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--e2e-passes", type=int, default=3, help="passes of the host-buffer e2e measurement (<= --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -56,7 +57,8 @@ def workload_config(args, n_gpus):
     return {"workload": "overcooked cramped_room (simple.layout), 2 agents, horizon %d, %d worlds/GPU, "
                         "random actions, env step + obs encode" % (HORIZON, args.worlds),
             "layout": args.layout, "worlds_per_gpu": args.worlds, "n_worlds": args.worlds * n_gpus,
-            "horizon": HORIZON, "steps_per_launch": args.steps_per_launch,
+            "horizon": HORIZON, "env_steps_per_pass": args.env_steps_per_pass,
+            "step_definition": "1 bench step = 1 fused launch = %d env steps of every world" % args.env_steps_per_pass,
             "l2_policy": "outputs larger than L2 (obs slab per launch >> 126 MB); no flush needed",
             "parallelism": "worlds sharded, %d per GPU, no data-path collective" % args.worlds}
 
@@ -131,16 +133,18 @@ def run_reference_arm(args):
     c_oracle.build()
     cores = host_cores()
     t0 = time.perf_counter()
-    steps = max(args.steps, 1)
-    # warm-up: a short run of the same worker (process pool start, imports)
+    # a pass of the CPU arm = env_steps_per_pass env steps over a bounded sample of worlds; the
+    # number of passes is capped so that the whole run stays within ~20 s of CPU work
+    env_steps = args.env_steps_per_pass * max(min(args.steps, 4), 1)
+    # warm-up: a short run of the same worker (imports, allocator)
     _py_port_worker((args.layout, HORIZON, 2, max(min(args.warmup, 50), 3), 1))
-    value, n_worlds, steps_done = cpu_port_throughput(args.layout, min(steps, 2000), 20.0, cores)
+    value, n_worlds, steps_done = cpu_port_throughput(args.layout, env_steps, 20.0, cores)
     c_value = c_port_throughput(args.layout, 3.0, cores)
     cfg = workload_config(args, args.gpus)
     sample = "%d worlds x %d steps over %d processes (python port of the reference env, 1 process per core)" % (
         n_worlds, steps_done, cores)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 2 * n_worlds / value,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * 2 * n_worlds * args.env_steps_per_pass / value,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": cfg,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
@@ -211,7 +215,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    N, K, W, spl = args.worlds, args.steps, args.warmup, args.steps_per_launch
+    N, K, W, spl = args.worlds, args.steps, args.warmup, args.env_steps_per_pass
     lp = layouts.load_layout(args.layout, HORIZON)
     P = lp.num_players
     env = B200Overcooked(args.layout, N, local, horizon=HORIZON, seed=0, world_offset=rank * N)
@@ -220,20 +224,17 @@ def run_ours(args):
     out = env.alloc_rollout(spl, obs=True, actions=False)
     bytes_ws = layouts.io_bytes_per_world_step(lp)
 
-    def run_steps(n_steps, events=None):
-        launches, done_steps = 0, 0
-        while done_steps < n_steps:
-            k = min(spl, n_steps - done_steps)
-            if events is not None:
+    def run_passes(n_passes, events=None):
+        for i in range(n_passes):
+            timed = events is not None and (i % 16 == 0)  # sample per-launch durations without flooding events
+            if timed:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            env.rollout_random(k, out)
-            if events is not None:
+            env.rollout_random(spl, out)
+            if timed:
                 e1.record()
-                events.append((k, e0, e1))
-            done_steps += k
-            launches += 1
-        return launches
+                events.append((e0, e1))
+        return n_passes
 
     def barrier():
         torch.cuda.synchronize()
@@ -241,14 +242,14 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    run_steps(max(W, 3))
+    run_passes(max(W, 3))
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     t_begin = time.perf_counter()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     events = []
     start.record()
-    launches = run_steps(K, events)
+    launches = run_passes(K, events)
     stop.record()
     barrier()
     t_end = time.perf_counter()
@@ -257,12 +258,11 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    value = P * N * world * K / (ms_total * 1e-3)
+    value = P * N * world * K * spl / (ms_total * 1e-3)
 
-    # per-launch duration of the dominant kernel (full launches only) -> roofline
-    full = [e0.elapsed_time(e1) for k, e0, e1 in events if k == spl]
-    launch_ms = statistics.mean(full) if full else ms_total / max(launches, 1)
-    k_launch = spl if full else K
+    # average launch duration of the dominant kernel, CUDA events on the launching stream -> roofline
+    launch_ms = statistics.mean(e0.elapsed_time(e1) for e0, e1 in events)
+    k_launch = spl
     achieved = bytes_ws * N * k_launch / (launch_ms * 1e-3) / 1e9
     peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
@@ -273,7 +273,7 @@ def run_ours(args):
         pass
 
     # end-to-end: the reference-facing single-step call with host buffers
-    E = max(args.e2e_steps, 1)
+    E = max(min(args.e2e_passes, K), 1) * spl  # single-step calls
     h_act = torch.randint(0, 6, (P, N), dtype=torch.int32).pin_memory()
     h_obs = torch.empty((P, N, lp.width, lp.height, lp.channels), dtype=torch.int8).pin_memory()
     h_rew = torch.empty((P, N), dtype=torch.int32).pin_memory()
@@ -308,8 +308,9 @@ def run_ours(args):
                              "launch_ms": launch_ms, "peak_source": peak_src},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "call": "ocb_step_host (1 launch / step, obs+reward+done to pinned host memory)",
-                        "steps": E, "value_without_obs_d2h_rank0": e2e_noobs},
-                "gpu_launches": launches, "clocks": clocks}
+                        "calls": E, "value_without_obs_d2h_rank0": e2e_noobs},
+                "gpu_launches": launches, "clocks": clocks,
+                "env_steps": K * spl, "us_per_env_step": 1e3 * ms_total / (K * spl)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 from oracle import c_oracle

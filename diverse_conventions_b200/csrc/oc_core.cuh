@@ -6,8 +6,10 @@
 // Semantics follow the reference's Python MDP (envs/overcooked2_reimplement.py,
 // "R:" below) — not its Madrona ECS systems.  The design differs from both:
 //   * world state is packed: one 32-bit word per player, one 16-bit word per cell;
-//   * the pot / dish bookkeeping needed by the shaped reward is kept incrementally
-//     (dishes lying on counters) instead of re-scanning the grid;
+//   * everything the shaped reward needs (dishes lying on counters, non-empty pots) is
+//     kept incrementally in registers instead of re-scanning the grid every step;
+//   * one table word per cell (terrain | plane offset | cell index) serves the
+//     transition and the encoder, so a step costs a handful of shared-memory loads;
 //   * the observation is not re-encoded from scratch: each world keeps its
 //     (W,H,C) planes resident in shared memory and only the bytes touched by the
 //     transition are rewritten before the planes are streamed out.
@@ -35,20 +37,47 @@ enum : int { T_AIR = 0, T_POT = 1, T_COUNTER = 2, T_ONION_SRC = 3, T_DISH_SRC = 
 enum : int { O_NONE = 0, O_TOMATO = 1, O_ONION = 2, O_DISH = 3, O_SOUP = 4 };
 enum : int { A_NORTH = 0, A_SOUTH = 1, A_EAST = 2, A_WEST = 3, A_STAY = 4, A_INTERACT = 5 };
 
-// Static per-layout tables, built on the host (ocb_api.cu: build_tables) and staged
+// cell info word: bits 0-2 terrain | 3-15 byte offset of the cell inside a (W,H,C)
+// plane, (x*H+y)*C | 16-23 cell index (pos = y*W+x)
+OCB_HD uint32_t info_make(int terrain, int slot, int cell) {
+    return (uint32_t)terrain | ((uint32_t)slot << 3) | ((uint32_t)cell << 16);
+}
+OCB_HD int info_terrain(uint32_t ci) { return (int)(ci & 7u); }
+OCB_HD int info_slot(uint32_t ci) { return (int)((ci >> 3) & 0x1FFFu); }
+OCB_HD int info_cell(uint32_t ci) { return (int)(ci >> 16); }
+
+// Static per-layout tables, built on the host (oc_tables.h: build_tables) and staged
 // into shared memory by every CTA.
 struct alignas(16) Tables {
-    int32_t W, H, S, P, C, SC; // SC = S*C bytes of one agent's observation
+    int32_t W, H, S, P, C, SC;  // SC = S*C bytes of one agent's observation
     int32_t horizon, n_pots, n_objcells;
     int32_t rew_place, rew_dish, rew_soup;
+    int32_t uniform_time;  // cook time if all 16 recipes share it, else -1
+    uint32_t dpack;        // int8 deltas of NORTH,SOUTH,EAST,WEST packed in one word
     int32_t start_pos[kMaxPlayers];
     int32_t rvalue[OCB_NUM_RECIPES];
     uint8_t rtime[OCB_NUM_RECIPES];
-    uint8_t terrain[kMaxCells];
-    uint16_t slot_off[kMaxCells];  // byte offset of a cell inside a (W,H,C) plane: (x*H+y)*C
-    uint16_t pot_cells[kMaxPots];  // cells with POT terrain
-    uint16_t objcells[kMaxCells];  // cells that can hold an object: counters, then pots
+    uint32_t cell_info[kMaxCells];  // indexed by pos
+    uint32_t pot_info[kMaxPots];    // info words of the POT cells
+    uint16_t objcells[kMaxCells];   // cells that can hold an object: counters, then pots
 };
+
+// per-thread copies of the scalars the step needs (registers; shared-memory reads
+// cannot be cached by the compiler across the warp barriers of the rollout loop)
+struct Consts {
+    int W, n_pots, n_objcells, horizon;
+    int rew_place, rew_dish, rew_soup;
+    int utime;
+    uint32_t dpack, pot0, pot1;
+};
+OCB_HD Consts load_consts(const Tables& tb) {
+    Consts c;
+    c.W = tb.W, c.n_pots = tb.n_pots, c.n_objcells = tb.n_objcells, c.horizon = tb.horizon;
+    c.rew_place = tb.rew_place, c.rew_dish = tb.rew_dish, c.rew_soup = tb.rew_soup;
+    c.utime = tb.uniform_time, c.dpack = tb.dpack;
+    c.pot0 = tb.pot_info[0], c.pot1 = tb.pot_info[1];
+    return c;
+}
 
 // ---------------------------------------------------------------- packed objects
 // bits 0-2 name | 3-4 tomatoes | 5-6 onions | 8-15 cooking_tick+1 ; NONE == 0.
@@ -62,6 +91,8 @@ OCB_HD int obj_onions(uint32_t o) { return (int)((o >> 5) & 3u); }
 OCB_HD int obj_recipe(uint32_t o) { return (int)((o >> 3) & 15u); }
 OCB_HD int obj_tickp1(uint32_t o) { return (int)((o >> 8) & 0xFFu); }
 OCB_HD int obj_ingredients(uint32_t o) { return obj_onions(o) + obj_tomatoes(o); }
+// a pot counts as non-empty for the dish-pickup shaping (get_pot_states, R:272-281)
+OCB_HD int pot_counts(uint32_t o) { return (o != 0u && (obj_tickp1(o) >= 1 || obj_ingredients(o) < 3)) ? 1 : 0; }
 
 // player word: bits 0-11 pos | 12-13 orientation | 16-31 held object
 OCB_HD uint32_t player_pack(int pos, int orient, uint32_t held) {
@@ -71,10 +102,12 @@ OCB_HD uint32_t player_pack(int pos, int orient, uint32_t held) {
 template <int P>
 struct World {
     int pos[P];
+    int slot[P];  // plane byte offset of the cell the player stands on
     int orient[P];
     uint32_t held[P];
     int timestep;
-    int counter_dishes;  // number of DISH objects lying on COUNTER cells
+    int counter_dishes;  // DISH objects lying on COUNTER cells
+    int nonempty_pots;   // pots counted by pot_counts()
 };
 
 template <int P>
@@ -92,114 +125,116 @@ OCB_HD uint32_t selu(const uint32_t (&a)[P], int idx) {
     return r;
 }
 
-OCB_HD int dir_delta(int d, int W) {  // R:22-32
-    return d == A_NORTH ? -W : d == A_SOUTH ? W : d == A_EAST ? 1 : d == A_WEST ? -1 : 0;
+// move_in_direction, R:22-32, branch-free: signed byte d of dpack, 0 for STAY / INTERACT
+OCB_HD int dir_delta(int d, uint32_t dpack) {
+    const int v = (int)(int8_t)(dpack >> ((d & 3) << 3));
+    return d < A_STAY ? v : 0;
 }
 
-// is_cooking / is_ready, R:159-163 (tick = tickp1-1, time = rtime[recipe])
-OCB_HD bool soup_cooking(const Tables& tb, uint32_t o) {
-    const int tp1 = obj_tickp1(o);
-    return tp1 >= 1 && tp1 <= (int)tb.rtime[obj_recipe(o)];
+OCB_HD int cook_time(const Tables& tb, const Consts& c, uint32_t o) {
+    return c.utime >= 0 ? c.utime : (int)tb.rtime[obj_recipe(o)];
 }
-OCB_HD bool soup_ready(const Tables& tb, uint32_t o) {
+// is_cooking / is_ready, R:159-163 (tick = tickp1-1)
+OCB_HD bool soup_cooking(const Tables& tb, const Consts& c, uint32_t o) {
     const int tp1 = obj_tickp1(o);
-    return tp1 >= 1 && tp1 > (int)tb.rtime[obj_recipe(o)];
+    return tp1 >= 1 && tp1 <= cook_time(tb, c, o);
+}
+OCB_HD bool soup_ready(const Tables& tb, const Consts& c, uint32_t o) {
+    const int tp1 = obj_tickp1(o);
+    return tp1 >= 1 && tp1 > cook_time(tb, c, o);
+}
+
+OCB_HD void tick_pot(const Tables& tb, const Consts& c, uint16_t* objs, int ostride, uint32_t pot_info) {
+    const int cell = info_cell(pot_info);
+    const uint32_t o = objs[cell * ostride];
+    if (obj_name(o) == O_SOUP && soup_cooking(tb, c, o)) objs[cell * ostride] = (uint16_t)(o + 0x100u);
 }
 
 // One world transition (R:381-385): resolve_interacts -> resolve_movement ->
 // step_environment_effects.  `objs[cell*ostride]` is this world's object on `cell`.
-// dirty[i] receives the counter / pot cell touched by player i's interact (or -1).
-// Returns the team reward (sum over players; envs/overcooked2_env.py:336).
+// dirty[i] receives the info word of the counter / pot cell touched by player i's
+// interact (or 0xFFFFFFFF).  Returns the team reward (sum over players;
+// envs/overcooked2_env.py:336).
 template <int P>
-OCB_HD int step_world(const Tables& tb, World<P>& w, uint16_t* objs, int ostride, const int (&act)[P], int (&dirty)[P]) {
+OCB_HD int step_world(const Tables& tb, const Consts& c, World<P>& w, uint16_t* objs, int ostride, const int (&act)[P],
+                      uint32_t (&dirty)[P]) {
     int reward = 0;
-    bool any_interact = false;
+    // pot snapshot "taken once before the player loop" (R:302): the running count as of step start
+    const int pots_before = w.nonempty_pots;
+
+    // resolve_interacts: players in index order on live state (R:305-353)
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-        dirty[i] = -1;
-        any_interact |= (act[i] == A_INTERACT);
-    }
-
-    if (any_interact) {
-        // pot snapshot taken once before the player loop (R:302, get_pot_states R:272-281)
-        int non_empty_pots = 0;
-        for (int q = 0; q < tb.n_pots; ++q) {
-            const uint32_t o = objs[(int)tb.pot_cells[q] * ostride];
-            non_empty_pots += (o != 0u && (obj_tickp1(o) >= 1 || obj_ingredients(o) < 3)) ? 1 : 0;
-        }
-        // players in index order on live state (R:305-353)
-#pragma unroll
-        for (int i = 0; i < P; ++i) {
-            if (act[i] != A_INTERACT) continue;
-            const int tgt = w.pos[i] + dir_delta(w.orient[i], tb.W);  // pre-move pose, R:309-310
-            const int t = tb.terrain[tgt];
-            const uint32_t h = w.held[i];
-            if (t == T_COUNTER) {  // R:313-319
-                const uint32_t o = objs[tgt * ostride];
-                if (h != 0u && o == 0u) {
-                    objs[tgt * ostride] = (uint16_t)h;
-                    w.held[i] = 0u;
-                    w.counter_dishes += (obj_name(h) == O_DISH);
-                } else if (h == 0u && o != 0u) {
-                    w.held[i] = o;
-                    objs[tgt * ostride] = 0;
-                    w.counter_dishes -= (obj_name(o) == O_DISH);
-                }
-                dirty[i] = tgt;
-            } else if (t == T_ONION_SRC) {  // R:320-321
-                if (h == 0u) w.held[i] = obj_make(O_ONION, 0, 0, -1);
-            } else if (t == T_TOMATO_SRC) {  // R:322-323
-                if (h == 0u) w.held[i] = obj_make(O_TOMATO, 0, 0, -1);
-            } else if (t == T_DISH_SRC) {  // R:324-327, is_dish_pickup_useful R:261-270
-                if (h == 0u) {
-                    if (P == 2) {
-                        int held_dishes = 0;
-#pragma unroll
-                        for (int j = 0; j < P; ++j) held_dishes += (obj_name(w.held[j]) == O_DISH);
-                        if (w.counter_dishes == 0 && held_dishes < non_empty_pots) reward += tb.rew_dish;
-                    }
-                    w.held[i] = obj_make(O_DISH, 0, 0, -1);
-                }
-            } else if (t == T_POT) {  // R:331-349
-                if (h != 0u) {
-                    uint32_t o = objs[tgt * ostride];
-                    const int hn = obj_name(h);
-                    if (hn == O_DISH && o != 0u && soup_ready(tb, o)) {  // R:332-336
-                        w.held[i] = o;
-                        objs[tgt * ostride] = 0;
-                        reward += tb.rew_soup;
-                    } else if (hn == O_ONION || hn == O_TOMATO) {  // R:337-349
-                        if (o == 0u) o = obj_make(O_SOUP, 0, 0, -1);
-                        if (!(obj_tickp1(o) >= 1 || obj_ingredients(o) == 3)) {
-                            o += (hn == O_ONION) ? (1u << 5) : (1u << 3);
-                            w.held[i] = 0u;
-                            reward += tb.rew_place;
-                        }
-                        // soup_to_be_cooked_at_location (R:287-296) and full -> auto start
-                        if (obj_name(o) == O_SOUP && !soup_cooking(tb, o) && !soup_ready(tb, o) &&
-                            obj_ingredients(o) == 3)
-                            o = (o & 0xFFu) | (1u << 8);
-                        objs[tgt * ostride] = (uint16_t)o;
-                    }
-                    dirty[i] = tgt;
-                }
-            } else if (t == T_SERVING) {  // R:350-353, deliver_soup R:283-285
-                if (h != 0u && obj_name(h) == O_SOUP) {
-                    reward += tb.rvalue[obj_recipe(h)];
-                    w.held[i] = 0u;
-                }
+        dirty[i] = 0xFFFFFFFFu;
+        if (act[i] != A_INTERACT) continue;
+        const uint32_t ci = tb.cell_info[w.pos[i] + dir_delta(w.orient[i], c.dpack)];  // pre-move pose, R:309-310
+        const int t = info_terrain(ci);
+        const int tgt = info_cell(ci);
+        const uint32_t h = w.held[i];
+        if (t == T_COUNTER) {  // R:313-319
+            const uint32_t o = objs[tgt * ostride];
+            if (h != 0u && o == 0u) {
+                objs[tgt * ostride] = (uint16_t)h;
+                w.held[i] = 0u;
+                w.counter_dishes += (obj_name(h) == O_DISH);
+            } else if (h == 0u && o != 0u) {
+                w.held[i] = o;
+                objs[tgt * ostride] = 0;
+                w.counter_dishes -= (obj_name(o) == O_DISH);
             }
+            dirty[i] = ci;
+        } else if (t == T_POT) {  // R:331-349
+            if (h != 0u) {
+                const uint32_t o0 = objs[tgt * ostride];
+                uint32_t o = o0;
+                const int hn = obj_name(h);
+                if (hn == O_DISH && o != 0u && soup_ready(tb, c, o)) {  // R:332-336
+                    w.held[i] = o;
+                    o = 0u;
+                    reward += c.rew_soup;
+                } else if (hn == O_ONION || hn == O_TOMATO) {  // R:337-349
+                    if (o == 0u) o = obj_make(O_SOUP, 0, 0, -1);
+                    if (!(obj_tickp1(o) >= 1 || obj_ingredients(o) == 3)) {
+                        o += (hn == O_ONION) ? (1u << 5) : (1u << 3);
+                        w.held[i] = 0u;
+                        reward += c.rew_place;
+                    }
+                    // soup_to_be_cooked_at_location (R:287-296) and full -> auto start
+                    if (obj_name(o) == O_SOUP && obj_tickp1(o) == 0 && obj_ingredients(o) == 3) o |= (1u << 8);
+                }
+                objs[tgt * ostride] = (uint16_t)o;
+                w.nonempty_pots += pot_counts(o) - pot_counts(o0);
+                dirty[i] = ci;
+            }
+        } else if (h == 0u) {  // the three dispensers only serve empty hands (R:320-327)
+            if (t == T_ONION_SRC) {
+                w.held[i] = obj_make(O_ONION, 0, 0, -1);
+            } else if (t == T_TOMATO_SRC) {
+                w.held[i] = obj_make(O_TOMATO, 0, 0, -1);
+            } else if (t == T_DISH_SRC) {  // is_dish_pickup_useful R:261-270
+                if (P == 2) {
+                    int held_dishes = 0;
+#pragma unroll
+                    for (int j = 0; j < P; ++j) held_dishes += (obj_name(w.held[j]) == O_DISH);
+                    if (w.counter_dishes == 0 && held_dishes < pots_before) reward += c.rew_dish;
+                }
+                w.held[i] = obj_make(O_DISH, 0, 0, -1);
+            }
+        } else if (t == T_SERVING && obj_name(h) == O_SOUP) {  // R:350-353, deliver_soup R:283-285
+            reward += tb.rvalue[obj_recipe(h)];
+            w.held[i] = 0u;
         }
     }
 
     // resolve_movement R:368-371, _move_if_direction R:393-399
-    int np[P], no[P];
+    int np[P], ns[P], no[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) {
         const int a = act[i];
-        const int cand = w.pos[i] + dir_delta(a, tb.W);  // INTERACT/STAY -> delta 0
-        const bool walk = (a < A_STAY) && (tb.terrain[cand] == T_AIR);
-        np[i] = walk ? cand : w.pos[i];
+        const uint32_t ci = tb.cell_info[w.pos[i] + dir_delta(a, c.dpack)];  // INTERACT/STAY -> own cell
+        const bool walk = (a < A_STAY) && (info_terrain(ci) == T_AIR);
+        np[i] = walk ? info_cell(ci) : w.pos[i];
+        ns[i] = walk ? info_slot(ci) : w.slot[i];
         no[i] = (a < A_STAY) ? a : w.orient[i];
     }
     // _handle_collisions R:356-366: any colliding pair freezes every position
@@ -212,16 +247,15 @@ OCB_HD int step_world(const Tables& tb, World<P>& w, uint16_t* objs, int ostride
 #pragma unroll
     for (int i = 0; i < P; ++i) {
         w.pos[i] = blocked ? w.pos[i] : np[i];
+        w.slot[i] = blocked ? w.slot[i] : ns[i];
         w.orient[i] = no[i];
     }
 
     // step_environment_effects R:373-379 (cooking soups only ever sit in pots)
     w.timestep += 1;
-    for (int q = 0; q < tb.n_pots; ++q) {
-        const int cell = tb.pot_cells[q];
-        const uint32_t o = objs[cell * ostride];
-        if (obj_name(o) == O_SOUP && soup_cooking(tb, o)) objs[cell * ostride] = (uint16_t)(o + 0x100u);
-    }
+    if (c.n_pots > 0) tick_pot(tb, c, objs, ostride, c.pot0);
+    if (c.n_pots > 1) tick_pot(tb, c, objs, ostride, c.pot1);
+    for (int q = 2; q < c.n_pots; ++q) tick_pot(tb, c, objs, ostride, tb.pot_info[q]);
     return reward;
 }
 
@@ -230,11 +264,13 @@ OCB_HD void reset_world(const Tables& tb, World<P>& w) {  // R:387-391
 #pragma unroll
     for (int i = 0; i < P; ++i) {
         w.pos[i] = tb.start_pos[i];
+        w.slot[i] = info_slot(tb.cell_info[tb.start_pos[i]]);
         w.orient[i] = 0;
         w.held[i] = 0u;
     }
     w.timestep = 0;
     w.counter_dishes = 0;
+    w.nonempty_pots = 0;
 }
 
 // ---------------------------------------------------------------- observation bytes
@@ -243,10 +279,10 @@ OCB_HD void reset_world(const Tables& tb, World<P>& w) {  // R:387-391
 
 // the five dynamic channels shift+5..shift+9 of a counter / pot cell (R:177-211)
 template <int P>
-OCB_HD void encode_cell(const Tables& tb, uint8_t* plane, int cell, uint32_t o) {
-    uint8_t* px = plane + tb.slot_off[cell] + 5 * P + 5;
+OCB_HD void encode_cell(uint8_t* plane, uint32_t ci, uint32_t o) {
+    uint8_t* px = plane + info_slot(ci) + 5 * P + 5;
     const int name = obj_name(o);
-    const bool soup_in_pot = (name == O_SOUP) && (tb.terrain[cell] == T_POT);
+    const bool soup_in_pot = (name == O_SOUP) && (info_terrain(ci) == T_POT);
     const int tp1 = obj_tickp1(o);
     px[0] = soup_in_pot ? (uint8_t)obj_onions(o) : (uint8_t)0;
     px[1] = (soup_in_pot && tp1 >= 1) ? (uint8_t)(tp1 - 1) : (uint8_t)0;
@@ -258,22 +294,20 @@ OCB_HD void encode_cell(const Tables& tb, uint8_t* plane, int cell, uint32_t o) 
 // player i as seen by `viewer` (R:221-257): position one-hot, orientation one-hot of
 // the relative player index, held object drawn on the holder's cell
 template <int P>
-OCB_HD void poke_player(const Tables& tb, uint8_t* plane, int viewer, int i, int pos, int orient, uint32_t held) {
-    uint8_t* px = plane + tb.slot_off[pos];
+OCB_HD void poke_player(uint8_t* plane, int viewer, int i, int slot, int orient, uint32_t held) {
+    uint8_t* px = plane + slot;
     const int rel = (i == viewer) ? 0 : (i < viewer ? i + 1 : i);
     px[rel] = 1;
     px[P + 4 * rel + orient] = 1;
     const int name = obj_name(held);
-    if (name == O_SOUP) px[5 * P + 7] = 1;
-    else if (name == O_DISH) px[5 * P + 8] = 1;
-    else if (name == O_ONION) px[5 * P + 9] = 1;
+    if (name >= O_ONION) px[5 * P + 11 - name] = 1;  // SOUP -> shift+7, DISH -> shift+8, ONION -> shift+9
 }
 
 // a cell a player has left: players only stand on AIR, whose static bytes are all 0
 template <int P>
-OCB_HD void clear_cell(const Tables& tb, uint8_t* plane, int pos) {
+OCB_HD void clear_cell(uint8_t* plane, int slot) {
     constexpr int C = 5 * P + 10;
-    uint8_t* px = plane + tb.slot_off[pos];
+    uint8_t* px = plane + slot;
     if (C % 4 == 0) {
         uint32_t* p4 = reinterpret_cast<uint32_t*>(px);
 #pragma unroll
@@ -291,7 +325,7 @@ OCB_HD void clear_cell(const Tables& tb, uint8_t* plane, int pos) {
 // planes: this world's plane of view v is at planes + v*view_stride.
 template <int P, int G>
 OCB_HD void obs_phase1(const Tables& tb, uint8_t* planes, int view_stride, const uint8_t* tmpl, bool full, int g,
-                       const int (&oldpos)[P]) {
+                       const int (&oldslot)[P]) {
     if (full) {
         if (tb.SC % 4 == 0) {
             const uint32_t* t4 = reinterpret_cast<const uint32_t*>(tmpl);
@@ -308,27 +342,35 @@ OCB_HD void obs_phase1(const Tables& tb, uint8_t* planes, int view_stride, const
 #pragma unroll
         for (int j0 = 0; j0 < P * P; j0 += G) {
             const int j = j0 + g;
-            if (j < P * P) clear_cell<P>(tb, planes + (j / P) * view_stride, sel<P>(oldpos, j % P));
+            if (j < P * P) clear_cell<P>(planes + (j / P) * view_stride, sel<P>(oldslot, j % P));
         }
     }
 }
 
 template <int P, int G>
-OCB_HD void obs_phase2(const Tables& tb, uint8_t* planes, int view_stride, const uint16_t* objs, int ostride,
-                       bool full, int g, const World<P>& w, const int (&dirty)[P]) {
+OCB_HD void obs_phase2(const Tables& tb, const Consts& c, uint8_t* planes, int view_stride, const uint16_t* objs,
+                       int ostride, bool full, int g, const World<P>& w, const uint32_t (&dirty)[P]) {
     if (full) {
-        for (int idx = g; idx < tb.n_objcells; idx += G) {
-            const int cell = tb.objcells[idx];
-            const uint32_t o = objs[cell * ostride];
+        for (int idx = g; idx < c.n_objcells; idx += G) {
+            const uint32_t ci = tb.cell_info[tb.objcells[idx]];
+            const uint32_t o = objs[info_cell(ci) * ostride];
             if (o != 0u)
-                for (int v = 0; v < P; ++v) encode_cell<P>(tb, planes + v * view_stride, cell, o);
+                for (int v = 0; v < P; ++v) encode_cell<P>(planes + v * view_stride, ci, o);
         }
     } else {
-        const int n = (P + tb.n_pots) * P;  // (interact targets + pots) x views
-        for (int j = g; j < n; j += G) {
-            const int v = j % P, d = j / P;
-            const int cell = (d < P) ? sel<P>(dirty, d) : (int)tb.pot_cells[d - P];
-            if (cell >= 0) encode_cell<P>(tb, planes + v * view_stride, cell, objs[cell * ostride]);
+        // (interact targets + pots) x views
+#pragma unroll
+        for (int j0 = 0; j0 < P * P; j0 += G) {
+            const int j = j0 + g;
+            if (j < P * P) {
+                const uint32_t ci = selu<P>(dirty, j / P);
+                if (ci != 0xFFFFFFFFu) encode_cell<P>(planes + (j % P) * view_stride, ci, objs[info_cell(ci) * ostride]);
+            }
+        }
+        for (int j = g; j < c.n_pots * P; j += G) {
+            const int q = j / P;
+            const uint32_t ci = q == 0 ? c.pot0 : q == 1 ? c.pot1 : tb.pot_info[q];
+            encode_cell<P>(planes + (j % P) * view_stride, ci, objs[info_cell(ci) * ostride]);
         }
     }
 #pragma unroll
@@ -336,7 +378,7 @@ OCB_HD void obs_phase2(const Tables& tb, uint8_t* planes, int view_stride, const
         const int j = j0 + g;
         if (j < P * P) {
             const int v = j / P, i = j % P;
-            poke_player<P>(tb, planes + v * view_stride, v, i, sel<P>(w.pos, i), sel<P>(w.orient, i), selu<P>(w.held, i));
+            poke_player<P>(planes + v * view_stride, v, i, sel<P>(w.slot, i), sel<P>(w.orient, i), selu<P>(w.held, i));
         }
     }
 }

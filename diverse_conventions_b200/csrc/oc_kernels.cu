@@ -10,9 +10,9 @@
 //   * each tile keeps its P x WPW observation planes resident in shared memory,
 //     laid out exactly like the [P, N, W, H, C] output so that one view of the
 //     tile is one contiguous run of WPW*S*C bytes in HBM.  After the few bytes
-//     touched by a transition are rewritten the run is streamed out either with
-//     16-byte coalesced streaming stores or with one TMA bulk copy
-//     (cp.async.bulk.global.shared::cta) per view.
+//     touched by a transition are rewritten the run is streamed out with one TMA
+//     bulk copy (cp.async.bulk.global.shared::cta) per view, or with 16-byte
+//     coalesced streaming stores when the run is not 16-byte aligned.
 // See DESIGN.md for the byte accounting and the roofline.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,9 +28,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
-                 "r"(bytes)
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -69,65 +68,92 @@ __device__ __forceinline__ void warp_copy_out(int8_t* __restrict__ dst, const ui
     }
 }
 
+// shared-memory carve-up of one CTA (all offsets 16-byte aligned):
+//   Tables | template[SC] | per warp: planes[P][view_stride] , objs[S][WPW] u16
 template <int P, int G>
-__global__ void __launch_bounds__(kThreadsPerCta) oc_rollout_kernel(const RolloutParams prm) {
-    constexpr int WPW = 32 / G;
-    extern __shared__ __align__(16) uint8_t smem[];
-
-    // ---- stage the static tables and the observation template
-    Tables& tb = *reinterpret_cast<Tables*>(smem);
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
+struct Carve {
+    static constexpr int WPW = 32 / G;
+    int view_stride;
+    size_t warp_bytes, warp0;
+    __device__ Carve(int S, int SC) {
+        view_stride = (int)align16((size_t)WPW * SC);
+        warp_bytes = (size_t)P * view_stride + align16((size_t)S * WPW * 2);
+        warp0 = align16(sizeof(Tables)) + align16((size_t)SC);
     }
+};
+
+__device__ __forceinline__ void stage_tables(uint8_t* smem, const RolloutParams& prm) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.tables);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+    for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
     __syncthreads();
-    const int SC = tb.SC, S = tb.S;
+    const int SC = reinterpret_cast<const Tables*>(smem)->SC;
     uint8_t* tmpl = smem + align16(sizeof(Tables));
     for (int i = threadIdx.x; i < SC; i += blockDim.x) tmpl[i] = prm.tmpl[i];
     __syncthreads();
+}
+
+// HBM -> registers / shared memory
+template <int P, int G>
+__device__ __forceinline__ void load_world(const Tables& tb, const Consts& c, const RolloutParams& prm, int nl, int g,
+                                           uint16_t* myobjs, World<P>& w) {
+    constexpr int WPW = 32 / G;
+    const int N = prm.N;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const uint32_t pw = prm.players[(size_t)i * N + nl];
+        w.pos[i] = (int)(pw & 0xFFFu);
+        w.slot[i] = info_slot(tb.cell_info[w.pos[i]]);
+        w.orient[i] = (int)((pw >> 12) & 3u);
+        w.held[i] = pw >> 16;
+    }
+    w.timestep = prm.timestep[nl];
+    for (int cell = g; cell < tb.S; cell += G) myobjs[cell * WPW] = prm.objs[(size_t)cell * N + nl];
+    __syncwarp();
+    int cd = 0, np = 0;
+    for (int idx = g; idx < c.n_objcells; idx += G) {
+        const uint32_t ci = tb.cell_info[tb.objcells[idx]];
+        const uint32_t o = myobjs[info_cell(ci) * WPW];
+        cd += (info_terrain(ci) == T_COUNTER && obj_name(o) == O_DISH);
+        np += (info_terrain(ci) == T_POT) ? pot_counts(o) : 0;
+    }
+#pragma unroll
+    for (int m = 1; m < G; m <<= 1) {
+        cd += __shfl_xor_sync(0xffffffffu, cd, m);
+        np += __shfl_xor_sync(0xffffffffu, np, m);
+    }
+    w.counter_dishes = cd;
+    w.nonempty_pots = np;
+}
+
+template <int P, int G>
+__global__ void __launch_bounds__(kThreadsPerCta, (G == 8 ? 6 : 4)) oc_rollout_kernel(const RolloutParams prm) {
+    constexpr int WPW = 32 / G;
+    extern __shared__ __align__(16) uint8_t smem[];
+    stage_tables(smem, prm);
+    const Tables& tb = *reinterpret_cast<const Tables*>(smem);
+    const Consts c = load_consts(tb);
+    const int SC = tb.SC, S = tb.S;
+    const uint8_t* tmpl = smem + align16(sizeof(Tables));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wi = lane / G, g = lane % G;
-    const int view_stride = align16(WPW * SC);  // one view of the tile
-    const size_t warp_bytes = (size_t)P * view_stride + align16(S * WPW * 2);
-    uint8_t* wbase = smem + align16(sizeof(Tables)) + align16(SC) + warp * warp_bytes;
-    uint8_t* planes = wbase;                                                       // [P][WPW][SC]
-    uint16_t* objs = reinterpret_cast<uint16_t*>(wbase + (size_t)P * view_stride);  // [S][WPW]
-    uint16_t* myobjs = objs + wi;
-    uint8_t* myplanes = planes + wi * SC;  // + v*view_stride
+    const Carve<P, G> cv(S, SC);
+    const int view_stride = cv.view_stride;
+    uint8_t* planes = smem + cv.warp0 + warp * cv.warp_bytes;                                 // [P][WPW][SC]
+    uint16_t* myobjs = reinterpret_cast<uint16_t*>(planes + (size_t)P * view_stride) + wi;  // [S][WPW]
+    uint8_t* myplanes = planes + wi * SC;                                                     // + v*view_stride
 
     const int N = prm.N;
-    const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
-    const int n0 = tile * WPW;
+    const int n0 = (blockIdx.x * (blockDim.x >> 5) + warp) * WPW;
     if (n0 >= N) return;  // whole warp idle (no block-level sync below)
     const int nvalid = min(WPW, N - n0);
     const int n = n0 + wi;
     const bool valid = n < N;
     const int nl = valid ? n : N - 1;
 
-    // ---- load world state: HBM -> registers / shared memory
     World<P> w;
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-        const uint32_t pw = prm.players[(size_t)i * N + nl];
-        w.pos[i] = (int)(pw & 0xFFFu);
-        w.orient[i] = (int)((pw >> 12) & 3u);
-        w.held[i] = pw >> 16;
-    }
-    w.timestep = prm.timestep[nl];
-    for (int c = g; c < S; c += G) myobjs[c * WPW] = prm.objs[(size_t)c * N + nl];
-    __syncwarp();
-    {
-        int cd = 0;
-        for (int idx = g; idx < tb.n_objcells; idx += G) {
-            const int cell = tb.objcells[idx];
-            cd += (tb.terrain[cell] == T_COUNTER && obj_name(myobjs[cell * WPW]) == O_DISH);
-        }
-#pragma unroll
-        for (int m = 1; m < G; m <<= 1) cd += __shfl_xor_sync(0xffffffffu, cd, m);
-        w.counter_dishes = cd;
-    }
+    load_world<P, G>(tb, c, prm, nl, g, myobjs, w);
     int cur_return = prm.cur_return[nl];
     long long ret_add = 0;
     int ep_add = 0;
@@ -136,48 +162,70 @@ __global__ void __launch_bounds__(kThreadsPerCta) oc_rollout_kernel(const Rollou
     const bool want_obs = prm.obs != nullptr;
     ActionRng<P> rng;
     unsigned long long t = prm.step0;
-    if (use_rng && (t % ActionRng<P>::kStepsPerBlock) != 0) rng.refill(prm.seed, (uint32_t)(prm.world0 + nl), t);
+    const uint32_t gworld = prm.world0 + (uint32_t)nl;
+    if (use_rng && (t % ActionRng<P>::kStepsPerBlock) != 0) rng.refill(prm.seed, gworld, t);
+
+    // per-lane output cursors, advanced by one step's stride each iteration
+    const size_t PN = (size_t)P * N;
+    int32_t* rew_ptr = prm.rew ? prm.rew + n : nullptr;      // + i*N
+    int32_t* done_ptr = prm.done ? prm.done + n : nullptr;
+    uint8_t* aout_ptr = prm.actions_out ? prm.actions_out + n : nullptr;
+    size_t act_idx = nl;                                     // + i*N
+    int8_t* obs_ptr = want_obs ? prm.obs + (size_t)n0 * SC : nullptr;
+    const size_t obs_view_stride = (size_t)N * SC, obs_step_stride = PN * SC;
+    const int nbytes = nvalid * SC;
+    const bool tma_ok = want_obs && prm.use_tma && ((nbytes & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(obs_ptr) & 15u) == 0) && ((obs_view_stride & 15u) == 0);
+    const uint32_t planes_s = smem_u32(planes);
     bool tma_pending = false;
 
     for (int k = 0; k < prm.K; ++k, ++t) {
         // ---- joint action
         int act[P];
         if (use_rng) {
-            if ((t % ActionRng<P>::kStepsPerBlock) == 0) rng.refill(prm.seed, (uint32_t)(prm.world0 + nl), t);
+            if ((t % ActionRng<P>::kStepsPerBlock) == 0) rng.refill(prm.seed, gworld, t);
 #pragma unroll
             for (int i = 0; i < P; ++i) act[i] = rng.action(t, i, 6);
         } else {
 #pragma unroll
-            for (int i = 0; i < P; ++i) act[i] = load_action(prm.actions, prm.act_dtype, ((size_t)k * P + i) * N + nl);
+            for (int i = 0; i < P; ++i) act[i] = load_action(prm.actions, prm.act_dtype, act_idx + (size_t)i * N);
+            act_idx += PN;
         }
-        if (prm.actions_out != nullptr && valid) {
+        if (aout_ptr != nullptr) {
+            if (valid) {
 #pragma unroll
-            for (int i = 0; i < P; ++i)
-                if (i % G == g) prm.actions_out[((size_t)k * P + i) * N + n] = (uint8_t)act[i];
+                for (int i = 0; i < P; ++i)
+                    if (i % G == g) aout_ptr[(size_t)i * N] = (uint8_t)act[i];
+            }
+            aout_ptr += PN;
         }
 
         // ---- transition (registers + shared memory only)
-        int oldpos[P], dirty[P];
+        int oldslot[P];
+        uint32_t dirty[P];
 #pragma unroll
-        for (int i = 0; i < P; ++i) oldpos[i] = w.pos[i];
-        const int r = step_world<P>(tb, w, myobjs, WPW, act, dirty);
-        const bool done = w.timestep >= tb.horizon;  // envs/overcooked2_env.py:334
+        for (int i = 0; i < P; ++i) oldslot[i] = w.slot[i];
+        const int r = step_world<P>(tb, c, w, myobjs, WPW, act, dirty);
+        const bool done = w.timestep >= c.horizon;  // envs/overcooked2_env.py:334
         cur_return += r;
         if (done) {  // auto-reset, pantheonrl_extension/vectorenv.py:369-370
             ret_add += cur_return;
             ep_add += 1;
             cur_return = 0;
             reset_world<P>(tb, w);
-            for (int idx = g; idx < tb.n_objcells; idx += G) myobjs[(int)tb.objcells[idx] * WPW] = 0;
+            for (int idx = g; idx < c.n_objcells; idx += G) myobjs[(int)tb.objcells[idx] * WPW] = 0;
         }
-        __syncwarp();  // cleared cells are read by the sibling lanes of the world
-        if (valid) {
-            if (prm.rew != nullptr) {
+        if (rew_ptr != nullptr) {
+            if (valid) {
 #pragma unroll
                 for (int i = 0; i < P; ++i)
-                    if (i % G == g) prm.rew[((size_t)k * P + i) * N + n] = r;
+                    if (i % G == g) rew_ptr[(size_t)i * N] = r;
             }
-            if (prm.done != nullptr && g == G - 1) prm.done[(size_t)k * N + n] = done ? 1 : 0;
+            rew_ptr += PN;
+        }
+        if (done_ptr != nullptr) {
+            if (valid && g == G - 1) *done_ptr = done ? 1 : 0;
+            done_ptr += N;
         }
 
         // ---- observation planes: rewrite touched bytes, stream the tile out
@@ -187,30 +235,28 @@ __global__ void __launch_bounds__(kThreadsPerCta) oc_rollout_kernel(const Rollou
                 if (lane == 0) bulk_wait_read_all();
                 tma_pending = false;
             }
+            __syncwarp();  // also orders the cleared cells of a reset before the sibling lanes' reads
+            obs_phase1<P, G>(tb, myplanes, view_stride, tmpl, full, g, oldslot);
             __syncwarp();
-            obs_phase1<P, G>(tb, myplanes, view_stride, tmpl, full, g, oldpos);
-            __syncwarp();
-            obs_phase2<P, G>(tb, myplanes, view_stride, myobjs, WPW, full, g, w, dirty);
-            const int nbytes = nvalid * SC;
-            int8_t* dst0 = prm.obs + (((size_t)k * P) * N + n0) * SC;
-            const size_t dst_view_stride = (size_t)N * SC;
-            const bool tma_ok = prm.use_tma && ((nbytes & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst0) & 15u) == 0) &&
-                                ((dst_view_stride & 15u) == 0);
+            obs_phase2<P, G>(tb, c, myplanes, view_stride, myobjs, WPW, full, g, w, dirty);
             if (tma_ok) {
                 fence_proxy_async_smem();  // generic-proxy pokes -> visible to the async proxy
                 __syncwarp();
                 if (lane == 0) {
 #pragma unroll
                     for (int v = 0; v < P; ++v)
-                        bulk_store_s2g(dst0 + v * dst_view_stride, planes + v * view_stride, (uint32_t)nbytes);
+                        bulk_store_s2g(obs_ptr + v * obs_view_stride, planes_s + v * view_stride, (uint32_t)nbytes);
                     bulk_commit();
                 }
                 tma_pending = true;
             } else {
                 __syncwarp();
 #pragma unroll
-                for (int v = 0; v < P; ++v) warp_copy_out(dst0 + v * dst_view_stride, planes + v * view_stride, nbytes, lane);
+                for (int v = 0; v < P; ++v) warp_copy_out(obs_ptr + v * obs_view_stride, planes + v * view_stride, nbytes, lane);
             }
+            obs_ptr += obs_step_stride;
+        } else {
+            __syncwarp();  // cleared cells of a reset are read by the sibling lanes of the world
         }
     }
     if (tma_pending && lane == 0) bulk_wait_read_all();
@@ -220,7 +266,7 @@ __global__ void __launch_bounds__(kThreadsPerCta) oc_rollout_kernel(const Rollou
 #pragma unroll
         for (int i = 0; i < P; ++i)
             if (i % G == g) prm.players[(size_t)i * N + n] = player_pack(w.pos[i], w.orient[i], w.held[i]);
-        for (int c = g; c < S; c += G) prm.objs[(size_t)c * N + n] = myobjs[c * WPW];
+        for (int cell = g; cell < S; cell += G) prm.objs[(size_t)cell * N + n] = myobjs[cell * WPW];
         if (g == 0) {
             prm.timestep[n] = w.timestep;
             prm.cur_return[n] = cur_return;
@@ -237,25 +283,18 @@ template <int P, int G>
 __global__ void __launch_bounds__(kThreadsPerCta) oc_observe_kernel(const RolloutParams prm) {
     constexpr int WPW = 32 / G;
     extern __shared__ __align__(16) uint8_t smem[];
-    Tables& tb = *reinterpret_cast<Tables*>(smem);
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
+    stage_tables(smem, prm);
+    const Tables& tb = *reinterpret_cast<const Tables*>(smem);
+    const Consts c = load_consts(tb);
     const int SC = tb.SC, S = tb.S;
-    uint8_t* tmpl = smem + align16(sizeof(Tables));
-    for (int i = threadIdx.x; i < SC; i += blockDim.x) tmpl[i] = prm.tmpl[i];
-    __syncthreads();
+    const uint8_t* tmpl = smem + align16(sizeof(Tables));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wi = lane / G, g = lane % G;
-    const int view_stride = align16(WPW * SC);
-    const size_t warp_bytes = (size_t)P * view_stride + align16(S * WPW * 2);
-    uint8_t* wbase = smem + align16(sizeof(Tables)) + align16(SC) + warp * warp_bytes;
-    uint8_t* planes = wbase;
-    uint16_t* myobjs = reinterpret_cast<uint16_t*>(wbase + (size_t)P * view_stride) + wi;
+    const Carve<P, G> cv(S, SC);
+    const int view_stride = cv.view_stride;
+    uint8_t* planes = smem + cv.warp0 + warp * cv.warp_bytes;
+    uint16_t* myobjs = reinterpret_cast<uint16_t*>(planes + (size_t)P * view_stride) + wi;
     uint8_t* myplanes = planes + wi * SC;
 
     const int N = prm.N;
@@ -265,23 +304,14 @@ __global__ void __launch_bounds__(kThreadsPerCta) oc_observe_kernel(const Rollou
     const int nl = min(n0 + wi, N - 1);
 
     World<P> w;
+    load_world<P, G>(tb, c, prm, nl, g, myobjs, w);
+    int noslot[P];
+    uint32_t nodirty[P];
 #pragma unroll
-    for (int i = 0; i < P; ++i) {
-        const uint32_t pw = prm.players[(size_t)i * N + nl];
-        w.pos[i] = (int)(pw & 0xFFFu);
-        w.orient[i] = (int)((pw >> 12) & 3u);
-        w.held[i] = pw >> 16;
-    }
-    w.timestep = 0;
-    w.counter_dishes = 0;
-    for (int c = g; c < S; c += G) myobjs[c * WPW] = prm.objs[(size_t)c * N + nl];
-    int none[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) none[i] = -1;
+    for (int i = 0; i < P; ++i) noslot[i] = 0, nodirty[i] = 0xFFFFFFFFu;
+    obs_phase1<P, G>(tb, myplanes, view_stride, tmpl, true, g, noslot);
     __syncwarp();
-    obs_phase1<P, G>(tb, myplanes, view_stride, tmpl, true, g, none);
-    __syncwarp();
-    obs_phase2<P, G>(tb, myplanes, view_stride, myobjs, WPW, true, g, w, none);
+    obs_phase2<P, G>(tb, c, myplanes, view_stride, myobjs, WPW, true, g, w, nodirty);
     __syncwarp();
     const int nbytes = nvalid * SC;
 #pragma unroll
@@ -322,9 +352,9 @@ __global__ void oc_export_state_kernel(const Tables* __restrict__ tables, const 
             pl[4] = obj_tomatoes(h);
             pl[5] = h ? obj_tickp1(h) - 1 : 0;
         }
-        for (int c = 0; c < S; ++c) {
-            const uint32_t o = objs[(size_t)c * N + n];
-            int32_t* oc = row + 1 + 6 * P + 4 * c;
+        for (int cell = 0; cell < S; ++cell) {
+            const uint32_t o = objs[(size_t)cell * N + n];
+            int32_t* oc = row + 1 + 6 * P + 4 * cell;
             oc[0] = obj_name(o);
             oc[1] = obj_onions(o);
             oc[2] = obj_tomatoes(o);
@@ -333,41 +363,43 @@ __global__ void oc_export_state_kernel(const Tables* __restrict__ tables, const 
     }
 }
 
-// returns (through *bad) the number of worlds holding a state the CUDA path does not
-// represent: out-of-range fields, objects on cells that cannot hold one, a pot
-// holding anything but a soup, a cooking soup outside a pot, a player off the AIR cells.
+// counts (through *bad) the worlds holding a state the CUDA path does not represent:
+// out-of-range fields, objects on cells that cannot hold one, a pot holding anything but
+// a soup, a cooking soup outside a pot, a player off the AIR cells.
 __global__ void oc_import_state_kernel(const Tables* __restrict__ tables, const int32_t* in, uint32_t* players,
                                        uint16_t* objs, int32_t* timestep, int32_t* cur_return, int N, int* bad) {
     const int P = tables->P, S = tables->S, L = 1 + 6 * P + 4 * S;
+    Consts c = load_consts(*tables);
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
         const int32_t* row = in + (size_t)n * L;
         bool ok = row[0] >= 0;
         auto check_obj = [&](const int32_t* o) {
             if (o[0] == O_NONE) return o[1] == 0 && o[2] == 0 && o[3] == 0;
-            bool g = o[0] >= O_TOMATO && o[0] <= O_SOUP && o[1] >= 0 && o[2] >= 0 && o[1] + o[2] <= 3 && o[3] >= -1 &&
-                     o[3] <= OCB_MAX_COOK_TIME + 1;
-            if (g && o[0] != O_SOUP) g = (o[1] == 0 && o[2] == 0 && o[3] == -1);
-            return g;
+            bool good = o[0] >= O_TOMATO && o[0] <= O_SOUP && o[1] >= 0 && o[2] >= 0 && o[1] + o[2] <= 3 && o[3] >= -1 &&
+                        o[3] <= OCB_MAX_COOK_TIME + 1;
+            if (good && o[0] != O_SOUP) good = (o[1] == 0 && o[2] == 0 && o[3] == -1);
+            return good;
         };
         for (int i = 0; i < P; ++i) {
             const int32_t* pl = row + 1 + 6 * i;
             ok = ok && pl[0] >= 0 && pl[0] < S && pl[1] >= 0 && pl[1] <= 3 && check_obj(pl + 2);
-            if (ok) ok = tables->terrain[pl[0]] == T_AIR;
+            if (ok) ok = info_terrain(tables->cell_info[pl[0]]) == T_AIR;
             if (ok) {
                 const uint32_t h = pl[2] ? obj_make(pl[2], pl[3], pl[4], pl[5]) : 0u;
                 players[(size_t)i * N + n] = player_pack(pl[0], pl[1], h);
             }
         }
-        for (int c = 0; c < S; ++c) {
-            const int32_t* oc = row + 1 + 6 * P + 4 * c;
+        for (int cell = 0; cell < S; ++cell) {
+            const int32_t* oc = row + 1 + 6 * P + 4 * cell;
             ok = ok && check_obj(oc);
             uint32_t o = 0u;
             if (ok && oc[0] != O_NONE) {
-                const int t = tables->terrain[c];
+                const int t = info_terrain(tables->cell_info[cell]);
                 o = obj_make(oc[0], oc[1], oc[2], oc[3]);
-                ok = (t == T_POT && oc[0] == O_SOUP) || (t == T_COUNTER && !(oc[0] == O_SOUP && soup_cooking(*tables, o)));
+                ok = (t == T_POT && oc[0] == O_SOUP) ||
+                     (t == T_COUNTER && !(oc[0] == O_SOUP && soup_cooking(*tables, c, o)));
             }
-            objs[(size_t)c * N + n] = (uint16_t)o;
+            objs[(size_t)cell * N + n] = (uint16_t)o;
         }
         timestep[n] = row[0];
         cur_return[n] = 0;
@@ -394,7 +426,7 @@ static cudaError_t launch_pg(const RolloutParams& prm, int warps_per_cta, size_t
 size_t rollout_smem_bytes(int P, int S, int C, int G, int warps_per_cta) {
     const int WPW = 32 / G;
     const size_t SC = (size_t)S * C;
-    const size_t per_warp = (size_t)P * align16(WPW * SC) + align16(S * WPW * 2);
+    const size_t per_warp = (size_t)P * align16(WPW * SC) + align16((size_t)S * WPW * 2);
     return align16(sizeof(Tables)) + align16(SC) + warps_per_cta * per_warp;
 }
 
@@ -404,7 +436,8 @@ static cudaError_t launch_p(const RolloutParams& prm, int G, int warps_per_cta, 
     switch (G) {
         case 1: return launch_pg<P, 1>(prm, warps_per_cta, smem_bytes, observe_only, stream);
         case 2: return launch_pg<P, 2>(prm, warps_per_cta, smem_bytes, observe_only, stream);
-        default: return launch_pg<P, 4>(prm, warps_per_cta, smem_bytes, observe_only, stream);
+        case 4: return launch_pg<P, 4>(prm, warps_per_cta, smem_bytes, observe_only, stream);
+        default: return launch_pg<P, 8>(prm, warps_per_cta, smem_bytes, observe_only, stream);
     }
 }
 

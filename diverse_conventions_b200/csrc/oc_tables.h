@@ -40,6 +40,11 @@ inline int build_tables(const ocb_config* cfg, Tables* tb, uint8_t* tmpl, char* 
         tb->rtime[i] = (uint8_t)cfg->recipe_times[i];
         tb->rvalue[i] = cfg->recipe_values[i];
     }
+    if (W > 127) OCB_TABLE_FAIL(OCB_ERR_BAD_LAYOUT, "width %d > 127", W);
+    tb->dpack = (uint32_t)(uint8_t)(int8_t)(-W) | ((uint32_t)(uint8_t)(int8_t)W << 8) | (1u << 16) | (0xFFu << 24);
+    tb->uniform_time = cfg->recipe_times[0];
+    for (int i = 1; i < OCB_NUM_RECIPES; ++i)
+        if (cfg->recipe_times[i] != cfg->recipe_times[0]) tb->uniform_time = -1;
     int n_counters = 0;
     for (int pos = 0; pos < S; ++pos) {
         const int t = cfg->terrain[pos];
@@ -47,15 +52,14 @@ inline int build_tables(const ocb_config* cfg, Tables* tb, uint8_t* tmpl, char* 
         const int x = pos % W, y = pos / W;
         if ((x == 0 || y == 0 || x == W - 1 || y == H - 1) && t == T_AIR)
             OCB_TABLE_FAIL(OCB_ERR_BAD_LAYOUT, "border cell (%d,%d) is walkable", x, y);
-        tb->terrain[pos] = (uint8_t)t;
-        tb->slot_off[pos] = (uint16_t)((x * H + y) * C);
+        tb->cell_info[pos] = info_make(t, (x * H + y) * C, pos);
         if (t == T_COUNTER) tb->objcells[n_counters++] = (uint16_t)pos;
     }
     tb->n_objcells = n_counters;
     for (int pos = 0; pos < S; ++pos)
         if (cfg->terrain[pos] == T_POT) {
             if (tb->n_pots == kMaxPots) OCB_TABLE_FAIL(OCB_ERR_BAD_LAYOUT, "more than %d pots", kMaxPots);
-            tb->pot_cells[tb->n_pots++] = (uint16_t)pos;
+            tb->pot_info[tb->n_pots++] = tb->cell_info[pos];
             tb->objcells[tb->n_objcells++] = (uint16_t)pos;
         }
     for (int i = 0; i < P; ++i) {
@@ -68,7 +72,7 @@ inline int build_tables(const ocb_config* cfg, Tables* tb, uint8_t* tmpl, char* 
     memset(tmpl, 0, (size_t)S * C);
     for (int pos = 0; pos < S; ++pos) {
         const int t = cfg->terrain[pos];
-        if (t > T_AIR) tmpl[tb->slot_off[pos] + t - 1 + 5 * P] = 1;
+        if (t > T_AIR) tmpl[info_slot(tb->cell_info[pos]) + t - 1 + 5 * P] = 1;
     }
     return OCB_OK;
 }

@@ -58,6 +58,11 @@ static int build_tables_or_fail(const ocb_config* cfg, Tables* tb, uint8_t* tmpl
     return rc == OCB_OK ? OCB_OK : fail(rc, "%s", msg);
 }
 
+// lanes per world: few worlds -> more (redundant) lanes so that every SM scheduler still has
+// several warps to hide the latency of the sequential transition; many worlds -> fewer lanes,
+// less redundant issue.  Thresholds from tools/sweep.py on B200 (profiles/README.md).
+static int default_lanes(int N) { return N < 49152 ? 4 : 2; }
+
 static int pick_launch_shape(const ocb_env* e, int G, int* warps, size_t* smem) {
     for (int w = 4; w >= 1; w >>= 1) {
         const size_t b = rollout_smem_bytes(e->P, e->S, e->C, G, w);
@@ -126,8 +131,8 @@ extern "C" int ocb_create(const ocb_config* cfg, int device, uint32_t num_worlds
     e->P = e->h_tables.P, e->S = e->h_tables.S, e->C = e->h_tables.C, e->SC = e->h_tables.SC;
     e->L = 1 + 6 * e->P + 4 * e->S;
     e->seed = seed;
-    e->lanes_per_world = 4;
-    e->use_tma = 0;
+    e->lanes_per_world = default_lanes(e->N);
+    e->use_tma = 1;
 
     DeviceGuard guard(device);
     const size_t N = num_worlds;
@@ -177,9 +182,9 @@ extern "C" uint64_t ocb_step_count(const ocb_env* e) { return e ? e->step_count 
 
 extern "C" int ocb_set_tuning(ocb_env* e, int lanes_per_world, int use_tma) {
     if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "env is NULL");
-    if (lanes_per_world == 0) lanes_per_world = 4;
-    if (lanes_per_world != 1 && lanes_per_world != 2 && lanes_per_world != 4)
-        return fail(OCB_ERR_INVALID_ARG, "lanes_per_world must be 1, 2 or 4");
+    if (lanes_per_world == 0) lanes_per_world = default_lanes(e->N);
+    if (lanes_per_world != 1 && lanes_per_world != 2 && lanes_per_world != 4 && lanes_per_world != 8)
+        return fail(OCB_ERR_INVALID_ARG, "lanes_per_world must be 1, 2, 4 or 8");
     int warps;
     size_t smem;
     int rc = pick_launch_shape(e, lanes_per_world, &warps, &smem);

@@ -112,7 +112,8 @@ int ocb_obs_channels(const ocb_env* env);         /* C = 5P + 10 */
 int ocb_obs_bytes_per_agent(const ocb_env* env);  /* W*H*C */
 int ocb_state_ints_per_world(const ocb_env* env); /* length of one packed world state */
 
-/* kernel tuning knobs: lanes_per_world in {1,2,4} (0 = default), use_tma in {0,1} */
+/* kernel tuning knobs: lanes_per_world in {1,2,4,8} (0 = default by world count),
+ * use_tma in {0,1} (default 1: TMA bulk stores of the observation tiles) */
 int ocb_set_tuning(ocb_env* env, int lanes_per_world, int use_tma);
 
 /* ------------------------------------------------------- Overcooked: hot path */

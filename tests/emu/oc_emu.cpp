@@ -26,6 +26,7 @@ int rollout(const Tables& tb, const uint8_t* tmpl, int32_t* state, int N, int K,
             uint64_t step0, uint32_t world0, int8_t* obs, int32_t* rew, int32_t* done, uint8_t* actions_out) {
     constexpr int WPW = 32 / G;
     const int S = tb.S, SC = tb.SC, L = 1 + 6 * P + 4 * S;
+    const Consts c = load_consts(tb);
     const int view_stride = (int)a16((size_t)WPW * SC);
     std::vector<uint8_t> planes((size_t)P * view_stride);
     std::vector<uint16_t> objs((size_t)S * WPW);
@@ -42,6 +43,7 @@ int rollout(const Tables& tb, const uint8_t* tmpl, int32_t* state, int N, int K,
             for (int i = 0; i < P; ++i) {
                 const int32_t* pl = row + 1 + 6 * i;
                 w[lane].pos[i] = pl[0];
+                w[lane].slot[i] = info_slot(tb.cell_info[pl[0]]);
                 w[lane].orient[i] = pl[1];
                 w[lane].held[i] = pl[2] ? obj_make(pl[2], pl[3], pl[4], pl[5]) : 0u;
             }
@@ -54,19 +56,23 @@ int rollout(const Tables& tb, const uint8_t* tmpl, int32_t* state, int N, int K,
         }
         for (int lane = 0; lane < 32; ++lane) {
             const int wi = lane / G;
-            int cd = 0;
+            int cd = 0, np = 0;
             for (int idx = 0; idx < tb.n_objcells; ++idx) {
-                const int cell = tb.objcells[idx];
-                cd += (tb.terrain[cell] == T_COUNTER && obj_name(objs[(size_t)cell * WPW + wi]) == O_DISH);
+                const uint32_t ci = tb.cell_info[tb.objcells[idx]];
+                const uint32_t o = objs[(size_t)info_cell(ci) * WPW + wi];
+                cd += (info_terrain(ci) == T_COUNTER && obj_name(o) == O_DISH);
+                np += (info_terrain(ci) == T_POT) ? pot_counts(o) : 0;
             }
             w[lane].counter_dishes = cd;
+            w[lane].nonempty_pots = np;
             const int nl = (n0 + wi < N) ? n0 + wi : N - 1;
             if (actions == nullptr && (step0 % ActionRng<P>::kStepsPerBlock) != 0)
                 rng[lane].refill(seed, world0 + (uint32_t)nl, step0);
         }
         uint64_t t = step0;
         for (int k = 0; k < K; ++k, ++t) {
-            int oldpos[32][P], dirty[32][P];
+            int oldslot[32][P];
+            uint32_t dirty[32][P];
             bool full[32];
             // transition: the G lanes of a world run in lockstep -> emulate by letting only the
             // first lane of each world touch the shared object array and copying its registers
@@ -86,9 +92,9 @@ int rollout(const Tables& tb, const uint8_t* tmpl, int32_t* state, int N, int K,
                 }
                 if (actions_out && n < N)
                     for (int i = 0; i < P; ++i) actions_out[((size_t)k * P + i) * N + n] = (uint8_t)act[i];
-                for (int i = 0; i < P; ++i) oldpos[lane][i] = w[lane].pos[i];
-                const int r = step_world<P>(tb, w[lane], objs.data() + wi, WPW, act, dirty[lane]);
-                const bool d = w[lane].timestep >= tb.horizon;
+                for (int i = 0; i < P; ++i) oldslot[lane][i] = w[lane].slot[i];
+                const int r = step_world<P>(tb, c, w[lane], objs.data() + wi, WPW, act, dirty[lane]);
+                const bool d = w[lane].timestep >= c.horizon;
                 cur_ret[lane] += r;
                 if (d) {
                     cur_ret[lane] = 0;
@@ -100,7 +106,7 @@ int rollout(const Tables& tb, const uint8_t* tmpl, int32_t* state, int N, int K,
                     w[lane + g] = w[lane];
                     rng[lane + g] = rng[lane];
                     full[lane + g] = full[lane];
-                    for (int i = 0; i < P; ++i) oldpos[lane + g][i] = oldpos[lane][i], dirty[lane + g][i] = dirty[lane][i];
+                    for (int i = 0; i < P; ++i) oldslot[lane + g][i] = oldslot[lane][i], dirty[lane + g][i] = dirty[lane][i];
                 }
                 if (n < N) {
                     if (rew)
@@ -111,9 +117,9 @@ int rollout(const Tables& tb, const uint8_t* tmpl, int32_t* state, int N, int K,
             if (obs) {
                 for (int lane = 0; lane < 32; ++lane)  // phase 1, then the kernel's __syncwarp()
                     obs_phase1<P, G>(tb, planes.data() + (lane / G) * SC, view_stride, tmpl, full[lane], lane % G,
-                                     oldpos[lane]);
+                                     oldslot[lane]);
                 for (int lane = 0; lane < 32; ++lane)  // phase 2
-                    obs_phase2<P, G>(tb, planes.data() + (lane / G) * SC, view_stride, objs.data() + lane / G, WPW,
+                    obs_phase2<P, G>(tb, c, planes.data() + (lane / G) * SC, view_stride, objs.data() + lane / G, WPW,
                                      full[lane], lane % G, w[lane], dirty[lane]);
                 for (int v = 0; v < P; ++v)
                     memcpy(obs + (((size_t)k * P + v) * N + n0) * SC, planes.data() + (size_t)v * view_stride,
@@ -149,6 +155,7 @@ int rollout_p(int G, const Tables& tb, const uint8_t* tmpl, int32_t* state, int 
         case 1: return rollout<P, 1>(tb, tmpl, state, N, K, actions, seed, step0, world0, obs, rew, done, actions_out);
         case 2: return rollout<P, 2>(tb, tmpl, state, N, K, actions, seed, step0, world0, obs, rew, done, actions_out);
         case 4: return rollout<P, 4>(tb, tmpl, state, N, K, actions, seed, step0, world0, obs, rew, done, actions_out);
+        case 8: return rollout<P, 8>(tb, tmpl, state, N, K, actions, seed, step0, world0, obs, rew, done, actions_out);
         default: return -1;
     }
 }

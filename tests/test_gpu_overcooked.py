@@ -79,7 +79,7 @@ def test_replays_reference_trajectory_fused(golden_dir, name, G, tma):
 @pytest.mark.parametrize("name,N,horizon", [("simple", 1003, 37), ("unident_s", 257, 50), ("random0", 64, 400),
                                             ("corridor", 33, 60), ("multiplayer_schelling", 100, 45),
                                             ("simple_single", 9, 20), ("mdp_test", 130, 33)])
-@pytest.mark.parametrize("G,tma", [(4, 0), (4, 1), (2, 1), (1, 0)])
+@pytest.mark.parametrize("G,tma", [(4, 0), (4, 1), (2, 1), (1, 0), (8, 1), (0, 1)])
 def test_random_rollout_matches_oracle(name, N, horizon, G, tma):
     lp = layouts.load_layout(name, horizon)
     env = make_env(name, N, horizon, seed=1234)

@@ -29,7 +29,7 @@ def scripted_actions(lp, N, K, rng, noise=0.25):
 
 @pytest.mark.parametrize("name", ["simple", "random0", "random1", "random3", "unident_s", "simple_tomato",
                                   "multiplayer_schelling", "simple_single", "corridor"])
-@pytest.mark.parametrize("G", [1, 2, 4])
+@pytest.mark.parametrize("G", [1, 2, 4, 8])
 def test_emulated_kernel_matches_oracle(name, G):
     rng = np.random.default_rng(hash((name, G)) % 2**32)
     lp = layouts.load_layout(name, 50)
