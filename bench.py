@@ -303,7 +303,8 @@ def run_ours(args):
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "oc_rollout_kernel<2,%d>" % (args.lanes or 4),
+                             "traffic": None, "kernel": "oc_rollout_kernel<%d,%d>" % (P, env.get_tuning()["lanes_per_world"]),
+                             "tuning": env.get_tuning(),
                              "bytes_per_world_step": bytes_ws, "world_steps_per_launch": N * k_launch,
                              "launch_ms": launch_ms, "peak_source": peak_src},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

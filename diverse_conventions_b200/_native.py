@@ -38,6 +38,7 @@ PROTOTYPES = {
     "ocb_obs_bytes_per_agent": (_i, [_vp]),
     "ocb_state_ints_per_world": (_i, [_vp]),
     "ocb_set_tuning": (_i, [_vp, _i, _i]),
+    "ocb_get_tuning": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "ocb_reset": (_i, [_vp, _vp, _vp]),
     "ocb_observe": (_i, [_vp, _vp, _vp]),
     "ocb_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -61,10 +62,17 @@ static int build_tables_or_fail(const ocb_config* cfg, Tables* tb, uint8_t* tmpl
 // lanes per world: few worlds -> more (redundant) lanes so that every SM scheduler still has
 // several warps to hide the latency of the sequential transition; many worlds -> fewer lanes,
 // less redundant issue.  Thresholds from tools/sweep.py on B200 (profiles/README.md).
-static int default_lanes(int N) { return N < 49152 ? 4 : 2; }
+static int default_lanes(int N) { return N >= 8192 ? 1 : (N >= 2048 ? 2 : 4); }
 
 static int pick_launch_shape(const ocb_env* e, int G, int* warps, size_t* smem) {
-    for (int w = 4; w >= 1; w >>= 1) {
+    // 4 warps per CTA measured best on B200 even when that leaves some SMs without a CTA
+    // (16,384 worlds, G=1: 128 CTAs; 1- and 2-warp CTAs were 6% / 3% slower, profiles/README.md)
+    int wmax = 4;
+    if (const char* ev = getenv("OCB_WARPS_PER_CTA")) {  // tuning experiments only
+        const int v = atoi(ev);
+        if (v == 1 || v == 2 || v == 4) wmax = v;
+    }
+    for (int w = wmax; w >= 1; w >>= 1) {
         const size_t b = rollout_smem_bytes(e->P, e->S, e->C, G, w);
         if (b <= 200 * 1024) {
             *warps = w, *smem = b;
@@ -191,6 +199,18 @@ extern "C" int ocb_set_tuning(ocb_env* e, int lanes_per_world, int use_tma) {
     if (rc != OCB_OK) return rc;
     e->lanes_per_world = lanes_per_world;
     e->use_tma = use_tma ? 1 : 0;
+    return OCB_OK;
+}
+
+extern "C" int ocb_get_tuning(const ocb_env* e, int* lanes_per_world, int* use_tma, int* warps_per_cta) {
+    if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "env is NULL");
+    int warps = 0;
+    size_t smem = 0;
+    int rc = pick_launch_shape(e, e->lanes_per_world, &warps, &smem);
+    if (rc != OCB_OK) return rc;
+    if (lanes_per_world) *lanes_per_world = e->lanes_per_world;
+    if (use_tma) *use_tma = e->use_tma;
+    if (warps_per_cta) *warps_per_cta = warps;
     return OCB_OK;
 }
 

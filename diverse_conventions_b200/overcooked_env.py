@@ -108,6 +108,11 @@ class B200Overcooked(VectorMultiAgentEnv):
     def set_tuning(self, lanes_per_world: int = 0, use_tma: bool = False):
         _native.check(self._lib.ocb_set_tuning(self._h, lanes_per_world, int(use_tma)))
 
+    def get_tuning(self) -> dict:
+        g, t, w = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _native.check(self._lib.ocb_get_tuning(self._h, ctypes.byref(g), ctypes.byref(t), ctypes.byref(w)))
+        return {"lanes_per_world": g.value, "use_tma": bool(t.value), "warps_per_cta": w.value}
+
     # ------------------------------------------------------------------ reference API
     def get_obs(self) -> List[VectorObservation]:
         mask = self.to_torch(self.static_action_mask)

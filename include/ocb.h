@@ -115,6 +115,8 @@ int ocb_state_ints_per_world(const ocb_env* env); /* length of one packed world 
 /* kernel tuning knobs: lanes_per_world in {1,2,4,8} (0 = default by world count),
  * use_tma in {0,1} (default 1: TMA bulk stores of the observation tiles) */
 int ocb_set_tuning(ocb_env* env, int lanes_per_world, int use_tma);
+/* the launch shape currently in effect (any out pointer may be NULL) */
+int ocb_get_tuning(const ocb_env* env, int* lanes_per_world, int* use_tma, int* warps_per_cta);
 
 /* ------------------------------------------------------- Overcooked: hot path */
 /* VectorMultiAgentEnv.n_reset (vectorenv.py:241-252 / SyncVectorEnv.n_reset 398-425):
