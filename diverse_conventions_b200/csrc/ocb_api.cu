@@ -33,7 +33,8 @@ struct ocb_env {
     uint64_t seed;
     uint64_t step_count;
     uint32_t world0;
-    int lanes_per_world;  // G
+    int lanes_per_world;  // G of the fused K-step launches
+    int step_lanes;       // G of single-step / observe launches (load + full rebuild dominate there)
     int use_tma;
     Tables h_tables;
     // device
@@ -140,6 +141,7 @@ extern "C" int ocb_create(const ocb_config* cfg, int device, uint32_t num_worlds
     e->L = 1 + 6 * e->P + 4 * e->S;
     e->seed = seed;
     e->lanes_per_world = default_lanes(e->N);
+    e->step_lanes = 8;
     e->use_tma = 1;
 
     DeviceGuard guard(device);
@@ -190,6 +192,7 @@ extern "C" uint64_t ocb_step_count(const ocb_env* e) { return e ? e->step_count 
 
 extern "C" int ocb_set_tuning(ocb_env* e, int lanes_per_world, int use_tma) {
     if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "env is NULL");
+    const bool explicit_lanes = lanes_per_world != 0;
     if (lanes_per_world == 0) lanes_per_world = default_lanes(e->N);
     if (lanes_per_world != 1 && lanes_per_world != 2 && lanes_per_world != 4 && lanes_per_world != 8)
         return fail(OCB_ERR_INVALID_ARG, "lanes_per_world must be 1, 2, 4 or 8");
@@ -198,6 +201,7 @@ extern "C" int ocb_set_tuning(ocb_env* e, int lanes_per_world, int use_tma) {
     int rc = pick_launch_shape(e, lanes_per_world, &warps, &smem);
     if (rc != OCB_OK) return rc;
     e->lanes_per_world = lanes_per_world;
+    e->step_lanes = explicit_lanes ? lanes_per_world : 8;
     e->use_tma = use_tma ? 1 : 0;
     return OCB_OK;
 }
@@ -245,9 +249,12 @@ static int run_rollout(ocb_env* e, int K, const void* actions, int act_dtype, in
     p.obs = obs, p.rew = rew, p.done = done;
     int warps;
     size_t smem;
-    int rc = pick_launch_shape(e, e->lanes_per_world, &warps, &smem);
+    // single steps are dominated by the state load and the full plane rebuild: spread each world over
+    // more lanes there (tools/step_latency.py); fused launches use the throughput-tuned shape
+    const int G = (observe_only || K <= 2) ? e->step_lanes : e->lanes_per_world;
+    int rc = pick_launch_shape(e, G, &warps, &smem);
     if (rc != OCB_OK) return rc;
-    cudaError_t err = launch_rollout(p, e->P, e->lanes_per_world, warps, smem, observe_only, (cudaStream_t)stream);
+    cudaError_t err = launch_rollout(p, e->P, G, warps, smem, observe_only, (cudaStream_t)stream);
     if (err != cudaSuccess) {
         cudaGetLastError();
         return fail(OCB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));

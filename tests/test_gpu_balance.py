@@ -71,7 +71,8 @@ def test_adapter_contract_and_reset_distribution():
     assert ob.action_mask.shape == (N, 4) and ob.action_mask.all()
     ob2, rew, done, info = env.step(torch.randint(0, 4, (N, 1), device="cuda"))
     assert rew.shape == (N,) and rew.dtype == torch.float32 and done.shape == (N,) and len(info) == N
-    assert set(np.unique(rew.cpu().numpy()).round(4).tolist()) <= {1.0, -0.2, -0.4, -0.6, -0.8, -1.0, -1.2, -1.4, -1.6, -2.0, -3.0}
+    seen = set(np.round(np.unique(rew.cpu().numpy()).astype(np.float64), 4).tolist())
+    assert seen <= {1.0, -0.2, -0.4, -0.6, -0.8, -1.0, -1.2, -1.4, -1.6, -2.0, -3.0}, seen
     # reset positions: uniform on {0..4}^2 (the reference draws them with numpy's randint)
     env.hard_reset()
     st = env.get_state()
