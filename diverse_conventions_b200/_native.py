@@ -52,6 +52,11 @@ PROTOTYPES = {
     "ocb_clear_episode_stats": (_i, [_vp, _vp]),
     "ocb_step_count": (_u64, [_vp]),
     "ocb_set_world_offset": (_i, [_vp, _u32]),
+    "ocb_policy_create": (_i, [ctypes.POINTER(ocb_config), _i, _i, _i, _pp]),
+    "ocb_policy_destroy": (_i, [_vp]),
+    "ocb_policy_set_weights": (_i, [_vp, _i, _i] + [_vp] * 8),
+    "ocb_policy_act": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _u64, _u64, _vp]),
+    "ocb_policy_value": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "bb_create": (_i, [_i, _u32, _u64, _pp]),
     "bb_destroy": (_i, [_vp]),
     "bb_num_worlds": (_i, [_vp]),

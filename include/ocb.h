@@ -176,6 +176,31 @@ uint64_t ocb_step_count(const ocb_env* env);
  * (a multi-GPU shard of rank r with N worlds per rank uses r*N); default 0 */
 int ocb_set_world_offset(ocb_env* env, uint32_t world0);
 
+/* ------------------------------------------------------- policy forward (MAPPO actor / critic) */
+/* Fused tensor-core forward of the reference's CNN actor / critic (R_Actor / R_Critic,
+ * train/MAPPO/r_actor_critic.py:12-71,142-197; CNNLayer train/MAPPO/utils/cnn.py:22-42;
+ * Categorical head train/MAPPO/utils/distributions.py:55-68) for hidden_size 64, 2 players.
+ * A handle holds n_policies (actor, critic) weight sets for one layout. */
+typedef struct ocb_policy ocb_policy;
+int ocb_policy_create(const ocb_config* cfg, int device, int hidden, int n_policies, ocb_policy** out);
+int ocb_policy_destroy(ocb_policy* pol);
+/* HOST fp32 weights in the reference's state-dict layouts: conv_w [32,20,3,3] (base.cnn.cnn.0),
+ * fc1_w [64, 32*(W-2)*(H-2)] (base.cnn.cnn.3), fc2_w [64,64] (base.cnn.cnn.5), head_w [6,64]
+ * (act.action_out.linear, net 0) or [1,64] (v_out, net 1), and the matching biases. */
+int ocb_policy_set_weights(ocb_policy* pol, int policy, int net, const float* conv_w, const float* conv_b,
+                           const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b,
+                           const float* head_w, const float* head_b);
+/* actor: obs int8 [M, W, H, C] (DEVICE) -> sampled (or arg-max) actions int32 [M], log-probs
+ * float [M], raw logits float [M,6]; any output may be NULL.  tile_policy int32 [ceil(M/128)]
+ * selects the weight set per 128-row tile (NULL = set 0) — the cross-play slice multiplexing of
+ * train/partner_agents.py:87-137 / train/XD/xd_player.py:177-230.  Sampling uses the counter RNG
+ * keyed by (seed, row, offset). */
+int ocb_policy_act(ocb_policy* pol, const int8_t* obs, int M, const int32_t* tile_policy, int32_t* actions,
+                   float* logp, float* logits, int deterministic, uint64_t seed, uint64_t offset, void* stream);
+/* critic: values float [M] */
+int ocb_policy_value(ocb_policy* pol, const int8_t* obs, int M, const int32_t* tile_policy, float* values,
+                     void* stream);
+
 /* ------------------------------------------------------- Balance-Beam */
 /* replaces BalanceBeamSimulator (src/balance_beam_env/mgr.cpp:191-233) behind
  * MadronaEnv.n_step / n_reset (vectorenv.py:306-343).
