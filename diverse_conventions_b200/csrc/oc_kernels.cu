@@ -260,6 +260,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, (G == 8 ? 6 : 4)) oc_rollout_k
         }
     }
     if (tma_pending && lane == 0) bulk_wait_read_all();
+    // device-side step counter: read by kernels launched after this one (policy sampling offset)
+    if (prm.step_counter != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *prm.step_counter += (unsigned long long)prm.K;
 
     // ---- store world state back
     if (valid) {

@@ -34,6 +34,7 @@ struct RolloutParams {
     int32_t* rew;          // [K][P][N] or nullptr
     int32_t* done;         // [K][N] or nullptr
     int use_tma;
+    unsigned long long* step_counter;  // device mirror of the global step counter (+= K per launch) or nullptr
 };
 
 size_t rollout_smem_bytes(int P, int S, int C, int G, int warps_per_cta);

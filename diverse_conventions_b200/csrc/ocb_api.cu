@@ -46,6 +46,7 @@ struct ocb_env {
     int32_t* d_cur_return;
     long long* d_ret_sum;
     int32_t* d_episodes;
+    unsigned long long* d_step_counter;  // device mirror of step_count
     // scratch for the host-buffer entry points
     int32_t* d_h_actions;
     int8_t* d_h_obs;
@@ -109,6 +110,7 @@ extern "C" int ocb_destroy(ocb_env* e) {
     cudaFree(e->d_cur_return);
     cudaFree(e->d_ret_sum);
     cudaFree(e->d_episodes);
+    cudaFree(e->d_step_counter);
     cudaFree(e->d_h_actions);
     cudaFree(e->d_h_obs);
     cudaFree(e->d_h_rew);
@@ -164,6 +166,8 @@ extern "C" int ocb_create(const ocb_config* cfg, int device, uint32_t num_worlds
     OCB_TRY(cudaMalloc(&e->d_cur_return, sizeof(int32_t) * N));
     OCB_TRY(cudaMalloc(&e->d_ret_sum, sizeof(long long) * N));
     OCB_TRY(cudaMalloc(&e->d_episodes, sizeof(int32_t) * N));
+    OCB_TRY(cudaMalloc(&e->d_step_counter, sizeof(unsigned long long)));
+    OCB_TRY(cudaMemset(e->d_step_counter, 0, sizeof(unsigned long long)));
     OCB_TRY(cudaMemcpy(e->d_tables, &e->h_tables, sizeof(Tables), cudaMemcpyHostToDevice));
     OCB_TRY(cudaMemcpy(e->d_tmpl, tmpl, e->SC, cudaMemcpyHostToDevice));
     OCB_TRY(cudaMemset(e->d_ret_sum, 0, sizeof(long long) * N));
@@ -235,6 +239,7 @@ static RolloutParams base_params(ocb_env* e) {
     p.cur_return = e->d_cur_return, p.ret_sum = e->d_ret_sum, p.episodes = e->d_episodes;
     p.N = e->N, p.seed = e->seed, p.world0 = e->world0, p.step0 = e->step_count;
     p.use_tma = e->use_tma;
+    p.step_counter = e->d_step_counter;
     return p;
 }
 
@@ -419,4 +424,36 @@ extern "C" int ocb_clear_episode_stats(ocb_env* e, void* stream) {
         return fail(OCB_ERR_CUDA, "clear_episode_stats: %s", cudaGetErrorString(err));
     }
     return OCB_OK;
+}
+
+// ------------------------------------------------------------------ device-resident policy rollout
+extern "C" const uint64_t* ocb_step_counter_device(const ocb_env* e) {
+    return e ? reinterpret_cast<const uint64_t*>(e->d_step_counter) : nullptr;
+}
+
+// T x (fused actor+critic forward on the current observations -> one env step), all launches on
+// `stream`, nothing synchronises; graph-capturable (the sampling offset is read from the device-side
+// step counter, so a replayed graph draws fresh actions).  Writes the PPO rollout buffer in place.
+extern "C" int ocb_rollout_policy(ocb_env* e, ocb_policy* pol, int T, const int32_t* tile_policy, int8_t* obs_slab,
+                                  int32_t* actions, float* logp, float* values, int32_t* reward, int32_t* done,
+                                  int deterministic, uint64_t seed, void* stream) {
+    if (e == nullptr || pol == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL handle");
+    if (obs_slab == nullptr || actions == nullptr || values == nullptr)
+        return fail(OCB_ERR_INVALID_ARG, "obs_slab, actions and values are required");
+    if (T < 1) return fail(OCB_ERR_INVALID_ARG, "T must be >= 1");
+    if (e->P != 2) return fail(OCB_ERR_UNSUPPORTED, "the policy rollout supports 2 players");
+    const size_t PN = (size_t)e->P * e->N, obs_step = PN * (size_t)e->SC;
+    const int M = (int)PN;
+    for (int t = 0; t < T; ++t) {
+        int rc = ocb_policy_forward(pol, obs_slab + t * obs_step, M, tile_policy, actions + t * PN,
+                                    logp ? logp + t * PN : nullptr, nullptr, values + t * PN, deterministic, seed, 0,
+                                    reinterpret_cast<const uint64_t*>(e->d_step_counter), stream);
+        if (rc != OCB_OK) return rc;
+        rc = ocb_step(e, actions + t * PN, obs_slab + (t + 1) * obs_step, reward ? reward + t * PN : nullptr,
+                      done ? done + (size_t)t * e->N : nullptr, stream);
+        if (rc != OCB_OK) return rc;
+    }
+    // bootstrap value of the observation after the last step (MainPlayer.compute_one,
+    // train/MAPPO/main_player.py:293-307)
+    return ocb_policy_value(pol, obs_slab + (size_t)T * obs_step, M, tile_policy, values + (size_t)T * PN, stream);
 }

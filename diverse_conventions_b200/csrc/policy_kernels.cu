@@ -4,20 +4,32 @@
 // 142-197; train/MAPPO/utils/cnn.py:22-42; hidden 64 as in every train/*.sh):
 //   obs int8 [M, W, H, C=20] -> Conv3x3(20->32) -> ReLU -> FC((W-2)(H-2)*32 -> 64) -> ReLU
 //   -> FC(64->64) -> ReLU -> head (6 logits, orthogonal gain 0.01 | 1 value).
-// One CTA (128 threads) owns a tile of 128 observation rows and runs the whole network:
-//   * the tile is converted once to bf16 and stored as per-cell [128 x 16] K-major operand
-//     blocks in shared memory; the convolution then needs NO im2col: for output position p
-//     the k-slice of window cell (dx,dy) is simply the block of cell (ox+dx, oy+dy), so the
-//     conv is 9 tcgen05.mma (M128 N32 K16) per position pointing at different blocks;
-//     the 5 static terrain channels are folded into a per-position bias on the host;
-//   * accumulators live in TMEM (conv 32 cols, FC1 64, FC2 64); each conv position is drained
-//     with tcgen05.ld, bias+ReLU'd and fed straight back as the A operand of FC1, which
-//     accumulates over positions in TMEM — activations never touch HBM;
+//
+// One persistent, warp-specialised kernel runs BOTH networks (even CTAs the actor, odd CTAs the
+// critic); a work unit is (tile of 128 observation rows, network):
+//   * loader warps (4): coalesced loads of one grid column of the tile ([128 rows] x H cells x
+//     20 B, software-prefetched in registers), transposed through a small staging buffer into
+//     per-cell [128 x 16] bf16 K-major operand blocks held in a ring of 4 grid columns.  The
+//     convolution needs NO im2col: for output position (ox, oy) the k-slice of window cell
+//     (dx, dy) is the block of cell (ox+dx, oy+dy), so the conv is 9 x (hi, lo) tcgen05.mma
+//     (M128 N32 K16) per position pointing at different blocks; the 5 static terrain channels
+//     are folded into a per-position bias on the host;
+//   * one MMA thread issues every tcgen05.mma; accumulators live in TMEM (conv: 4 stages x 32
+//     columns, FC1 and FC2: 2 x 64 columns each, double-buffered across units) and the issue
+//     order keeps the conv up to 3 positions ahead of the FC1 partial sums so the tensor pipe
+//     has work while the epilogue warps run;
+//   * epilogue warps (4): tcgen05.ld a conv position, bias + ReLU, split into bf16 hi + lo and
+//     store it as the A operand of the FC1 partial product of that position (2-stage ring);
+//     FC2 flows through the same ring as two more K=32 items fed from the FC1 accumulator;
+//     the tiny head (64 -> 6 | 1), softmax sampling and log-prob run in fp32 on CUDA cores;
+//   * one producer thread streams the FC weights as 8 KB chunks with cp.async.bulk
+//     (global -> shared, mbarrier complete_tx) into a ring; when the whole set fits the ring
+//     the chunks stay resident and are only re-fetched when a tile selects another policy;
 //   * precision: operands are bf16 hi+lo splits (x = hi + lo, 3 products, fp32 accumulate),
 //     observations are exact in bf16, so logits agree with the fp32 reference to ~1e-5
-//     relative (the 1e-3 bar of the north star is not reachable with plain bf16 operands,
-//     see tests/test_policy_precision.py);
-//   * the tiny head (64 -> 6 | 1), softmax sampling and log-prob run in fp32 on CUDA cores.
+//     relative (the 1e-3 bar of the north star is not reachable with plain bf16 operands);
+//   * activations never touch HBM; per unit the kernel reads the tile's observations once.
+// All inter-role hand-offs are mbarriers; waits are bounded spins that trap instead of hanging.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -34,23 +46,32 @@ using namespace ocb;
 
 namespace {
 
-constexpr int kRows = 128;     // rows (agents) per CTA == UMMA M
+constexpr int kRows = 128;     // rows (agents) per tile == UMMA M
 constexpr int kHid = 64;       // hidden size
 constexpr int kCo = 32;        // conv output channels (hidden / 2)
 constexpr int kSlots = 16;     // bf16 slots per cell: channels 0-9, 15-19, one zero pad
 constexpr int kK1 = 9 * kSlots;  // conv K
 constexpr int kCellBlock = kRows * kSlots * 2;  // 4096 B
-constexpr int kTmemCols = 256;
-constexpr int kColD1 = 0, kColD2 = 32, kColD3 = 96;
+constexpr int kColRing = 4;    // grid columns resident per CTA (3 in use by the conv + 1 being loaded)
+constexpr int kD1Stages = 4;   // conv accumulators in flight
+constexpr int kConvAhead = 3;  // conv positions issued ahead of their FC1 item (< kD1Stages, see mma_role)
+constexpr int kChunk = 8192;   // one FC weight chunk: [64 x 32] bf16 hi | lo
+constexpr int kA2Stage = 16384;  // one FC A-operand stage: [128 x 32] bf16 hi | lo
+constexpr int kMaxRing = 16;   // weight-ring slots (resident when >= chunks per unit)
+constexpr int kMaxH = 6;       // a grid column must fit one warp-wide load (5*H words <= 32)
+constexpr int kThreads = 320;  // warps 0-3 epilogue, 4-7 loader, 8 MMA issuer, 9 weight producer
+constexpr int kTmemCols = 512;
+constexpr int kColD1 = 0, kColD2 = 128, kColD3 = 256;
+constexpr int kSmemBudget = 227 * 1024 - 256;
 
-// packed weight blob of one network (byte offsets; all 128-B aligned)
+// packed weight blob of one network: a resident "head" followed by 8 KB FC chunks
 struct BlobLayout {
     int wc_hi, wc_lo;    // [32 x 144] bf16 canonical, 9216 B each
-    int w2_hi, w2_lo;    // [64 x 64], 8192 B each
-    int w1_hi, w1_lo;    // npos x [64 x 32], 4096 B per position each
     int bias1;           // [npos][32] fp32 (conv bias + static terrain contribution)
     int b1, b2;          // [64] fp32
     int wh, bh;          // [8][64] fp32 (rows >= head_out are zero), [8] fp32
+    int head_bytes;      // everything above (multiple of 128)
+    int chunks;          // npos FC1 chunks + 2 FC2 chunks (K halves)
     int total;
 };
 __host__ __device__ inline int al128(int x) { return (x + 127) & ~127; }
@@ -59,36 +80,67 @@ __host__ __device__ inline BlobLayout blob_layout(int npos) {
     int o = 0;
     L.wc_hi = o, o += 9216;
     L.wc_lo = o, o += 9216;
-    L.w2_hi = o, o += 8192;
-    L.w2_lo = o, o += 8192;
     L.bias1 = o, o += al128(npos * kCo * 4);
     L.b1 = o, o += 256;
     L.b2 = o, o += 256;
     L.wh = o, o += 8 * kHid * 4;
     L.bh = o, o += 128;
-    L.w1_hi = o, o += npos * 4096;
-    L.w1_lo = o, o += npos * 4096;
-    L.total = o;
+    L.head_bytes = o;
+    L.chunks = npos + 2;
+    L.total = o + L.chunks * kChunk;
     return L;
 }
-// the part of the blob that is copied to shared memory once per CTA (everything before w1)
-__host__ __device__ inline int blob_resident_bytes(int npos) { return blob_layout(npos).w1_hi; }
 
 struct PolicyParams {
     const uint8_t* blobs;     // [n_policies][2 nets][blob]
     size_t blob_stride;       // bytes between nets
-    int n_policies;
     int W, H, S, SC, npos;
-    int net;                  // 0 actor, 1 critic
     const int8_t* obs;        // [M][SC]
-    int M;
-    const int32_t* tile_policy;  // [ceil(M/128)] or nullptr
+    int M, tiles;
+    const int32_t* tile_policy;  // [tiles] or nullptr
     float* logits;            // [M][6] or nullptr
     int32_t* actions;         // [M] or nullptr
     float* logp;              // [M] or nullptr
     float* values;            // [M] or nullptr
     int deterministic;
     unsigned long long seed, offset;
+    const unsigned long long* d_offset;  // optional device-resident addend of `offset`
+    int net_mask;             // 1 actor, 2 critic, 3 both (even CTAs actor, odd critic)
+    int ring;                 // weight-ring slots in shared memory
+    int stage_stride;         // words per row of the loader staging buffer (odd)
+};
+
+// shared-memory carve-up (byte offsets from a 128-byte aligned base)
+struct SmemLayout {
+    int cols, stage, head, a2, wring, bars, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int H, int npos, int ring, int stage_stride) {
+    SmemLayout s;
+    int o = 0;
+    s.cols = o, o += kColRing * H * kCellBlock;
+    s.stage = o, o += al128(4 * 32 * stage_stride * 4);
+    s.head = o, o += blob_layout(npos).head_bytes;
+    s.a2 = o, o += 2 * kA2Stage;
+    s.wring = o, o += ring * kChunk;
+    s.bars = o, o += 512;
+    s.total = o + 128;  // slack for aligning the dynamic base
+    return s;
+}
+
+// barrier indices inside the 512-byte barrier block (8 bytes each); [60] holds the TMEM base
+enum : int {
+    B_COL_FULL = 0,                      // [4]  loader -> MMA (128 arrivals)
+    B_COL_EMPTY = 4,                     // [4]  MMA commit -> loader
+    B_D1_FULL = 8,                       // [4]  MMA commit -> epilogue
+    B_A2_FULL = 12,                      // [2]  epilogue -> MMA (128 arrivals)
+    B_A2_EMPTY = 14,                     // [2]  MMA commit -> epilogue
+    B_W_FULL = 16,                       // [16] bulk copy complete_tx -> MMA
+    B_W_EMPTY = 32,                      // [16] MMA commit -> producer
+    B_HEAD_FULL = 48,                    //      bulk copy -> MMA, epilogue
+    B_HEAD_EMPTY = 49,                   // [2]  by unit parity: MMA commit + 128 epilogue arrivals -> producer
+    B_D2_FULL = 51,                      //      MMA commit -> epilogue
+    B_D3_FULL = 52,                      //      MMA commit -> epilogue
+    B_COUNT = 53
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -118,8 +170,14 @@ __device__ __forceinline__ void umma_commit(uint32_t mbar) {
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-    // bounded spin: a tensor-core pipeline that never signals traps instead of hanging the GPU
+    // bounded spin: a pipeline that never signals traps instead of hanging the GPU
     for (uint32_t spins = 0;; ++spins) {
         uint32_t ok;
         asm volatile(
@@ -130,8 +188,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
             : "r"(mbar), "r"(parity)
             : "memory");
         if (ok) return;
-        if (spins > (1u << 22)) __trap();
+        if (spins > (1u << 24)) __trap();
     }
+}
+// global -> shared bulk copy that completes `bytes` of transaction count on `mbar`
+__device__ __forceinline__ void bulk_g2s(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst),
+                 "l"(gsrc), "r"(bytes), "r"(mbar)
+                 : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -154,44 +218,363 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);  // .x = a (low half), .y = b
-    return *reinterpret_cast<const uint32_t*>(&v);
-}
-// x -> (hi, lo) with hi = bf16(x), lo = bf16(x - hi); eight values -> two 16-byte operand chunks
-__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
-    float h[8], l[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        h[i] = __bfloat162float(__float2bfloat16_rn(x[i]));
-        l[i] = x[i] - h[i];
-    }
-    hi = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-    lo = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+// (x0, x1) -> packed bf16 pair of the high parts and of the residuals: x = hi + lo
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);  // .x = x0 (low half)
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xFFFF0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 // small unsigned int (observation byte) -> bf16 bits, exact
 __device__ __forceinline__ uint32_t byte_bf16(uint32_t b) { return __float_as_uint((float)b) >> 16; }
 
-// ---------------------------------------------------------------- the kernel
-__global__ void __launch_bounds__(kRows, 1) policy_fwd_kernel(const PolicyParams prm) {
-    extern __shared__ __align__(128) uint8_t smem[];
+// ---------------------------------------------------------------- unit iteration shared by all roles
+struct UnitRange {
+    int net, t0, t1;
+};
+__device__ __forceinline__ UnitRange my_units(const PolicyParams& prm) {
+    UnitRange u;
+    int c, g;
+    if (prm.net_mask == 3) {
+        u.net = blockIdx.x & 1, c = blockIdx.x >> 1, g = gridDim.x >> 1;
+    } else {
+        u.net = prm.net_mask == 1 ? 0 : 1, c = blockIdx.x, g = gridDim.x;
+    }
+    u.t0 = (int)(((long long)c * prm.tiles) / g);
+    u.t1 = (int)(((long long)(c + 1) * prm.tiles) / g);
+    return u;
+}
+__device__ __forceinline__ int tile_pol(const PolicyParams& prm, int t) { return prm.tile_policy ? prm.tile_policy[t] : 0; }
+// does tile t need another weight set than the previous tile of this CTA
+__device__ __forceinline__ bool blob_changed(const PolicyParams& prm, int t, int t0) {
+    return t == t0 || (prm.tile_policy != nullptr && prm.tile_policy[t] != prm.tile_policy[t - 1]);
+}
+
+// ---------------------------------------------------------------- roles
+// loader: global observations -> bf16 cell blocks, one grid column at a time
+__device__ __forceinline__ void loader_role(const PolicyParams& prm, const UnitRange ur, uint8_t* s_cols, uint32_t* s_stage,
+                                            uint32_t bars) {
+    const int lw = (threadIdx.x >> 5) - 4, lane = threadIdx.x & 31;
+    const int W = prm.W, H = prm.H, SC4 = prm.SC >> 2, seg = 5 * H, stride = prm.stage_stride;
+    uint32_t* stg = s_stage + lw * 32 * stride;
+    const uint32_t* obs32 = reinterpret_cast<const uint32_t*>(prm.obs);
+    const int rloc = lw * 32 + lane;                           // this thread's row inside the tile (convert phase)
+    const int roff = (rloc >> 3) * 256 + (rloc & 7) * 16;      // its place inside a [128 x 16] block
+    uint32_t pre[32];
+
+    auto issue_loads = [&](int t, int x) {
+        const long long r0 = (long long)t * kRows + lw * 32;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            long long row = r0 + r;
+            row = row < prm.M ? row : prm.M - 1;
+            pre[r] = lane < seg ? __ldg(obs32 + row * SC4 + x * seg + lane) : 0u;
+        }
+    };
+    if (ur.t0 < ur.t1) issue_loads(ur.t0, 0);
+    uint32_t gc = 0;  // running column counter: ring slot and phase
+    for (int t = ur.t0; t < ur.t1; ++t) {
+        for (int x = 0; x < W; ++x, ++gc) {
+            if (lane < seg) {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) stg[r * stride + lane] = pre[r];
+            }
+            __syncwarp();
+            if (x + 1 < W) issue_loads(t, x + 1);
+            else if (t + 1 < ur.t1) issue_loads(t + 1, 0);
+            const int slot = gc % kColRing;
+            if (gc >= kColRing) mbar_wait(bars + 8 * (B_COL_EMPTY + slot), ((gc / kColRing) - 1) & 1);
+            const uint32_t* mine = stg + lane * stride;
+            for (int y = 0; y < H; ++y) {
+                uint32_t w[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) w[q] = mine[y * 5 + q];
+                auto by = [&](int ch) { return (w[ch >> 2] >> ((ch & 3) * 8)) & 0xFFu; };
+                // chunk 0: channels 0..7 ; chunk 1: channels 8, 9, 15, 16, 17, 18, 19, pad
+                const uint4 c0 = make_uint4(byte_bf16(by(0)) | (byte_bf16(by(1)) << 16), byte_bf16(by(2)) | (byte_bf16(by(3)) << 16),
+                                            byte_bf16(by(4)) | (byte_bf16(by(5)) << 16), byte_bf16(by(6)) | (byte_bf16(by(7)) << 16));
+                const uint4 c1 = make_uint4(byte_bf16(by(8)) | (byte_bf16(by(9)) << 16), byte_bf16(by(15)) | (byte_bf16(by(16)) << 16),
+                                            byte_bf16(by(17)) | (byte_bf16(by(18)) << 16), byte_bf16(by(19)));
+                uint8_t* blk = s_cols + (size_t)(slot * H + y) * kCellBlock + roff;
+                *reinterpret_cast<uint4*>(blk) = c0;
+                *reinterpret_cast<uint4*>(blk + 128) = c1;
+            }
+            proxy_fence();
+            mbar_arrive(bars + 8 * (B_COL_FULL + slot));
+            __syncwarp();  // the staging rows are rewritten by the next column
+        }
+    }
+}
+
+// producer: weight head (conv weights, biases, head) and the FC chunk ring
+__device__ __forceinline__ void producer_role(const PolicyParams& prm, const UnitRange ur, const BlobLayout L, uint32_t s_head,
+                                              uint32_t s_wring, uint32_t bars) {
+    const int R = prm.ring;
+    const bool resident = R >= L.chunks;
+    const int Reff = resident ? L.chunks : R;
+    uint32_t wc = 0, u = 0;
+    for (int t = ur.t0; t < ur.t1; ++t, ++u) {
+        const bool chg = blob_changed(prm, t, ur.t0);
+        const uint8_t* blob = prm.blobs + ((size_t)tile_pol(prm, t) * 2 + ur.net) * prm.blob_stride;
+        if (chg) {
+            // the previous unit must be completely done with the head (conv MMAs, biases, head weights);
+            // arrivals alternate between two barriers so that a late waiter cannot alias an older phase
+            if (u > 0) mbar_wait(bars + 8 * (B_HEAD_EMPTY + ((u - 1) & 1)), ((u - 1) >> 1) & 1);
+            mbar_arrive_expect_tx(bars + 8 * B_HEAD_FULL, (uint32_t)L.head_bytes);
+            bulk_g2s(s_head, blob, (uint32_t)L.head_bytes, bars + 8 * B_HEAD_FULL);
+        }
+        const bool load = !resident || chg;
+        for (int j = 0; j < L.chunks; ++j, ++wc) {
+            const int slot = wc % Reff;
+            if (wc >= (uint32_t)Reff) mbar_wait(bars + 8 * (B_W_EMPTY + slot), ((wc / Reff) - 1) & 1);
+            if (load) {
+                mbar_arrive_expect_tx(bars + 8 * (B_W_FULL + slot), kChunk);
+                bulk_g2s(s_wring + slot * kChunk, blob + L.head_bytes + (size_t)j * kChunk, kChunk, bars + 8 * (B_W_FULL + slot));
+            }
+        }
+    }
+}
+
+// MMA issuer (one thread)
+__device__ __forceinline__ void mma_role(const PolicyParams& prm, const UnitRange ur, const BlobLayout L, uint32_t tmem,
+                                         uint32_t a_cols, uint32_t a_head, uint32_t a_a2, uint32_t a_wring, uint32_t bars) {
+    const int W = prm.W, H = prm.H, PH = H - 2, npos = prm.npos;
+    const int R = prm.ring;
+    const bool resident = R >= L.chunks;
+    const int Reff = resident ? L.chunks : R;
+    const uint32_t idesc32 = make_idesc(kRows, kCo), idesc64 = make_idesc(kRows, kHid);
+    const uint32_t a_wchi = a_head + L.wc_hi, a_wclo = a_head + L.wc_lo;
+
+    // conv stream
+    int tc = ur.t0, pc = 0;
+    uint32_t gcb = 0;          // running column index of column 0 of unit tc
+    uint32_t convs = 0;        // conv positions issued
+    // item stream (FC1 positions, then the two FC2 halves of each unit)
+    int ti = ur.t0, ji = 0;
+    uint32_t fc1s = 0;         // FC1 items issued
+    uint32_t items = 0;        // items issued (A2 ring counter)
+    uint32_t wc = 0;           // weight chunk counter
+    uint32_t ui = 0;           // unit counter of the item stream
+    uint32_t head_gen = 0;     // head loads waited for so far (conv stream)
+    uint32_t w_gen = 0;        // resident mode: ring fills waited for so far (item stream)
+    bool w_loaded = false;
+
+    while (ti < ur.t1) {
+        // keep the conv ahead of the FC items, but never across a change of weights (the new head is only
+        // loaded once the previous unit has drained completely)
+        const bool conv_ok = tc < ur.t1 && (int)(convs - fc1s) < kConvAhead && (tc == ti || !blob_changed(prm, tc, ur.t0));
+        if (conv_ok) {
+            const int ox = pc / PH, oy = pc - ox * PH;
+            if (pc == 0 && blob_changed(prm, tc, ur.t0)) {
+                mbar_wait(bars + 8 * B_HEAD_FULL, head_gen & 1);
+                ++head_gen;
+            }
+            if (oy == 0) {  // new window column(s)
+                for (int d = (ox == 0 ? 0 : 2); d < 3; ++d) {
+                    const uint32_t g = gcb + ox + d;
+                    mbar_wait(bars + 8 * (B_COL_FULL + g % kColRing), (g / kColRing) & 1);
+                }
+            }
+            tc_fence_after();
+            const uint32_t d1 = tmem + kColD1 + (convs % kD1Stages) * kCo;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const int dx = j / 3, dy = j - dx * 3;
+                const uint32_t blk = a_cols + (((gcb + ox + dx) % kColRing) * H + oy + dy) * kCellBlock;
+                const uint64_t da = make_desc(blk, 128, 256);
+                umma_bf16(d1, da, make_desc(a_wchi + j * 256, 128, 2304), idesc32, j > 0);
+                umma_bf16(d1, da, make_desc(a_wclo + j * 256, 128, 2304), idesc32, 1);
+            }
+            umma_commit(bars + 8 * (B_D1_FULL + convs % kD1Stages));
+            if (oy == PH - 1) {  // the window leaves column ox (and the last two columns with the last window)
+                umma_commit(bars + 8 * (B_COL_EMPTY + (gcb + ox) % kColRing));
+                if (ox == W - 3) {
+                    umma_commit(bars + 8 * (B_COL_EMPTY + (gcb + ox + 1) % kColRing));
+                    umma_commit(bars + 8 * (B_COL_EMPTY + (gcb + ox + 2) % kColRing));
+                }
+            }
+            ++convs;
+            if (++pc == npos) {
+                // last conv of the unit: the conv weights of the head are free once these MMAs complete
+                umma_commit(bars + 8 * (B_HEAD_EMPTY + ((uint32_t)(tc - ur.t0) & 1)));
+                pc = 0, ++tc, gcb += W;
+            }
+            continue;
+        }
+        // ---- one FC item: D2 (+)= A2 x W1_j   or   D3 (+)= A2 x W2_half
+        if (ji == 0) {
+            w_loaded = !resident || blob_changed(prm, ti, ur.t0);
+            if (resident && w_loaded) ++w_gen;
+        }
+        const int a2s = items & 1;
+        const int slot = wc % Reff;
+        mbar_wait(bars + 8 * (B_A2_FULL + a2s), (items >> 1) & 1);
+        if (w_loaded) mbar_wait(bars + 8 * (B_W_FULL + slot), resident ? ((w_gen - 1) & 1) : ((wc / Reff) & 1));
+        tc_fence_after();
+        const uint32_t dst = tmem + (ji < npos ? kColD2 : kColD3) + (ui & 1) * kHid;
+        const bool first = (ji == 0 || ji == npos);
+        const uint32_t a_hi = a_a2 + a2s * kA2Stage, a_lo = a_hi + 8192;
+        const uint32_t b_hi = a_wring + slot * kChunk, b_lo = b_hi + 4096;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t ahi = make_desc(a_hi + ks * 256, 128, 512), alo = make_desc(a_lo + ks * 256, 128, 512);
+            const uint64_t bhi = make_desc(b_hi + ks * 256, 128, 512), blo = make_desc(b_lo + ks * 256, 128, 512);
+            umma_bf16(dst, ahi, bhi, idesc64, (!first || ks != 0) ? 1u : 0u);
+            umma_bf16(dst, ahi, blo, idesc64, 1);
+            umma_bf16(dst, alo, bhi, idesc64, 1);
+        }
+        umma_commit(bars + 8 * (B_A2_EMPTY + a2s));
+        umma_commit(bars + 8 * (B_W_EMPTY + slot));
+        if (ji == npos - 1) umma_commit(bars + 8 * B_D2_FULL);
+        if (ji == npos + 1) umma_commit(bars + 8 * B_D3_FULL);
+        ++items, ++wc;
+        if (ji < npos) ++fc1s;
+        if (++ji == npos + 2) ji = 0, ++ti, ++ui;
+    }
+}
+
+// epilogue: TMEM -> bias/ReLU -> bf16 hi/lo A operand; head, sampling and outputs
+__device__ __forceinline__ void epilogue_role(const PolicyParams& prm, const UnitRange ur, const BlobLayout L, uint32_t tmem,
+                                              const uint8_t* s_head, uint8_t* s_a2, uint32_t bars) {
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int S = prm.S, SC = prm.SC, npos = prm.npos, H = prm.H;
-    const BlobLayout L = blob_layout(npos);
-    const int resident = L.w1_hi;
+    const int npos = prm.npos;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
+    const int roff = (tid >> 3) * 512 + (tid & 7) * 16;          // row position inside a [128 x 32] operand
+    const float* s_bias1 = reinterpret_cast<const float*>(s_head + L.bias1);
+    const float* s_b1 = reinterpret_cast<const float*>(s_head + L.b1);
+    const float* s_b2 = reinterpret_cast<const float*>(s_head + L.b2);
+    const float* s_wh = reinterpret_cast<const float*>(s_head + L.wh);
+    const float* s_bh = reinterpret_cast<const float*>(s_head + L.bh);
+    unsigned long long offset = prm.offset;
+    if (prm.d_offset != nullptr) offset += *prm.d_offset;
 
-    // shared-memory carve-up
-    uint8_t* s_cells = smem;                           // S x 4096 (later reused for the FC2 operand)
-    uint8_t* s_blob = s_cells + (size_t)S * kCellBlock;  // resident part of the weight blob
-    uint8_t* s_w1hi = s_blob + resident;               // 4096
-    uint8_t* s_w1lo = s_w1hi + 4096;                   // 4096
-    uint8_t* s_a2hi = s_w1lo + 4096;                   // 8192
-    uint8_t* s_a2lo = s_a2hi + 8192;                   // 8192
-    uint64_t* s_mbar = reinterpret_cast<uint64_t*>(s_a2lo + 8192);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_mbar + 1);
+    uint32_t d1c = 0, items = 0, u = 0, head_gen = 0;
+    for (int t = ur.t0; t < ur.t1; ++t, ++u) {
+        if (blob_changed(prm, t, ur.t0)) {
+            mbar_wait(bars + 8 * B_HEAD_FULL, head_gen & 1);
+            ++head_gen;
+        }
+        for (int j = 0; j < npos + 2; ++j, ++items) {
+            float v[32];
+            const float* bias;
+            if (j < npos) {
+                const int st = d1c % kD1Stages;
+                mbar_wait(bars + 8 * (B_D1_FULL + st), (d1c / kD1Stages) & 1);
+                tc_fence_after();
+                tmem_ld32(trow + kColD1 + st * kCo, v);
+                ++d1c;
+                bias = s_bias1 + j * kCo;
+            } else {
+                if (j == npos) {
+                    mbar_wait(bars + 8 * B_D2_FULL, u & 1);
+                    tc_fence_after();
+                }
+                tmem_ld32(trow + kColD2 + (u & 1) * kHid + (j - npos) * 32, v);
+                bias = s_b1 + (j - npos) * 32;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[i], 0.0f);
+            const int a2s = items & 1;
+            if (items >= 2) mbar_wait(bars + 8 * (B_A2_EMPTY + a2s), ((items >> 1) - 1) & 1);
+            uint8_t* hi_base = s_a2 + a2s * kA2Stage + roff;
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {
+                uint4 hi, lo;
+                split2(v[kc * 8 + 0], v[kc * 8 + 1], hi.x, lo.x);
+                split2(v[kc * 8 + 2], v[kc * 8 + 3], hi.y, lo.y);
+                split2(v[kc * 8 + 4], v[kc * 8 + 5], hi.z, lo.z);
+                split2(v[kc * 8 + 6], v[kc * 8 + 7], hi.w, lo.w);
+                *reinterpret_cast<uint4*>(hi_base + kc * 128) = hi;
+                *reinterpret_cast<uint4*>(hi_base + 8192 + kc * 128) = lo;
+            }
+            proxy_fence();
+            tc_fence_before();
+            mbar_arrive(bars + 8 * (B_A2_FULL + a2s));
+        }
 
-    const int pol = prm.tile_policy ? prm.tile_policy[blockIdx.x] : 0;
-    const uint8_t* blob = prm.blobs + ((size_t)pol * 2 + prm.net) * prm.blob_stride;
+        // ---- FC2 epilogue + head (fp32 on CUDA cores)
+        float head[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) head[a] = s_bh[a];
+        mbar_wait(bars + 8 * B_D3_FULL, u & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tmem_ld32(trow + kColD3 + (u & 1) * kHid + half * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float h = fmaxf(v[i] + s_b2[half * 32 + i], 0.0f);
+#pragma unroll
+                for (int a = 0; a < 6; ++a) head[a] = fmaf(h, s_wh[a * kHid + half * 32 + i], head[a]);
+            }
+        }
+        tc_fence_before();
+        mbar_arrive(bars + 8 * (B_HEAD_EMPTY + (u & 1)));  // done with the head block of this unit
+
+        const long long row = (long long)t * kRows + tid;
+        if (row < prm.M) {
+            if (ur.net == 1) {
+                if (prm.values) prm.values[row] = head[0];
+            } else {
+                if (prm.logits) {
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) prm.logits[row * 6 + a] = head[a];
+                }
+                if (prm.actions || prm.logp) {
+                    // FixedCategorical(logits): sample / mode and log-prob (train/MAPPO/utils/distributions.py:14-28)
+                    float mx = head[0];
+#pragma unroll
+                    for (int a = 1; a < 6; ++a) mx = fmaxf(mx, head[a]);
+                    float e[6], sum = 0.0f;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) e[a] = expf(head[a] - mx), sum += e[a];
+                    int act = 0;
+                    if (prm.deterministic) {
+#pragma unroll
+                        for (int a = 1; a < 6; ++a) act = (head[a] > head[act]) ? a : act;
+                    } else {
+                        uint32_t r[4] = {(uint32_t)row, (uint32_t)offset, (uint32_t)(offset >> 32), 0x5A17u};
+                        philox4x32_10(r, (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
+                        const float uu = (float)(r[0] >> 8) * (1.0f / 16777216.0f) * sum;
+                        float cum = 0.0f;
+                        act = 5;  // inverse CDF; falls through to the last action on round-off
+                        bool found = false;
+#pragma unroll
+                        for (int a = 0; a < 6; ++a) {
+                            cum += e[a];
+                            if (!found && uu < cum) act = a, found = true;
+                        }
+                    }
+                    if (prm.actions) prm.actions[row] = act;
+                    if (prm.logp) {
+                        float la = head[0];
+#pragma unroll
+                        for (int a = 1; a < 6; ++a) la = (act == a) ? head[a] : la;
+                        prm.logp[row] = la - mx - logf(sum);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(kThreads, 1) policy_fwd_kernel(const PolicyParams prm) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const BlobLayout L = blob_layout(prm.npos);
+    const SmemLayout sl = smem_layout(prm.H, prm.npos, prm.ring, prm.stage_stride);
+    uint8_t* s_cols = smem + sl.cols;
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(smem + sl.stage);
+    uint8_t* s_head = smem + sl.head;
+    uint8_t* s_a2 = smem + sl.a2;
+    uint8_t* s_wring = smem + sl.wring;
+    uint64_t* s_bars = reinterpret_cast<uint64_t*>(smem + sl.bars);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bars + 60);
+    const uint32_t bars = smem_addr(s_bars);
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)),
@@ -199,228 +582,35 @@ __global__ void __launch_bounds__(kRows, 1) policy_fwd_kernel(const PolicyParams
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 0) {
-        mbar_init(smem_addr(s_mbar), 1);
+    if (tid == 32) {
+        for (int i = 0; i < B_COUNT; ++i) {
+            uint32_t count = 1;
+            if ((i >= B_COL_FULL && i < B_COL_FULL + 4) || (i >= B_A2_FULL && i < B_A2_FULL + 2)) count = 128;
+            if (i >= B_HEAD_EMPTY && i < B_HEAD_EMPTY + 2) count = 129;
+            mbar_init(bars + 8 * i, count);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // resident weights: global -> shared, 16-byte copies
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(blob);
-        uint4* dst = reinterpret_cast<uint4*>(s_blob);
-        for (int i = tid; i < resident / 16; i += kRows) dst[i] = __ldg(src + i);
-    }
-    // this thread's observation row -> bf16 cell blocks
-    const long long row = (long long)blockIdx.x * kRows + tid;
-    const bool valid = row < prm.M;
-    {
-        const uint32_t* orow = reinterpret_cast<const uint32_t*>(prm.obs + (size_t)(valid ? row : prm.M - 1) * SC);
-        const int roff = (tid >> 3) * 256 + (tid & 7) * 16;  // row position inside a [128 x 16] block
-        for (int cell = 0; cell < S; ++cell) {
-            uint32_t w[5];
-#pragma unroll
-            for (int q = 0; q < 5; ++q) w[q] = __ldg(orow + cell * 5 + q);
-            auto by = [&](int ch) { return (w[ch >> 2] >> ((ch & 3) * 8)) & 0xFFu; };
-            // chunk 0: channels 0..7 ; chunk 1: channels 8, 9, 15, 16, 17, 18, 19, pad
-            const uint4 c0 = make_uint4(byte_bf16(by(0)) | (byte_bf16(by(1)) << 16), byte_bf16(by(2)) | (byte_bf16(by(3)) << 16),
-                                        byte_bf16(by(4)) | (byte_bf16(by(5)) << 16), byte_bf16(by(6)) | (byte_bf16(by(7)) << 16));
-            const uint4 c1 = make_uint4(byte_bf16(by(8)) | (byte_bf16(by(9)) << 16), byte_bf16(by(15)) | (byte_bf16(by(16)) << 16),
-                                        byte_bf16(by(17)) | (byte_bf16(by(18)) << 16), byte_bf16(by(19)));
-            uint8_t* blk = s_cells + (size_t)cell * kCellBlock + roff;
-            *reinterpret_cast<uint4*>(blk) = c0;
-            *reinterpret_cast<uint4*>(blk + 128) = c1;
-        }
-    }
-    proxy_fence();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
-    const uint32_t mbar = smem_addr(s_mbar);
-    uint32_t phase = 0;
+    const UnitRange ur = my_units(prm);
 
-    const uint32_t a_cells = smem_addr(s_cells), a_wchi = smem_addr(s_blob + L.wc_hi), a_wclo = smem_addr(s_blob + L.wc_lo);
-    const uint32_t a_w1hi = smem_addr(s_w1hi), a_w1lo = smem_addr(s_w1lo), a_a2hi = smem_addr(s_a2hi), a_a2lo = smem_addr(s_a2lo);
-    const uint32_t idesc32 = make_idesc(kRows, kCo), idesc64 = make_idesc(kRows, kHid);
-    const float* s_bias1 = reinterpret_cast<const float*>(s_blob + L.bias1);
-    const int PH = H - 2;  // positions are enumerated p = ox * (H-2) + oy
-
-    for (int p = 0; p < npos; ++p) {
-        const int ox = p / PH, oy = p % PH;
-        if (tid == 0) {
-            // conv: D1[128 x 32] = sum over the 9 window cells of block(cell) x Wc[k-slice], W = hi + lo
-#pragma unroll
-            for (int j = 0; j < 9; ++j) {
-                const int cell = (ox + j / 3) * H + (oy + j % 3);
-                const uint64_t da = make_desc(a_cells + cell * kCellBlock, 128, 256);
-                umma_bf16(tmem + kColD1, da, make_desc(a_wchi + j * 256, 128, 2304), idesc32, j > 0);
-                umma_bf16(tmem + kColD1, da, make_desc(a_wclo + j * 256, 128, 2304), idesc32, 1);
-            }
-            umma_commit(mbar);
-        }
-        // FC1 weights of this position (after the wait: the previous position's FC1 MMAs, which read
-        // the same buffers, were issued before this commit and are therefore complete too)
-        mbar_wait(mbar, phase);
-        phase ^= 1;
-        tc_fence_after();
-        {
-            const uint4* shi = reinterpret_cast<const uint4*>(blob + L.w1_hi + (size_t)p * 4096);
-            const uint4* slo = reinterpret_cast<const uint4*>(blob + L.w1_lo + (size_t)p * 4096);
-            uint4* dhi = reinterpret_cast<uint4*>(s_w1hi);
-            uint4* dlo = reinterpret_cast<uint4*>(s_w1lo);
-            for (int i = tid; i < 256; i += kRows) dhi[i] = __ldg(shi + i), dlo[i] = __ldg(slo + i);
-        }
-        // drain D1: bias (+ static terrain part), ReLU, split, store as FC1 A operand [128 x 32]
-        {
-            float v[32];
-            tmem_ld32(trow + kColD1, v);
-            const float* b = s_bias1 + p * kCo;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b[i], 0.0f);
-            const int roff = (tid >> 3) * 512 + (tid & 7) * 16;
-#pragma unroll
-            for (int kc = 0; kc < 4; ++kc) {
-                uint4 hi, lo;
-                split8(v + kc * 8, hi, lo);
-                *reinterpret_cast<uint4*>(s_a2hi + roff + kc * 128) = hi;
-                *reinterpret_cast<uint4*>(s_a2lo + roff + kc * 128) = lo;
-            }
-        }
-        proxy_fence();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            // FC1 partial: D2[128 x 64] += A2[128 x 32] x W1_p[32 x 64]   (hi*hi + hi*lo + lo*hi)
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t ahi = make_desc(a_a2hi + ks * 256, 128, 512), alo = make_desc(a_a2lo + ks * 256, 128, 512);
-                const uint64_t bhi = make_desc(a_w1hi + ks * 256, 128, 512), blo = make_desc(a_w1lo + ks * 256, 128, 512);
-                umma_bf16(tmem + kColD2, ahi, bhi, idesc64, (p | ks) != 0);
-                umma_bf16(tmem + kColD2, ahi, blo, idesc64, 1);
-                umma_bf16(tmem + kColD2, alo, bhi, idesc64, 1);
-            }
-        }
+    if (warp < 4) {
+        epilogue_role(prm, ur, L, tmem, s_head, s_a2, bars);
+    } else if (warp < 8) {
+        loader_role(prm, ur, s_cols, s_stage, bars);
+    } else if (tid == 8 * 32) {
+        mma_role(prm, ur, L, tmem, smem_addr(s_cols), smem_addr(s_head), smem_addr(s_a2), smem_addr(s_wring), bars);
+    } else if (tid == 9 * 32) {
+        producer_role(prm, ur, L, smem_addr(s_head), smem_addr(s_wring), bars);
     }
-    if (tid == 0) umma_commit(mbar);
-    mbar_wait(mbar, phase);
-    phase ^= 1;
-    tc_fence_after();
-
-    // FC1 epilogue -> FC2 operand [128 x 64] (reuses the cell blocks: every conv MMA has completed)
-    uint8_t* s_a3hi = s_cells;
-    uint8_t* s_a3lo = s_cells + 16384;
-    {
-        const float* b1 = reinterpret_cast<const float*>(s_blob + L.b1);
-        const int roff = (tid >> 3) * 1024 + (tid & 7) * 16;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float v[32];
-            tmem_ld32(trow + kColD2 + half * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b1[half * 32 + i], 0.0f);
-#pragma unroll
-            for (int kc = 0; kc < 4; ++kc) {
-                uint4 hi, lo;
-                split8(v + kc * 8, hi, lo);
-                *reinterpret_cast<uint4*>(s_a3hi + roff + (half * 4 + kc) * 128) = hi;
-                *reinterpret_cast<uint4*>(s_a3lo + roff + (half * 4 + kc) * 128) = lo;
-            }
-        }
-    }
-    proxy_fence();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-        tc_fence_after();
-        const uint32_t a3hi = smem_addr(s_a3hi), a3lo = smem_addr(s_a3lo);
-        const uint32_t w2hi = smem_addr(s_blob + L.w2_hi), w2lo = smem_addr(s_blob + L.w2_lo);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ahi = make_desc(a3hi + ks * 256, 128, 1024), alo = make_desc(a3lo + ks * 256, 128, 1024);
-            const uint64_t bhi = make_desc(w2hi + ks * 256, 128, 1024), blo = make_desc(w2lo + ks * 256, 128, 1024);
-            umma_bf16(tmem + kColD3, ahi, bhi, idesc64, ks != 0);
-            umma_bf16(tmem + kColD3, ahi, blo, idesc64, 1);
-            umma_bf16(tmem + kColD3, alo, bhi, idesc64, 1);
-        }
-        umma_commit(mbar);
-    }
-    mbar_wait(mbar, phase);
-    phase ^= 1;
-    tc_fence_after();
-
-    // FC2 epilogue + head (fp32 on CUDA cores)
-    float head[6];
-    {
-        const float* b2 = reinterpret_cast<const float*>(s_blob + L.b2);
-        const float* wh = reinterpret_cast<const float*>(s_blob + L.wh);
-        const float* bh = reinterpret_cast<const float*>(s_blob + L.bh);
-#pragma unroll
-        for (int a = 0; a < 6; ++a) head[a] = bh[a];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float v[32];
-            tmem_ld32(trow + kColD3 + half * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float h = fmaxf(v[i] + b2[half * 32 + i], 0.0f);
-#pragma unroll
-                for (int a = 0; a < 6; ++a) head[a] = fmaf(h, wh[a * kHid + half * 32 + i], head[a]);
-            }
-        }
-    }
-    if (valid) {
-        if (prm.net == 1) {
-            if (prm.values) prm.values[row] = head[0];
-        } else {
-            if (prm.logits) {
-#pragma unroll
-                for (int a = 0; a < 6; ++a) prm.logits[row * 6 + a] = head[a];
-            }
-            if (prm.actions || prm.logp) {
-                // FixedCategorical(logits): sample / mode and log-prob (train/MAPPO/utils/distributions.py:14-28)
-                float mx = head[0];
-#pragma unroll
-                for (int a = 1; a < 6; ++a) mx = fmaxf(mx, head[a]);
-                float e[6], sum = 0.0f;
-#pragma unroll
-                for (int a = 0; a < 6; ++a) e[a] = expf(head[a] - mx), sum += e[a];
-                int act = 0;
-                if (prm.deterministic) {
-#pragma unroll
-                    for (int a = 1; a < 6; ++a) act = (head[a] > head[act]) ? a : act;
-                } else {
-                    uint32_t r[4] = {(uint32_t)row, (uint32_t)prm.offset, (uint32_t)(prm.offset >> 32), 0x5A17u};
-                    philox4x32_10(r, (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
-                    const float u = (float)(r[0] >> 8) * (1.0f / 16777216.0f) * sum;
-                    float cum = 0.0f;
-                    act = 5;  // inverse CDF; falls through to the last action on round-off
-                    bool found = false;
-#pragma unroll
-                    for (int a = 0; a < 6; ++a) {
-                        cum += e[a];
-                        if (!found && u < cum) act = a, found = true;
-                    }
-                }
-                if (prm.actions) prm.actions[row] = act;
-                if (prm.logp) {
-                    float la = head[0];
-#pragma unroll
-                    for (int a = 1; a < 6; ++a) la = (act == a) ? head[a] : la;
-                    prm.logp[row] = la - mx - logf(sum);
-                }
-            }
-        }
-    }
-
+    __syncwarp();
     tc_fence_before();
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
-}
-
-size_t policy_smem_bytes(int S, int npos) {
-    return (size_t)S * kCellBlock + blob_resident_bytes(npos) + 4096 * 2 + 8192 * 2 + 64;
 }
 
 // ---------------------------------------------------------------- host-side packing
@@ -450,6 +640,8 @@ void put_split(uint8_t* hi, uint8_t* lo, size_t off, float w) {
 struct ocb_policy {
     int device;
     int W, H, S, SC, C, npos, n_policies;
+    int sm_count, ring, stage_stride;
+    size_t smem_bytes;
     std::vector<uint8_t> terrain;
     BlobLayout L;
     uint8_t* d_blobs;
@@ -471,6 +663,10 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
     if (hidden != kHid) return fail(OCB_ERR_UNSUPPORTED, "the fused policy kernel supports hidden_size 64 only (got %d)", hidden);
     if (cfg->num_players != 2) return fail(OCB_ERR_UNSUPPORTED, "the fused policy kernel supports 2 players only");
     if (cfg->width < 3 || cfg->height < 3) return fail(OCB_ERR_BAD_LAYOUT, "grid smaller than the 3x3 convolution");
+    if ((cfg->width - 2) * (cfg->height - 2) < 2) return fail(OCB_ERR_UNSUPPORTED, "the fused policy kernel needs at least two conv positions");
+    if (cfg->width * cfg->height > OCB_MAX_CELLS) return fail(OCB_ERR_BAD_LAYOUT, "grid larger than OCB_MAX_CELLS");
+    if (cfg->height > kMaxH)
+        return fail(OCB_ERR_UNSUPPORTED, "the fused policy kernel supports grids up to %d rows high (got %d)", kMaxH, cfg->height);
     if (n_policies < 1 || n_policies > 4096) return fail(OCB_ERR_INVALID_ARG, "n_policies out of range");
     const int ndev = ocb_device_count();
     if (ndev <= 0) return fail(OCB_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
@@ -478,20 +674,28 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
     ocb_policy* p = new (std::nothrow) ocb_policy();
     if (p == nullptr) return fail(OCB_ERR_INVALID_ARG, "out of host memory");
     p->device = device, p->W = cfg->width, p->H = cfg->height, p->S = p->W * p->H, p->C = 20, p->SC = p->S * 20;
-    p->npos = (p->W - 2) * (p->H - 2), p->n_policies = n_policies, p->calls = 0;
+    p->npos = (p->W - 2) * (p->H - 2), p->n_policies = n_policies, p->calls = 0, p->d_blobs = nullptr;
     p->terrain.assign(cfg->terrain, cfg->terrain + p->S);
     p->L = blob_layout(p->npos);
-    if (policy_smem_bytes(p->S, p->npos) > 220 * 1024) {
+    p->stage_stride = (5 * p->H) | 1;
+    // weight ring: as many 8 KB chunks as fit; all of them (resident weights) when possible
+    const int fixed = smem_layout(p->H, p->npos, 0, p->stage_stride).total;
+    int ring = (kSmemBudget - fixed) / kChunk;
+    if (ring > kMaxRing) ring = kMaxRing;
+    if (ring > p->L.chunks) ring = p->L.chunks;
+    if (ring < 2) {
         delete p;
-        return fail(OCB_ERR_UNSUPPORTED, "layout too large for the fused policy kernel (%d cells)", cfg->width * cfg->height);
+        return fail(OCB_ERR_UNSUPPORTED, "layout too large for the fused policy kernel (%d x %d)", cfg->width, cfg->height);
     }
+    p->ring = ring;
+    p->smem_bytes = (size_t)smem_layout(p->H, p->npos, ring, p->stage_stride).total;
     DeviceGuard guard(device);
     const size_t bytes = (size_t)n_policies * 2 * p->L.total;
-    cudaError_t err = cudaMalloc(&p->d_blobs, bytes);
+    cudaError_t err = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (err == cudaSuccess) err = cudaMalloc(&p->d_blobs, bytes);
     if (err == cudaSuccess) err = cudaMemset(p->d_blobs, 0, bytes);
     if (err == cudaSuccess)
-        err = cudaFuncSetAttribute(policy_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)policy_smem_bytes(p->S, p->npos));
+        err = cudaFuncSetAttribute(policy_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
     if (err != cudaSuccess) {
         cudaGetLastError();
         ocb_policy_destroy(p);
@@ -537,13 +741,17 @@ extern "C" int ocb_policy_set_weights(ocb_policy* p, int policy, int net, const 
             bias1[pos * kCo + co] = (float)acc;
         }
     }
+    // FC chunks: chunk pos = W1 of that position [64 x 32]; chunks npos, npos+1 = the K halves of W2 [64 x 32]
+    uint8_t* chunks = blob.data() + L.head_bytes;
     for (int n = 0; n < kHid; ++n) {
         for (int pos = 0; pos < npos; ++pos)
             for (int co = 0; co < kCo; ++co)
-                put_split(blob.data() + L.w1_hi + (size_t)pos * 4096, blob.data() + L.w1_lo + (size_t)pos * 4096,
-                          canon_off(n, co, kCo), fc1_w[(size_t)n * (kCo * npos) + co * npos + pos]);
-        for (int k = 0; k < kHid; ++k)
-            put_split(blob.data() + L.w2_hi, blob.data() + L.w2_lo, canon_off(n, k, kHid), fc2_w[n * kHid + k]);
+                put_split(chunks + (size_t)pos * kChunk, chunks + (size_t)pos * kChunk + 4096, canon_off(n, co, kCo),
+                          fc1_w[(size_t)n * (kCo * npos) + co * npos + pos]);
+        for (int k = 0; k < kHid; ++k) {
+            uint8_t* c = chunks + (size_t)(npos + k / 32) * kChunk;
+            put_split(c, c + 4096, canon_off(n, k % 32, 32), fc2_w[n * kHid + k]);
+        }
     }
     memcpy(blob.data() + L.b1, fc1_b, kHid * 4);
     memcpy(blob.data() + L.b2, fc2_b, kHid * 4);
@@ -560,21 +768,31 @@ extern "C" int ocb_policy_set_weights(ocb_policy* p, int policy, int net, const 
     return OCB_OK;
 }
 
-static int policy_launch(ocb_policy* p, int net, const int8_t* obs, int M, const int32_t* tile_policy, float* logits,
+static int policy_launch(ocb_policy* p, int net_mask, const int8_t* obs, int M, const int32_t* tile_policy, float* logits,
                          int32_t* actions, float* logp, float* values, int deterministic, uint64_t seed, uint64_t offset,
-                         void* stream) {
+                         const uint64_t* d_offset, void* stream) {
     if (p == nullptr || obs == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL argument");
     if (M < 1) return fail(OCB_ERR_INVALID_ARG, "M must be >= 1");
+    if ((reinterpret_cast<uintptr_t>(obs) & 3u) != 0) return fail(OCB_ERR_INVALID_ARG, "obs must be 4-byte aligned");
     DeviceGuard guard(p->device);
     PolicyParams prm;
     memset(&prm, 0, sizeof(prm));
-    prm.blobs = p->d_blobs, prm.blob_stride = (size_t)p->L.total, prm.n_policies = p->n_policies;
-    prm.W = p->W, prm.H = p->H, prm.S = p->S, prm.SC = p->SC, prm.npos = p->npos, prm.net = net;
-    prm.obs = obs, prm.M = M, prm.tile_policy = tile_policy;
+    prm.blobs = p->d_blobs, prm.blob_stride = (size_t)p->L.total;
+    prm.W = p->W, prm.H = p->H, prm.S = p->S, prm.SC = p->SC, prm.npos = p->npos;
+    prm.obs = obs, prm.M = M, prm.tiles = (M + kRows - 1) / kRows, prm.tile_policy = tile_policy;
     prm.logits = logits, prm.actions = actions, prm.logp = logp, prm.values = values;
     prm.deterministic = deterministic, prm.seed = seed, prm.offset = offset;
-    const int ctas = (M + kRows - 1) / kRows;
-    policy_fwd_kernel<<<ctas, kRows, policy_smem_bytes(p->S, p->npos), (cudaStream_t)stream>>>(prm);
+    prm.d_offset = reinterpret_cast<const unsigned long long*>(d_offset);
+    prm.net_mask = net_mask, prm.ring = p->ring, prm.stage_stride = p->stage_stride;
+    // persistent grid: one CTA per SM; with both networks even CTAs run the actor, odd ones the critic
+    int ctas;
+    if (net_mask == 3) {
+        const int per_net = prm.tiles < p->sm_count / 2 ? prm.tiles : p->sm_count / 2;
+        ctas = 2 * per_net;
+    } else {
+        ctas = prm.tiles < p->sm_count ? prm.tiles : p->sm_count;
+    }
+    policy_fwd_kernel<<<ctas, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(prm);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "policy kernel launch failed: %s", cudaGetErrorString(err));
     p->calls += 1;
@@ -584,11 +802,26 @@ static int policy_launch(ocb_policy* p, int net, const int8_t* obs, int M, const
 extern "C" int ocb_policy_act(ocb_policy* p, const int8_t* obs, int M, const int32_t* tile_policy, int32_t* actions,
                               float* logp, float* logits, int deterministic, uint64_t seed, uint64_t offset,
                               void* stream) {
-    return policy_launch(p, 0, obs, M, tile_policy, logits, actions, logp, nullptr, deterministic, seed, offset, stream);
+    return policy_launch(p, 1, obs, M, tile_policy, logits, actions, logp, nullptr, deterministic, seed, offset, nullptr, stream);
 }
 
 extern "C" int ocb_policy_value(ocb_policy* p, const int8_t* obs, int M, const int32_t* tile_policy, float* values,
                                 void* stream) {
     if (values == nullptr) return fail(OCB_ERR_INVALID_ARG, "values is NULL");
-    return policy_launch(p, 1, obs, M, tile_policy, nullptr, nullptr, nullptr, values, 0, 0, 0, stream);
+    return policy_launch(p, 2, obs, M, tile_policy, nullptr, nullptr, nullptr, values, 0, 0, 0, nullptr, stream);
+}
+
+extern "C" int ocb_policy_forward(ocb_policy* p, const int8_t* obs, int M, const int32_t* tile_policy, int32_t* actions,
+                                  float* logp, float* logits, float* values, int deterministic, uint64_t seed,
+                                  uint64_t offset, const uint64_t* d_offset, void* stream) {
+    if (values == nullptr) return fail(OCB_ERR_INVALID_ARG, "values is NULL");
+    return policy_launch(p, 3, obs, M, tile_policy, logits, actions, logp, values, deterministic, seed, offset, d_offset, stream);
+}
+
+extern "C" int ocb_policy_info(const ocb_policy* p, int* ring_slots, int* chunks_per_unit, int* smem_bytes) {
+    if (p == nullptr) return fail(OCB_ERR_INVALID_ARG, "policy is NULL");
+    if (ring_slots) *ring_slots = p->ring;
+    if (chunks_per_unit) *chunks_per_unit = p->L.chunks;
+    if (smem_bytes) *smem_bytes = (int)p->smem_bytes;
+    return OCB_OK;
 }

@@ -175,6 +175,32 @@ class FusedPolicy:
                                                         seed, offset, self._stream()))
         return out
 
+    def forward(self, obs, tile_policy=None, deterministic=False, seed=0, offset=None, d_offset=None,
+                want_logits=False, out=None):
+        """Actor and critic in ONE launch (ocb_policy_forward): dict(actions, logp, logits|None, values).
+        `d_offset` is an optional device address (int) of a uint64 added to `offset` on the device."""
+        M = self._rows(obs)
+        if out is None:
+            out = {"actions": torch.empty((M,), dtype=torch.int32, device=self.device),
+                   "logp": torch.empty((M,), dtype=torch.float32, device=self.device),
+                   "logits": torch.empty((M, NUM_ACTIONS), dtype=torch.float32, device=self.device) if want_logits else None,
+                   "values": torch.empty((M,), dtype=torch.float32, device=self.device)}
+        if offset is None:
+            offset = self.calls
+        self.calls += 1
+        with torch.cuda.device(self.device):
+            self._native.check(self._lib.ocb_policy_forward(
+                self._h, self._p(obs), M, self._p(tile_policy), self._p(out["actions"]), self._p(out["logp"]),
+                self._p(out.get("logits")), self._p(out["values"]), int(deterministic), seed, offset,
+                self._ct.c_void_p(d_offset) if d_offset else None, self._stream()))
+        return out
+
+    def info(self) -> dict:
+        r, c, b = self._ct.c_int(), self._ct.c_int(), self._ct.c_int()
+        self._native.check(self._lib.ocb_policy_info(self._h, self._ct.byref(r), self._ct.byref(c), self._ct.byref(b)))
+        return {"ring_slots": r.value, "chunks_per_unit": c.value, "weights_resident": r.value >= c.value,
+                "smem_bytes": b.value}
+
     def value(self, obs, tile_policy=None, out=None):
         M = self._rows(obs)
         if out is None:

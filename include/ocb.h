@@ -201,6 +201,35 @@ int ocb_policy_act(ocb_policy* pol, const int8_t* obs, int M, const int32_t* til
 int ocb_policy_value(ocb_policy* pol, const int8_t* obs, int M, const int32_t* tile_policy, float* values,
                      void* stream);
 
+/* both networks in ONE launch (even CTAs run the actor, odd CTAs the critic): everything
+ * ocb_policy_act and ocb_policy_value write; values is required.  d_offset (DEVICE pointer, may
+ * be NULL) is added to `offset` on the device, so a CUDA graph that replays this launch samples
+ * with a fresh counter (pass ocb_step_counter_device(env)). */
+int ocb_policy_forward(ocb_policy* pol, const int8_t* obs, int M, const int32_t* tile_policy, int32_t* actions,
+                       float* logp, float* logits, float* values, int deterministic, uint64_t seed, uint64_t offset,
+                       const uint64_t* d_offset, void* stream);
+/* launch shape in effect: weight-ring slots in shared memory, FC weight chunks per (tile, network)
+ * unit (ring >= chunks means the weights stay resident), dynamic shared memory per CTA */
+int ocb_policy_info(const ocb_policy* pol, int* ring_slots, int* chunks_per_unit, int* smem_bytes);
+
+/* ------------------------------------------------------- device-resident self-play / cross-play rollout */
+/* DEVICE address of the env's step counter (uint64, += K after every K-step launch) */
+const uint64_t* ocb_step_counter_device(const ocb_env* env);
+/* The rollout half of MainPlayer.collect_episode / next_step (train/MAPPO/main_player.py:91-112,
+ * 211-261) with the partner seat of CentralizedAgent.get_action (train/partner_agents.py:28-63)
+ * or, with tile_policy, the slice-wise policy multiplexing of XDPlayer.next_step /
+ * CentralizedMultiAgent (train/XD/xd_player.py:177-230, train/partner_agents.py:87-137):
+ * T times { fused actor+critic forward of all P*N agent rows on obs_slab[t] -> actions[t],
+ * logp[t], values[t];  one env step -> obs_slab[t+1], reward[t], done[t] } and finally the
+ * bootstrap values[T] of obs_slab[T].  obs_slab[0] must hold the current observation
+ * (ocb_reset / ocb_observe).  Layouts (SharedReplayBuffer, train/MAPPO/utils/shared_buffer.py:45-76,
+ * kept seat-major): obs_slab [T+1,P,N,W,H,C] int8, actions [T,P,N] int32, logp [T,P,N] f32,
+ * values [T+1,P,N] f32, reward [T,P,N] int32, done [T,N] int32 (masks = 1 - done).
+ * logp, reward, done may be NULL.  2*T+1 launches on `stream`, no synchronisation. */
+int ocb_rollout_policy(ocb_env* env, ocb_policy* pol, int T, const int32_t* tile_policy, int8_t* obs_slab,
+                       int32_t* actions, float* logp, float* values, int32_t* reward, int32_t* done,
+                       int deterministic, uint64_t seed, void* stream);
+
 /* ------------------------------------------------------- Balance-Beam */
 /* replaces BalanceBeamSimulator (src/balance_beam_env/mgr.cpp:191-233) behind
  * MadronaEnv.n_step / n_reset (vectorenv.py:306-343).

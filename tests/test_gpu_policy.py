@@ -111,4 +111,46 @@ def test_unsupported_shapes_fail_loudly():
     with pytest.raises(_native.NativeError):
         FusedPolicy(layouts.load_layout("simple", 400), hidden=512)
     with pytest.raises(_native.NativeError):
-        FusedPolicy(layouts.load_layout("multiplayer_schelling", 400), hidden=64)
+        FusedPolicy(layouts.load_layout("multiplayer_schelling", 400), hidden=64)  # 4 players
+    with pytest.raises(_native.NativeError):
+        FusedPolicy(layouts.load_layout("corridor", 400), hidden=64)  # 9 rows high
+
+
+@pytest.mark.parametrize("layout", ["simple", "random0", "random3", "unident_s", "scenario3"])
+def test_fused_forward_all_layout_sizes(layout):
+    """both networks in one launch, weights resident (small grids) or streamed (large grids);
+    enough rows that every CTA runs several tiles back to back"""
+    lp = layouts.load_layout(layout, 400)
+    n_pol = 3
+    pol = FusedPolicy(lp, 64, n_pol)
+    actors = [PolicyNet("actor", lp.width, lp.height, 20, 64).init_like_reference(20 + i, gain=1.0) for i in range(n_pol)]
+    critics = [PolicyNet("critic", lp.width, lp.height, 20, 64).init_like_reference(70 + i) for i in range(n_pol)]
+    for i in range(n_pol):
+        for net in (actors[i], critics[i]):
+            for b in (net.conv_b, net.fc1_b, net.fc2_b, net.head_b):
+                b.uniform_(-0.1, 0.1)
+        pol.set_weights(i, actors[i], critics[i])
+    N = 148 * 64 * 2 + 77
+    orc = COracle(lp, N)
+    rng = np.random.default_rng(1)
+    for _ in range(60):
+        o, _, _ = orc.step(rng.choice(6, size=(2, N), p=[.15, .15, .15, .15, .05, .35]))
+    M = 2 * N
+    obs = torch.from_numpy(o.reshape(M, lp.width, lp.height, 20).copy()).cuda()
+    tiles = (M + 127) // 128
+    for tp in (None, torch.tensor([(t // 5) % n_pol for t in range(tiles)], dtype=torch.int32, device="cuda")):
+        out = pol.forward(obs, tile_policy=tp, deterministic=True, want_logits=True)
+        torch.cuda.synchronize()
+        pick = torch.arange(0, tiles, 7)
+        for t in pick.tolist() + [tiles - 1]:
+            sl = slice(t * 128, min(M, (t + 1) * 128))
+            k = 0 if tp is None else int(tp[t])
+            assert rel_err(out["logits"][sl].cpu(), actors[k].forward(obs[sl].cpu())) < REL_TOL, (layout, t)
+            assert rel_err(out["values"][sl].cpu(), critics[k].forward(obs[sl].cpu())[:, 0]) < REL_TOL, (layout, t)
+        # the single-network entry points agree bit for bit with the fused launch
+        a = pol.act(obs, tile_policy=tp, deterministic=True, want_logits=True)
+        v = pol.value(obs, tile_policy=tp)
+        assert torch.equal(a["logits"], out["logits"]) and torch.equal(a["actions"], out["actions"])
+        assert torch.equal(v, out["values"])
+    info = pol.info()
+    assert info["ring_slots"] >= 2 and info["smem_bytes"] <= 227 * 1024
