@@ -51,17 +51,21 @@ constexpr int kHid = 64;       // hidden size
 constexpr int kCo = 32;        // conv output channels (hidden / 2)
 constexpr int kSlots = 16;     // bf16 slots per cell: channels 0-9, 15-19, one zero pad
 constexpr int kK1 = 9 * kSlots;  // conv K
-constexpr int kCellBlock = kRows * kSlots * 2;  // 4096 B
+constexpr int kCellCols = kSlots / 2;  // TMEM columns of one cell block
 constexpr int kColRing = 4;    // grid columns resident per CTA (3 in use by the conv + 1 being loaded)
 constexpr int kD1Stages = 4;   // conv accumulators in flight
 constexpr int kConvAhead = 3;  // conv positions issued ahead of their FC1 item (< kD1Stages, see mma_role)
 constexpr int kChunk = 8192;   // one FC weight chunk: [64 x 32] bf16 hi | lo
-constexpr int kA2Stage = 16384;  // one FC A-operand stage: [128 x 32] bf16 hi | lo
+constexpr int kA2Cols = 32;    // TMEM columns of one FC A-operand stage: [128 x 32] bf16 hi (16) | lo (16)
 constexpr int kMaxRing = 16;   // weight-ring slots (resident when >= chunks per unit)
 constexpr int kMaxH = 6;       // a grid column must fit one warp-wide load (5*H words <= 32)
 constexpr int kThreads = 320;  // warps 0-3 epilogue, 4-7 loader, 8 MMA issuer, 9 weight producer
 constexpr int kTmemCols = 512;
-constexpr int kColD1 = 0, kColD2 = 128, kColD3 = 256;
+// TMEM map (32-bit columns x 128 lanes = rows of the tile): the A operands live here too, two bf16 per column
+constexpr int kColCells = 0;    // ring of 4 grid columns x H cells x 8 columns ([128 x 16] bf16 each), <= 192
+constexpr int kColD1 = 192;     // conv accumulators, 4 stages x 32
+constexpr int kColA2 = 320;     // FC A operand, 2 stages x (hi 16 | lo 16)
+constexpr int kColD2 = 384;     // FC1 accumulator (then FC2 accumulator of the same unit), 2 units x 64
 constexpr int kSmemBudget = 227 * 1024 - 256;
 
 // packed weight blob of one network: a resident "head" followed by 8 KB FC chunks
@@ -108,19 +112,18 @@ struct PolicyParams {
     int net_mask;             // 1 actor, 2 critic, 3 both (even CTAs actor, odd critic)
     int ring;                 // weight-ring slots in shared memory
     int stage_stride;         // words per row of the loader staging buffer (odd)
+    long long* prof;          // diagnostic build: [ctas][4 roles][PW_COUNT] stall cycles
 };
 
 // shared-memory carve-up (byte offsets from a 128-byte aligned base)
 struct SmemLayout {
-    int cols, stage, head, a2, wring, bars, total;
+    int stage, head, wring, bars, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int H, int npos, int ring, int stage_stride) {
     SmemLayout s;
     int o = 0;
-    s.cols = o, o += kColRing * H * kCellBlock;
     s.stage = o, o += al128(4 * 32 * stage_stride * 4);
     s.head = o, o += blob_layout(npos).head_bytes;
-    s.a2 = o, o += 2 * kA2Stage;
     s.wring = o, o += ring * kChunk;
     s.bars = o, o += 512;
     s.total = o + 128;  // slack for aligning the dynamic base
@@ -157,13 +160,28 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+// A operand from tensor memory ([128 lanes] x K/2 columns, two bf16 per column), B from shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
         : "memory");
 }
+// registers -> TMEM: thread l of warp w writes lane 32(w%4)+l, 8 / 16 consecutive columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& a, const uint4& b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(a.x),
+                 "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::
+            "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
@@ -191,15 +209,40 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
         if (spins > (1u << 24)) __trap();
     }
 }
+// wait that optionally accounts the stall cycles (diagnostic build of the kernel only)
+template <bool kProf>
+__device__ __forceinline__ void mbar_wait_p(uint32_t mbar, uint32_t parity, long long& acc) {
+    if (kProf) {
+        const long long t0 = clock64();
+        mbar_wait(mbar, parity);
+        acc += clock64() - t0;
+    } else {
+        mbar_wait(mbar, parity);
+    }
+}
+// stall accounts written by ocb_policy_debug_profile: per CTA, per role, [0] = total cycles of the role
+enum : int { PW_TOTAL = 0, PW_COL_EMPTY, PW_HEAD_FULL, PW_COL_FULL, PW_A2_FULL, PW_W_FULL, PW_D1_FULL, PW_D2_FULL,
+             PW_A2_EMPTY, PW_D3_FULL, PW_HEAD_EMPTY, PW_W_EMPTY, PW_ISSUE_CONV, PW_ISSUE_FC, PW_LDG, PW_COUNT = 16 };
+
 // global -> shared bulk copy that completes `bytes` of transaction count on `mbar`
 __device__ __forceinline__ void bulk_g2s(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst),
                  "l"(gsrc), "r"(bytes), "r"(mbar)
                  : "memory");
 }
+// one lane of the (converged) warp; the tcgen05 / bulk-copy instructions below are issued under it so
+// that the compiler keeps their operands in uniform registers instead of a per-lane waterfall loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // 32 lanes x 32 columns of fp32: thread l of warp w receives row 32w+l, columns col..col+31
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
@@ -253,14 +296,14 @@ __device__ __forceinline__ bool blob_changed(const PolicyParams& prm, int t, int
 
 // ---------------------------------------------------------------- roles
 // loader: global observations -> bf16 cell blocks, one grid column at a time
-__device__ __forceinline__ void loader_role(const PolicyParams& prm, const UnitRange ur, uint8_t* s_cols, uint32_t* s_stage,
+template <bool kProf>
+__device__ __forceinline__ void loader_role(long long* pw, const PolicyParams& prm, const UnitRange ur, uint32_t tmem, uint32_t* s_stage,
                                             uint32_t bars) {
     const int lw = (threadIdx.x >> 5) - 4, lane = threadIdx.x & 31;
     const int W = prm.W, H = prm.H, SC4 = prm.SC >> 2, seg = 5 * H, stride = prm.stage_stride;
     uint32_t* stg = s_stage + lw * 32 * stride;
     const uint32_t* obs32 = reinterpret_cast<const uint32_t*>(prm.obs);
-    const int rloc = lw * 32 + lane;                           // this thread's row inside the tile (convert phase)
-    const int roff = (rloc >> 3) * 256 + (rloc & 7) * 16;      // its place inside a [128 x 16] block
+    const uint32_t tcells = tmem + ((uint32_t)(lw * 32) << 16) + kColCells;  // this warp's 32 TMEM lanes (rows)
     uint32_t pre[32];
 
     auto issue_loads = [&](int t, int x) {
@@ -276,15 +319,20 @@ __device__ __forceinline__ void loader_role(const PolicyParams& prm, const UnitR
     uint32_t gc = 0;  // running column counter: ring slot and phase
     for (int t = ur.t0; t < ur.t1; ++t) {
         for (int x = 0; x < W; ++x, ++gc) {
+            const long long tl0 = kProf ? clock64() : 0;
             if (lane < seg) {
 #pragma unroll
                 for (int r = 0; r < 32; ++r) stg[r * stride + lane] = pre[r];
             }
             __syncwarp();
+            if (kProf) pw[PW_LDG] += clock64() - tl0;
             if (x + 1 < W) issue_loads(t, x + 1);
             else if (t + 1 < ur.t1) issue_loads(t + 1, 0);
             const int slot = gc % kColRing;
-            if (gc >= kColRing) mbar_wait(bars + 8 * (B_COL_EMPTY + slot), ((gc / kColRing) - 1) & 1);
+            if (gc >= kColRing) {
+                mbar_wait_p<kProf>(bars + 8 * (B_COL_EMPTY + slot), ((gc / kColRing) - 1) & 1, pw[PW_COL_EMPTY]);
+                tc_fence_after();
+            }
             const uint32_t* mine = stg + lane * stride;
             for (int y = 0; y < H; ++y) {
                 uint32_t w[5];
@@ -296,11 +344,10 @@ __device__ __forceinline__ void loader_role(const PolicyParams& prm, const UnitR
                                             byte_bf16(by(4)) | (byte_bf16(by(5)) << 16), byte_bf16(by(6)) | (byte_bf16(by(7)) << 16));
                 const uint4 c1 = make_uint4(byte_bf16(by(8)) | (byte_bf16(by(9)) << 16), byte_bf16(by(15)) | (byte_bf16(by(16)) << 16),
                                             byte_bf16(by(17)) | (byte_bf16(by(18)) << 16), byte_bf16(by(19)));
-                uint8_t* blk = s_cols + (size_t)(slot * H + y) * kCellBlock + roff;
-                *reinterpret_cast<uint4*>(blk) = c0;
-                *reinterpret_cast<uint4*>(blk + 128) = c1;
+                tmem_st8(tcells + (slot * H + y) * kCellCols, c0, c1);
             }
-            proxy_fence();
+            tmem_st_wait();
+            tc_fence_before();
             mbar_arrive(bars + 8 * (B_COL_FULL + slot));
             __syncwarp();  // the staging rows are rewritten by the next column
         }
@@ -308,7 +355,8 @@ __device__ __forceinline__ void loader_role(const PolicyParams& prm, const UnitR
 }
 
 // producer: weight head (conv weights, biases, head) and the FC chunk ring
-__device__ __forceinline__ void producer_role(const PolicyParams& prm, const UnitRange ur, const BlobLayout L, uint32_t s_head,
+template <bool kProf>
+__device__ __forceinline__ void producer_role(long long* pw, const PolicyParams& prm, const UnitRange ur, const BlobLayout L, uint32_t s_head,
                                               uint32_t s_wring, uint32_t bars) {
     const int R = prm.ring;
     const bool resident = R >= L.chunks;
@@ -320,25 +368,33 @@ __device__ __forceinline__ void producer_role(const PolicyParams& prm, const Uni
         if (chg) {
             // the previous unit must be completely done with the head (conv MMAs, biases, head weights);
             // arrivals alternate between two barriers so that a late waiter cannot alias an older phase
-            if (u > 0) mbar_wait(bars + 8 * (B_HEAD_EMPTY + ((u - 1) & 1)), ((u - 1) >> 1) & 1);
-            mbar_arrive_expect_tx(bars + 8 * B_HEAD_FULL, (uint32_t)L.head_bytes);
-            bulk_g2s(s_head, blob, (uint32_t)L.head_bytes, bars + 8 * B_HEAD_FULL);
+            if (u > 0) mbar_wait_p<kProf>(bars + 8 * (B_HEAD_EMPTY + ((u - 1) & 1)), ((u - 1) >> 1) & 1, pw[PW_HEAD_EMPTY]);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bars + 8 * B_HEAD_FULL, (uint32_t)L.head_bytes);
+                bulk_g2s(s_head, blob, (uint32_t)L.head_bytes, bars + 8 * B_HEAD_FULL);
+            }
+            __syncwarp();
         }
         const bool load = !resident || chg;
         for (int j = 0; j < L.chunks; ++j, ++wc) {
             const int slot = wc % Reff;
-            if (wc >= (uint32_t)Reff) mbar_wait(bars + 8 * (B_W_EMPTY + slot), ((wc / Reff) - 1) & 1);
+            if (wc >= (uint32_t)Reff) mbar_wait_p<kProf>(bars + 8 * (B_W_EMPTY + slot), ((wc / Reff) - 1) & 1, pw[PW_W_EMPTY]);
             if (load) {
-                mbar_arrive_expect_tx(bars + 8 * (B_W_FULL + slot), kChunk);
-                bulk_g2s(s_wring + slot * kChunk, blob + L.head_bytes + (size_t)j * kChunk, kChunk, bars + 8 * (B_W_FULL + slot));
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(bars + 8 * (B_W_FULL + slot), kChunk);
+                    bulk_g2s(s_wring + slot * kChunk, blob + L.head_bytes + (size_t)j * kChunk, kChunk,
+                             bars + 8 * (B_W_FULL + slot));
+                }
+                __syncwarp();
             }
         }
     }
 }
 
 // MMA issuer (one thread)
-__device__ __forceinline__ void mma_role(const PolicyParams& prm, const UnitRange ur, const BlobLayout L, uint32_t tmem,
-                                         uint32_t a_cols, uint32_t a_head, uint32_t a_a2, uint32_t a_wring, uint32_t bars) {
+template <bool kProf>
+__device__ __forceinline__ void mma_role(long long* pw, const PolicyParams& prm, const UnitRange ur, const BlobLayout L, uint32_t tmem,
+                                         uint32_t a_head, uint32_t a_wring, uint32_t bars) {
     const int W = prm.W, H = prm.H, PH = H - 2, npos = prm.npos;
     const int R = prm.ring;
     const bool resident = R >= L.chunks;
@@ -367,39 +423,42 @@ __device__ __forceinline__ void mma_role(const PolicyParams& prm, const UnitRang
         if (conv_ok) {
             const int ox = pc / PH, oy = pc - ox * PH;
             if (pc == 0 && blob_changed(prm, tc, ur.t0)) {
-                mbar_wait(bars + 8 * B_HEAD_FULL, head_gen & 1);
+                mbar_wait_p<kProf>(bars + 8 * B_HEAD_FULL, head_gen & 1, pw[PW_HEAD_FULL]);
                 ++head_gen;
             }
             if (oy == 0) {  // new window column(s)
                 for (int d = (ox == 0 ? 0 : 2); d < 3; ++d) {
                     const uint32_t g = gcb + ox + d;
-                    mbar_wait(bars + 8 * (B_COL_FULL + g % kColRing), (g / kColRing) & 1);
+                    mbar_wait_p<kProf>(bars + 8 * (B_COL_FULL + g % kColRing), (g / kColRing) & 1, pw[PW_COL_FULL]);
                 }
             }
             tc_fence_after();
             const uint32_t d1 = tmem + kColD1 + (convs % kD1Stages) * kCo;
+            const bool last = pc + 1 == npos;
+            const long long ti0 = kProf ? clock64() : 0;
+            if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < 9; ++j) {
-                const int dx = j / 3, dy = j - dx * 3;
-                const uint32_t blk = a_cols + (((gcb + ox + dx) % kColRing) * H + oy + dy) * kCellBlock;
-                const uint64_t da = make_desc(blk, 128, 256);
-                umma_bf16(d1, da, make_desc(a_wchi + j * 256, 128, 2304), idesc32, j > 0);
-                umma_bf16(d1, da, make_desc(a_wclo + j * 256, 128, 2304), idesc32, 1);
-            }
-            umma_commit(bars + 8 * (B_D1_FULL + convs % kD1Stages));
-            if (oy == PH - 1) {  // the window leaves column ox (and the last two columns with the last window)
-                umma_commit(bars + 8 * (B_COL_EMPTY + (gcb + ox) % kColRing));
-                if (ox == W - 3) {
-                    umma_commit(bars + 8 * (B_COL_EMPTY + (gcb + ox + 1) % kColRing));
-                    umma_commit(bars + 8 * (B_COL_EMPTY + (gcb + ox + 2) % kColRing));
+                for (int j = 0; j < 9; ++j) {
+                    const int dx = j / 3, dy = j - dx * 3;
+                    const uint32_t ta = tmem + kColCells + (((gcb + ox + dx) % kColRing) * H + oy + dy) * kCellCols;
+                    umma_bf16_ts(d1, ta, make_desc(a_wchi + j * 256, 128, 2304), idesc32, j > 0);
+                    umma_bf16_ts(d1, ta, make_desc(a_wclo + j * 256, 128, 2304), idesc32, 1);
                 }
-            }
-            ++convs;
-            if (++pc == npos) {
+                umma_commit(bars + 8 * (B_D1_FULL + convs % kD1Stages));
+                if (oy == PH - 1) {  // the window leaves column ox (and the last two columns with the last window)
+                    umma_commit(bars + 8 * (B_COL_EMPTY + (gcb + ox) % kColRing));
+                    if (ox == W - 3) {
+                        umma_commit(bars + 8 * (B_COL_EMPTY + (gcb + ox + 1) % kColRing));
+                        umma_commit(bars + 8 * (B_COL_EMPTY + (gcb + ox + 2) % kColRing));
+                    }
+                }
                 // last conv of the unit: the conv weights of the head are free once these MMAs complete
-                umma_commit(bars + 8 * (B_HEAD_EMPTY + ((uint32_t)(tc - ur.t0) & 1)));
-                pc = 0, ++tc, gcb += W;
+                if (last) umma_commit(bars + 8 * (B_HEAD_EMPTY + ((uint32_t)(tc - ur.t0) & 1)));
             }
+            __syncwarp();
+            if (kProf) pw[PW_ISSUE_CONV] += clock64() - ti0;
+            ++convs;
+            if (++pc == npos) pc = 0, ++tc, gcb += W;
             continue;
         }
         // ---- one FC item: D2 (+)= A2 x W1_j   or   D3 (+)= A2 x W2_half
@@ -409,25 +468,30 @@ __device__ __forceinline__ void mma_role(const PolicyParams& prm, const UnitRang
         }
         const int a2s = items & 1;
         const int slot = wc % Reff;
-        mbar_wait(bars + 8 * (B_A2_FULL + a2s), (items >> 1) & 1);
-        if (w_loaded) mbar_wait(bars + 8 * (B_W_FULL + slot), resident ? ((w_gen - 1) & 1) : ((wc / Reff) & 1));
+        mbar_wait_p<kProf>(bars + 8 * (B_A2_FULL + a2s), (items >> 1) & 1, pw[PW_A2_FULL]);
+        if (w_loaded) mbar_wait_p<kProf>(bars + 8 * (B_W_FULL + slot), resident ? ((w_gen - 1) & 1) : ((wc / Reff) & 1), pw[PW_W_FULL]);
         tc_fence_after();
-        const uint32_t dst = tmem + (ji < npos ? kColD2 : kColD3) + (ui & 1) * kHid;
+        // FC2 accumulates into the columns of the (already drained) FC1 accumulator of the same unit
+        const uint32_t dst = tmem + kColD2 + (ui & 1) * kHid;
         const bool first = (ji == 0 || ji == npos);
-        const uint32_t a_hi = a_a2 + a2s * kA2Stage, a_lo = a_hi + 8192;
+        const uint32_t a_hi = tmem + kColA2 + a2s * kA2Cols, a_lo = a_hi + 16;
         const uint32_t b_hi = a_wring + slot * kChunk, b_lo = b_hi + 4096;
+        const long long tf0 = kProf ? clock64() : 0;
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t ahi = make_desc(a_hi + ks * 256, 128, 512), alo = make_desc(a_lo + ks * 256, 128, 512);
-            const uint64_t bhi = make_desc(b_hi + ks * 256, 128, 512), blo = make_desc(b_lo + ks * 256, 128, 512);
-            umma_bf16(dst, ahi, bhi, idesc64, (!first || ks != 0) ? 1u : 0u);
-            umma_bf16(dst, ahi, blo, idesc64, 1);
-            umma_bf16(dst, alo, bhi, idesc64, 1);
+            for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t bhi = make_desc(b_hi + ks * 256, 128, 512), blo = make_desc(b_lo + ks * 256, 128, 512);
+                umma_bf16_ts(dst, a_hi + ks * 8, bhi, idesc64, (!first || ks != 0) ? 1u : 0u);
+                umma_bf16_ts(dst, a_hi + ks * 8, blo, idesc64, 1);
+                umma_bf16_ts(dst, a_lo + ks * 8, bhi, idesc64, 1);
+            }
+            umma_commit(bars + 8 * (B_A2_EMPTY + a2s));
+            umma_commit(bars + 8 * (B_W_EMPTY + slot));
+            if (ji == npos - 1) umma_commit(bars + 8 * B_D2_FULL);
+            if (ji == npos + 1) umma_commit(bars + 8 * B_D3_FULL);
         }
-        umma_commit(bars + 8 * (B_A2_EMPTY + a2s));
-        umma_commit(bars + 8 * (B_W_EMPTY + slot));
-        if (ji == npos - 1) umma_commit(bars + 8 * B_D2_FULL);
-        if (ji == npos + 1) umma_commit(bars + 8 * B_D3_FULL);
+        __syncwarp();
+        if (kProf) pw[PW_ISSUE_FC] += clock64() - tf0;
         ++items, ++wc;
         if (ji < npos) ++fc1s;
         if (++ji == npos + 2) ji = 0, ++ti, ++ui;
@@ -435,12 +499,12 @@ __device__ __forceinline__ void mma_role(const PolicyParams& prm, const UnitRang
 }
 
 // epilogue: TMEM -> bias/ReLU -> bf16 hi/lo A operand; head, sampling and outputs
-__device__ __forceinline__ void epilogue_role(const PolicyParams& prm, const UnitRange ur, const BlobLayout L, uint32_t tmem,
-                                              const uint8_t* s_head, uint8_t* s_a2, uint32_t bars) {
+template <bool kProf>
+__device__ __forceinline__ void epilogue_role(long long* pw, const PolicyParams& prm, const UnitRange ur, const BlobLayout L, uint32_t tmem,
+                                              const uint8_t* s_head, uint32_t bars) {
     const int tid = threadIdx.x, warp = tid >> 5;
     const int npos = prm.npos;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
-    const int roff = (tid >> 3) * 512 + (tid & 7) * 16;          // row position inside a [128 x 32] operand
     const float* s_bias1 = reinterpret_cast<const float*>(s_head + L.bias1);
     const float* s_b1 = reinterpret_cast<const float*>(s_head + L.b1);
     const float* s_b2 = reinterpret_cast<const float*>(s_head + L.b2);
@@ -452,43 +516,47 @@ __device__ __forceinline__ void epilogue_role(const PolicyParams& prm, const Uni
     uint32_t d1c = 0, items = 0, u = 0, head_gen = 0;
     for (int t = ur.t0; t < ur.t1; ++t, ++u) {
         if (blob_changed(prm, t, ur.t0)) {
-            mbar_wait(bars + 8 * B_HEAD_FULL, head_gen & 1);
+            mbar_wait_p<kProf>(bars + 8 * B_HEAD_FULL, head_gen & 1, pw[PW_HEAD_FULL]);
             ++head_gen;
         }
+        float fc1[64];  // the whole FC1 row: FC2 reuses the accumulator columns, so it is drained in one go
         for (int j = 0; j < npos + 2; ++j, ++items) {
             float v[32];
             const float* bias;
             if (j < npos) {
                 const int st = d1c % kD1Stages;
-                mbar_wait(bars + 8 * (B_D1_FULL + st), (d1c / kD1Stages) & 1);
+                mbar_wait_p<kProf>(bars + 8 * (B_D1_FULL + st), (d1c / kD1Stages) & 1, pw[PW_D1_FULL]);
                 tc_fence_after();
                 tmem_ld32(trow + kColD1 + st * kCo, v);
                 ++d1c;
                 bias = s_bias1 + j * kCo;
             } else {
                 if (j == npos) {
-                    mbar_wait(bars + 8 * B_D2_FULL, u & 1);
+                    mbar_wait_p<kProf>(bars + 8 * B_D2_FULL, u & 1, pw[PW_D2_FULL]);
                     tc_fence_after();
+                    float lo32[32], hi32[32];
+                    tmem_ld32(trow + kColD2 + (u & 1) * kHid, lo32);
+                    tmem_ld32(trow + kColD2 + (u & 1) * kHid + 32, hi32);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) fc1[i] = lo32[i], fc1[32 + i] = hi32[i];
                 }
-                tmem_ld32(trow + kColD2 + (u & 1) * kHid + (j - npos) * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = j == npos ? fc1[i] : fc1[32 + i];
                 bias = s_b1 + (j - npos) * 32;
             }
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[i], 0.0f);
             const int a2s = items & 1;
-            if (items >= 2) mbar_wait(bars + 8 * (B_A2_EMPTY + a2s), ((items >> 1) - 1) & 1);
-            uint8_t* hi_base = s_a2 + a2s * kA2Stage + roff;
-#pragma unroll
-            for (int kc = 0; kc < 4; ++kc) {
-                uint4 hi, lo;
-                split2(v[kc * 8 + 0], v[kc * 8 + 1], hi.x, lo.x);
-                split2(v[kc * 8 + 2], v[kc * 8 + 3], hi.y, lo.y);
-                split2(v[kc * 8 + 4], v[kc * 8 + 5], hi.z, lo.z);
-                split2(v[kc * 8 + 6], v[kc * 8 + 7], hi.w, lo.w);
-                *reinterpret_cast<uint4*>(hi_base + kc * 128) = hi;
-                *reinterpret_cast<uint4*>(hi_base + 8192 + kc * 128) = lo;
+            if (items >= 2) {
+                mbar_wait_p<kProf>(bars + 8 * (B_A2_EMPTY + a2s), ((items >> 1) - 1) & 1, pw[PW_A2_EMPTY]);
+                tc_fence_after();
             }
-            proxy_fence();
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+            tmem_st16(trow + kColA2 + a2s * kA2Cols, hi);
+            tmem_st16(trow + kColA2 + a2s * kA2Cols + 16, lo);
+            tmem_st_wait();
             tc_fence_before();
             mbar_arrive(bars + 8 * (B_A2_FULL + a2s));
         }
@@ -497,12 +565,12 @@ __device__ __forceinline__ void epilogue_role(const PolicyParams& prm, const Uni
         float head[6];
 #pragma unroll
         for (int a = 0; a < 6; ++a) head[a] = s_bh[a];
-        mbar_wait(bars + 8 * B_D3_FULL, u & 1);
+        mbar_wait_p<kProf>(bars + 8 * B_D3_FULL, u & 1, pw[PW_D3_FULL]);
         tc_fence_after();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             float v[32];
-            tmem_ld32(trow + kColD3 + (u & 1) * kHid + half * 32, v);
+            tmem_ld32(trow + kColD2 + (u & 1) * kHid + half * 32, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const float h = fmaxf(v[i] + s_b2[half * 32 + i], 0.0f);
@@ -561,16 +629,15 @@ __device__ __forceinline__ void epilogue_role(const PolicyParams& prm, const Uni
 }
 
 // ---------------------------------------------------------------- the kernel
+template <bool kProf>
 __global__ void __launch_bounds__(kThreads, 1) policy_fwd_kernel(const PolicyParams prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
     const int tid = threadIdx.x, warp = tid >> 5;
     const BlobLayout L = blob_layout(prm.npos);
     const SmemLayout sl = smem_layout(prm.H, prm.npos, prm.ring, prm.stage_stride);
-    uint8_t* s_cols = smem + sl.cols;
     uint32_t* s_stage = reinterpret_cast<uint32_t*>(smem + sl.stage);
     uint8_t* s_head = smem + sl.head;
-    uint8_t* s_a2 = smem + sl.a2;
     uint8_t* s_wring = smem + sl.wring;
     uint64_t* s_bars = reinterpret_cast<uint64_t*>(smem + sl.bars);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bars + 60);
@@ -597,14 +664,21 @@ __global__ void __launch_bounds__(kThreads, 1) policy_fwd_kernel(const PolicyPar
     const uint32_t tmem = *s_tmem;
     const UnitRange ur = my_units(prm);
 
+    long long pw[kProf ? PW_COUNT : 1] = {};
+    const long long t_begin = kProf ? clock64() : 0;
     if (warp < 4) {
-        epilogue_role(prm, ur, L, tmem, s_head, s_a2, bars);
+        epilogue_role<kProf>(pw, prm, ur, L, tmem, s_head, bars);
     } else if (warp < 8) {
-        loader_role(prm, ur, s_cols, s_stage, bars);
-    } else if (tid == 8 * 32) {
-        mma_role(prm, ur, L, tmem, smem_addr(s_cols), smem_addr(s_head), smem_addr(s_a2), smem_addr(s_wring), bars);
-    } else if (tid == 9 * 32) {
-        producer_role(prm, ur, L, smem_addr(s_head), smem_addr(s_wring), bars);
+        loader_role<kProf>(pw, prm, ur, tmem, s_stage, bars);
+    } else if (warp == 8) {  // whole warp runs the control flow, one elected lane issues
+        mma_role<kProf>(pw, prm, ur, L, tmem, smem_addr(s_head), smem_addr(s_wring), bars);
+    } else {
+        producer_role<kProf>(pw, prm, ur, L, smem_addr(s_head), smem_addr(s_wring), bars);
+    }
+    if (kProf && prm.prof != nullptr && (tid == 0 || tid == 128 || tid == 256 || tid == 288)) {
+        pw[PW_TOTAL] = clock64() - t_begin;
+        const int role = tid == 0 ? 0 : tid == 128 ? 1 : tid == 256 ? 2 : 3;  // epilogue, loader, MMA, producer
+        for (int i = 0; i < PW_COUNT; ++i) prm.prof[((size_t)blockIdx.x * 4 + role) * PW_COUNT + i] = pw[i];
     }
     __syncwarp();
     tc_fence_before();
@@ -695,7 +769,9 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
     if (err == cudaSuccess) err = cudaMalloc(&p->d_blobs, bytes);
     if (err == cudaSuccess) err = cudaMemset(p->d_blobs, 0, bytes);
     if (err == cudaSuccess)
-        err = cudaFuncSetAttribute(policy_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
+        err = cudaFuncSetAttribute(policy_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
+    if (err == cudaSuccess)
+        err = cudaFuncSetAttribute(policy_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
     if (err != cudaSuccess) {
         cudaGetLastError();
         ocb_policy_destroy(p);
@@ -770,7 +846,7 @@ extern "C" int ocb_policy_set_weights(ocb_policy* p, int policy, int net, const 
 
 static int policy_launch(ocb_policy* p, int net_mask, const int8_t* obs, int M, const int32_t* tile_policy, float* logits,
                          int32_t* actions, float* logp, float* values, int deterministic, uint64_t seed, uint64_t offset,
-                         const uint64_t* d_offset, void* stream) {
+                         const uint64_t* d_offset, void* stream, long long* prof = nullptr, int* ctas_out = nullptr) {
     if (p == nullptr || obs == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL argument");
     if (M < 1) return fail(OCB_ERR_INVALID_ARG, "M must be >= 1");
     if ((reinterpret_cast<uintptr_t>(obs) & 3u) != 0) return fail(OCB_ERR_INVALID_ARG, "obs must be 4-byte aligned");
@@ -792,7 +868,12 @@ static int policy_launch(ocb_policy* p, int net_mask, const int8_t* obs, int M, 
     } else {
         ctas = prm.tiles < p->sm_count ? prm.tiles : p->sm_count;
     }
-    policy_fwd_kernel<<<ctas, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(prm);
+    prm.prof = prof;
+    if (ctas_out) *ctas_out = ctas;
+    if (prof != nullptr)
+        policy_fwd_kernel<true><<<ctas, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(prm);
+    else
+        policy_fwd_kernel<false><<<ctas, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(prm);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "policy kernel launch failed: %s", cudaGetErrorString(err));
     p->calls += 1;
@@ -824,4 +905,29 @@ extern "C" int ocb_policy_info(const ocb_policy* p, int* ring_slots, int* chunks
     if (chunks_per_unit) *chunks_per_unit = p->L.chunks;
     if (smem_bytes) *smem_bytes = (int)p->smem_bytes;
     return OCB_OK;
+}
+
+// Diagnostic: one fused forward with the instrumented build of the kernel.  h_prof (HOST, int64
+// [max_ctas][4 roles: epilogue, loader, MMA, producer][16]) receives per role the total cycles ([0])
+// and the cycles stalled on each hand-off (enum PW_* in policy_kernels.cu).  Returns the CTA count.
+extern "C" int ocb_policy_debug_profile(ocb_policy* p, const int8_t* obs, int M, const int32_t* tile_policy, float* values,
+                                        int32_t* actions, int64_t* h_prof, int max_ctas) {
+    if (p == nullptr || h_prof == nullptr || values == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL argument");
+    DeviceGuard guard(p->device);
+    long long* d_prof = nullptr;
+    const size_t n = (size_t)p->sm_count * 4 * PW_COUNT;
+    if (max_ctas < p->sm_count) return fail(OCB_ERR_INVALID_ARG, "h_prof too small (%d CTAs needed)", p->sm_count);
+    cudaError_t err = cudaMalloc(&d_prof, n * sizeof(long long));
+    if (err == cudaSuccess) err = cudaMemset(d_prof, 0, n * sizeof(long long));
+    int ctas = 0;
+    int rc = OCB_OK;
+    if (err == cudaSuccess) rc = policy_launch(p, 3, obs, M, tile_policy, nullptr, actions, nullptr, values, 1, 0, 0, nullptr, nullptr, d_prof, &ctas);
+    if (err == cudaSuccess && rc == OCB_OK) err = cudaMemcpy(h_prof, d_prof, n * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(d_prof);
+    if (rc != OCB_OK) return rc;
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OCB_ERR_CUDA, "ocb_policy_debug_profile: %s", cudaGetErrorString(err));
+    }
+    return ctas;
 }

@@ -212,6 +212,12 @@ int ocb_policy_forward(ocb_policy* pol, const int8_t* obs, int M, const int32_t*
  * unit (ring >= chunks means the weights stay resident), dynamic shared memory per CTA */
 int ocb_policy_info(const ocb_policy* pol, int* ring_slots, int* chunks_per_unit, int* smem_bytes);
 
+/* diagnostic: one fused forward with the instrumented kernel build; h_prof (HOST) int64
+ * [max_ctas][4 roles: epilogue, loader, MMA issuer, producer][16] = total cycles and cycles stalled
+ * per hand-off; returns the number of CTAs launched (or a negative error) */
+int ocb_policy_debug_profile(ocb_policy* pol, const int8_t* obs, int M, const int32_t* tile_policy, float* values,
+                             int32_t* actions, int64_t* h_prof, int max_ctas);
+
 /* ------------------------------------------------------- device-resident self-play / cross-play rollout */
 /* DEVICE address of the env's step counter (uint64, += K after every K-step launch) */
 const uint64_t* ocb_step_counter_device(const ocb_env* env);
