@@ -56,6 +56,7 @@ PROTOTYPES = {
     "ocb_policy_destroy": (_i, [_vp]),
     "ocb_policy_set_weights": (_i, [_vp, _i, _i] + [_vp] * 8),
     "ocb_policy_act": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _u64, _u64, _vp]),
+    "ocb_policy_act_ex": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _u64, _u64, _vp, _vp]),
     "ocb_policy_value": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "ocb_policy_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _u64, _u64, _vp, _vp]),
     "ocb_policy_info": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),

@@ -438,21 +438,27 @@ extern "C" int ocb_rollout_policy(ocb_env* e, ocb_policy* pol, int T, const int3
                                   int32_t* actions, float* logp, float* values, int32_t* reward, int32_t* done,
                                   int deterministic, uint64_t seed, void* stream) {
     if (e == nullptr || pol == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL handle");
-    if (obs_slab == nullptr || actions == nullptr || values == nullptr)
-        return fail(OCB_ERR_INVALID_ARG, "obs_slab, actions and values are required");
+    if (obs_slab == nullptr || actions == nullptr) return fail(OCB_ERR_INVALID_ARG, "obs_slab and actions are required");
     if (T < 1) return fail(OCB_ERR_INVALID_ARG, "T must be >= 1");
     if (e->P != 2) return fail(OCB_ERR_UNSUPPORTED, "the policy rollout supports 2 players");
     const size_t PN = (size_t)e->P * e->N, obs_step = PN * (size_t)e->SC;
     const int M = (int)PN;
+    const uint64_t* ctr = reinterpret_cast<const uint64_t*>(e->d_step_counter);
     for (int t = 0; t < T; ++t) {
-        int rc = ocb_policy_forward(pol, obs_slab + t * obs_step, M, tile_policy, actions + t * PN,
-                                    logp ? logp + t * PN : nullptr, nullptr, values + t * PN, deterministic, seed, 0,
-                                    reinterpret_cast<const uint64_t*>(e->d_step_counter), stream);
+        int rc;
+        if (values != nullptr)
+            rc = ocb_policy_forward(pol, obs_slab + t * obs_step, M, tile_policy, actions + t * PN,
+                                    logp ? logp + t * PN : nullptr, nullptr, values + t * PN, deterministic, seed, 0, ctr,
+                                    stream);
+        else  // evaluation rollouts (train/testing.py:39-59, cross-play scoring) need no critic
+            rc = ocb_policy_act_ex(pol, obs_slab + t * obs_step, M, tile_policy, actions + t * PN,
+                                   logp ? logp + t * PN : nullptr, nullptr, deterministic, seed, 0, ctr, stream);
         if (rc != OCB_OK) return rc;
         rc = ocb_step(e, actions + t * PN, obs_slab + (t + 1) * obs_step, reward ? reward + t * PN : nullptr,
                       done ? done + (size_t)t * e->N : nullptr, stream);
         if (rc != OCB_OK) return rc;
     }
+    if (values == nullptr) return OCB_OK;
     // bootstrap value of the observation after the last step (MainPlayer.compute_one,
     // train/MAPPO/main_player.py:293-307)
     return ocb_policy_value(pol, obs_slab + (size_t)T * obs_step, M, tile_policy, values + (size_t)T * PN, stream);

@@ -886,6 +886,12 @@ extern "C" int ocb_policy_act(ocb_policy* p, const int8_t* obs, int M, const int
     return policy_launch(p, 1, obs, M, tile_policy, logits, actions, logp, nullptr, deterministic, seed, offset, nullptr, stream);
 }
 
+extern "C" int ocb_policy_act_ex(ocb_policy* p, const int8_t* obs, int M, const int32_t* tile_policy, int32_t* actions,
+                                 float* logp, float* logits, int deterministic, uint64_t seed, uint64_t offset,
+                                 const uint64_t* d_offset, void* stream) {
+    return policy_launch(p, 1, obs, M, tile_policy, logits, actions, logp, nullptr, deterministic, seed, offset, d_offset, stream);
+}
+
 extern "C" int ocb_policy_value(ocb_policy* p, const int8_t* obs, int M, const int32_t* tile_policy, float* values,
                                 void* stream) {
     if (values == nullptr) return fail(OCB_ERR_INVALID_ARG, "values is NULL");

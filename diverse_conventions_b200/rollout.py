@@ -1,0 +1,207 @@
+"""Device-resident self-play / cross-play rollouts (``ocb_rollout_policy``).
+
+Replaces the host-driven rollout half of the reference trainers:
+
+* ``MainPlayer.collect_episode`` / ``next_step`` (train/MAPPO/main_player.py:91-112, 211-261)
+  with the partner seat of ``CentralizedAgent.get_action`` (train/partner_agents.py:28-63):
+  per env step 2 actor + 2 critic forwards, ~40 torch launches and a D2H sync on dones.  Here a
+  T-step rollout is 2T+1 launches issued from C (or ONE CUDA-graph launch) and nothing
+  synchronises; per-world episode returns are accumulated on the device.
+* the slice-wise policy multiplexing of ``XDPlayer.next_step`` (train/XD/xd_player.py:177-230) /
+  ``CentralizedMultiAgent`` (train/partner_agents.py:87-137): contiguous world slices are driven
+  by different (seat-0 policy, seat-1 policy) pairs through a per-128-row ``tile_policy`` table.
+
+The kernels write straight into the PPO rollout buffer.  The buffer is kept SEAT-MAJOR
+(``[T(+1), P, N, ...]``, the env's native layout, so every store is contiguous);
+``RolloutBuffer.shared_buffer_views()`` exposes it with the axis order of the reference's
+``SharedReplayBuffer`` (train/MAPPO/utils/shared_buffer.py:45-76: ``[T(+1), N, P, ...]``) as
+zero-copy permuted views, observations stay int8 (the reference stores two fp32 copies).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _native
+from .overcooked_env import B200Overcooked, _ptr
+from .policy import FusedPolicy
+
+TILE = FusedPolicy.TILE
+
+
+class RolloutBuffer:
+    """Seat-major PPO rollout storage on the device (one allocation per field)."""
+
+    def __init__(self, env: B200Overcooked, T: int, with_critic: bool = True, with_logp: bool = True):
+        P, N, dev = env.num_players, env.num_envs, env.sim_device
+        self.T, self.P, self.N = T, P, N
+        self.obs = torch.empty((T + 1, P, N, env.width, env.height, env.channels), dtype=torch.int8, device=dev)
+        self.actions = torch.empty((T, P, N), dtype=torch.int32, device=dev)
+        self.action_log_probs = torch.empty((T, P, N), dtype=torch.float32, device=dev) if with_logp else None
+        self.value_preds = torch.empty((T + 1, P, N), dtype=torch.float32, device=dev) if with_critic else None
+        self.rewards = torch.empty((T, P, N), dtype=torch.int32, device=dev)
+        self.dones = torch.empty((T, N), dtype=torch.int32, device=dev)
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in
+                   (self.obs, self.actions, self.action_log_probs, self.value_preds, self.rewards, self.dones)
+                   if t is not None)
+
+    def shared_buffer_views(self) -> Dict[str, torch.Tensor]:
+        """Zero-copy views with the reference's SharedReplayBuffer names and axis order
+        (shared_buffer.py:45-76).  ``share_obs`` is ``obs`` (state == obs for Overcooked,
+        envs/overcooked2_env.py:110); ``masks[t+1] = 1 - done[t]`` is returned for t >= 0
+        (masks[0] belongs to the previous rollout, shared_buffer.py:222-232)."""
+        sw = lambda t: None if t is None else t.transpose(1, 2)  # [*, P, N, ...] -> [*, N, P, ...]
+        obs = sw(self.obs)
+        not_done = (1 - self.dones).to(torch.float32)  # [T, N]
+        return {
+            "obs": obs, "share_obs": obs,
+            "actions": sw(self.actions).unsqueeze(-1),
+            "action_log_probs": None if self.action_log_probs is None else sw(self.action_log_probs).unsqueeze(-1),
+            "value_preds": None if self.value_preds is None else sw(self.value_preds).unsqueeze(-1),
+            "rewards": sw(self.rewards).unsqueeze(-1),
+            "masks_next": not_done[:, :, None, None].expand(self.T, self.N, self.P, 1),
+        }
+
+
+class PolicyRollout:
+    """T-step on-device rollout of one env handle under one ``FusedPolicy`` handle.
+
+    ``tile_policy`` (int32 ``[ceil(P*N/128)]``, device) selects the (actor, critic) weight set per
+    tile of 128 agent rows; rows are seat-major (row = seat*N + world).  ``None`` = set 0 for
+    everybody (plain self-play, train/trainer.py:41-44)."""
+
+    def __init__(self, env: B200Overcooked, policy: FusedPolicy, T: int, tile_policy: Optional[torch.Tensor] = None,
+                 with_critic: bool = True, with_logp: bool = True, seed: int = 0, use_graph: bool = False):
+        if env.num_players != 2:
+            raise ValueError("the policy rollout supports 2 players")
+        if env.sim_device != policy.device:
+            raise ValueError("env and policy live on different devices")
+        if (policy.layout.width, policy.layout.height) != (env.width, env.height):
+            raise ValueError("env and policy were built for different layouts")
+        M = env.num_players * env.num_envs
+        if tile_policy is not None:
+            if tile_policy.dtype != torch.int32 or tile_policy.numel() != (M + TILE - 1) // TILE:
+                raise ValueError("tile_policy must be int32 [%d]" % ((M + TILE - 1) // TILE))
+            tile_policy = tile_policy.to(env.sim_device).contiguous()
+        self.env, self.policy, self.T, self.seed = env, policy, T, seed
+        self.tile_policy = tile_policy
+        self.buf = RolloutBuffer(env, T, with_critic, with_logp)
+        self._lib = _native.lib()
+        self._primed = False
+        self._graphs = {}
+        self.use_graph = use_graph
+        self.rollouts = 0
+
+    # ------------------------------------------------------------------ launches
+    def _issue(self, deterministic: bool):
+        b, env = self.buf, self.env
+        stream = ctypes.c_void_p(torch.cuda.current_stream(env.sim_device).cuda_stream)
+        _native.check(self._lib.ocb_rollout_policy(
+            env._h, self.policy._h, self.T, _ptr(self.tile_policy), _ptr(b.obs), _ptr(b.actions),
+            _ptr(b.action_log_probs), _ptr(b.value_preds), _ptr(b.rewards), _ptr(b.dones), int(deterministic),
+            self.seed, stream))
+
+    def prime(self):
+        """slot 0 <- observation of the current state (first rollout) or the last slot of the
+        previous rollout (SharedReplayBuffer.after_update, shared_buffer.py:222-226)"""
+        with torch.cuda.device(self.env.sim_device):
+            if not self._primed:
+                _native.check(self._lib.ocb_observe(self.env._h, _ptr(self.buf.obs[0]), self.env._stream()))
+                self._primed = True
+            else:
+                self.buf.obs[0].copy_(self.buf.obs[self.T])
+
+    def collect(self, deterministic: bool = False) -> RolloutBuffer:
+        """One T-step rollout, asynchronous on torch's current stream."""
+        with torch.cuda.device(self.env.sim_device):
+            self.prime()
+            if not self.use_graph:
+                self._issue(deterministic)
+            else:
+                g = self._graphs.get(bool(deterministic))
+                if g is None:
+                    g = self._capture(deterministic)
+                g.replay()
+        self.rollouts += 1
+        return self.buf
+
+    def _capture(self, deterministic: bool):
+        """capture the 2T+1 launches once; replays read the sampling offset from the device step
+        counter, so they draw fresh actions"""
+        torch.cuda.synchronize(self.env.sim_device)
+        # capture does not execute: the env state is untouched, only the launch sequence is recorded
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._issue(deterministic)
+        self._graphs[bool(deterministic)] = g
+        return g
+
+    # ------------------------------------------------------------------ scores
+    def episode_stats(self):
+        return self.env.episode_stats()
+
+    def mean_episode_return(self) -> float:
+        rs, ep = self.env.episode_stats()
+        n = int(ep.sum().item())
+        return float(rs.sum().item()) / n if n else float("nan")
+
+
+# ---------------------------------------------------------------------------- cross-play
+def pair_tile_policy(pairs: Sequence[Sequence[int]], worlds_per_pair: int, device=None) -> torch.Tensor:
+    """tile_policy of an env whose worlds are ``len(pairs)`` contiguous slices of ``worlds_per_pair``
+    worlds, slice s played by (seat 0: policy pairs[s][0], seat 1: policy pairs[s][1]) — the layout of
+    XDPlayer / CentralizedMultiAgent (xd_player.py:190-207, partner_agents.py:97-111) generalised to
+    arbitrary pairs.  Rows are seat-major, so the table is [seat-0 tiles..., seat-1 tiles...]."""
+    if worlds_per_pair % TILE != 0:
+        raise ValueError("worlds_per_pair must be a multiple of %d (one weight set per 128-row tile)" % TILE)
+    tiles_per_pair = worlds_per_pair // TILE
+    p = torch.as_tensor(list(pairs), dtype=torch.int32).reshape(-1, 2)
+    table = torch.cat([p[:, 0].repeat_interleave(tiles_per_pair), p[:, 1].repeat_interleave(tiles_per_pair)])
+    return table.to(device) if device is not None else table
+
+
+class CrossPlayEvaluator:
+    """Cross-play return matrix of a population (BASELINE config 5; the all-pairs generalisation of
+    the xp_scores of train/XD/xd_player.py:143-149 and of train/testing.py:39-59).
+
+    This rank evaluates ``pairs`` (a list of (i, j) policy indices): one env with
+    ``len(pairs) * worlds_per_pair`` worlds, actors only, one episode of ``horizon`` steps per world.
+    ``run()`` returns per-pair (sum of episode returns, number of episodes) on the device;
+    ``sharding.gather_pair_matrix`` assembles the [n, n] matrix across ranks."""
+
+    def __init__(self, layout: str, policy: FusedPolicy, pairs, worlds_per_pair: int = 1024, horizon: int = 400,
+                 gpu_id: int = 0, seed: int = 0, world_offset: int = 0, chunk_steps: int = 50, use_graph: bool = True,
+                 deterministic: bool = False):
+        self.pairs = [tuple(int(v) for v in p) for p in pairs]
+        if not self.pairs:
+            raise ValueError("no pairs on this rank")
+        if max(max(p) for p in self.pairs) >= policy.n_policies:
+            raise ValueError("pair refers to a policy the handle does not hold")
+        if horizon % chunk_steps != 0:
+            raise ValueError("horizon must be a multiple of chunk_steps")
+        self.worlds_per_pair, self.horizon, self.chunk_steps = worlds_per_pair, horizon, chunk_steps
+        self.deterministic = deterministic
+        N = len(self.pairs) * worlds_per_pair
+        self.env = B200Overcooked(layout, N, gpu_id, horizon=horizon, seed=seed, world_offset=world_offset)
+        table = pair_tile_policy(self.pairs, worlds_per_pair, self.env.sim_device)
+        # the slab holds chunk_steps observations, not the whole episode: evaluation keeps no trajectory
+        self.rollout = PolicyRollout(self.env, policy, chunk_steps, table, with_critic=False, with_logp=False, seed=seed,
+                                     use_graph=use_graph)
+
+    def run(self):
+        """one full episode per world -> (return_sum int64 [pairs], episodes int64 [pairs]) on the device"""
+        self.env.n_reset()
+        self.env.clear_episode_stats()
+        self.rollout._primed = False
+        for _ in range(self.horizon // self.chunk_steps):
+            self.rollout.collect(self.deterministic)
+        rs, ep = self.env.episode_stats()
+        n = len(self.pairs)
+        return rs.view(n, self.worlds_per_pair).sum(1), ep.view(n, self.worlds_per_pair).sum(1, dtype=torch.int64)
+
+    def close(self):
+        self.env.close()

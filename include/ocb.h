@@ -197,6 +197,10 @@ int ocb_policy_set_weights(ocb_policy* pol, int policy, int net, const float* co
  * keyed by (seed, row, offset). */
 int ocb_policy_act(ocb_policy* pol, const int8_t* obs, int M, const int32_t* tile_policy, int32_t* actions,
                    float* logp, float* logits, int deterministic, uint64_t seed, uint64_t offset, void* stream);
+/* same with a DEVICE-resident addend of `offset` (see ocb_policy_forward) */
+int ocb_policy_act_ex(ocb_policy* pol, const int8_t* obs, int M, const int32_t* tile_policy, int32_t* actions,
+                      float* logp, float* logits, int deterministic, uint64_t seed, uint64_t offset,
+                      const uint64_t* d_offset, void* stream);
 /* critic: values float [M] */
 int ocb_policy_value(ocb_policy* pol, const int8_t* obs, int M, const int32_t* tile_policy, float* values,
                      void* stream);
@@ -231,7 +235,10 @@ const uint64_t* ocb_step_counter_device(const ocb_env* env);
  * (ocb_reset / ocb_observe).  Layouts (SharedReplayBuffer, train/MAPPO/utils/shared_buffer.py:45-76,
  * kept seat-major): obs_slab [T+1,P,N,W,H,C] int8, actions [T,P,N] int32, logp [T,P,N] f32,
  * values [T+1,P,N] f32, reward [T,P,N] int32, done [T,N] int32 (masks = 1 - done).
- * logp, reward, done may be NULL.  2*T+1 launches on `stream`, no synchronisation. */
+ * logp, reward, done may be NULL; values may be NULL too, then only the actors run (evaluation
+ * and cross-play scoring, train/testing.py:39-59).  2*T+1 launches on `stream`, no
+ * synchronisation; the sequence is CUDA-graph capturable (sampling offsets are read from the
+ * device-side step counter, so a replayed graph draws fresh actions). */
 int ocb_rollout_policy(ocb_env* env, ocb_policy* pol, int T, const int32_t* tile_policy, int8_t* obs_slab,
                        int32_t* actions, float* logp, float* values, int32_t* reward, int32_t* done,
                        int deterministic, uint64_t seed, void* stream);

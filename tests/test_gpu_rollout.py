@@ -1,0 +1,224 @@
+"""GPU tests of the device-resident self-play / cross-play rollout (ocb_rollout_policy).
+
+Checks, through the C ABI:
+  * the trajectory the kernels wrote (observations, rewards, dones) is bit-identical to the
+    CPU oracle replaying the actions the policy kernel chose;
+  * at every step the recorded log-probs / values / actions are what a plain PyTorch fp32
+    forward of the same networks gives on the recorded observations (tolerance below);
+  * cross-play slices run the weight sets the pair table names, and the per-pair return
+    matrix equals the oracle's returns;
+  * a CUDA-graph replay is equivalent to issuing the launches one by one.
+"""
+import numpy as np
+import pytest
+import torch
+
+from diverse_conventions_b200 import layouts, sharding
+from diverse_conventions_b200.overcooked_env import B200Overcooked
+from diverse_conventions_b200.policy import FusedPolicy, PolicyNet, log_softmax_sample
+from diverse_conventions_b200.rollout import CrossPlayEvaluator, PolicyRollout, pair_tile_policy
+from oracle.c_oracle import COracle
+
+pytestmark = pytest.mark.gpu
+
+ATOL_LOGP = 2e-4  # log-probs are O(1); logits agree to ~1e-5 relative (north star: 1e-3)
+REL_TOL = 2e-4
+
+
+def make_policies(lp, n, gain=2.0, seed0=11):
+    actors = [PolicyNet("actor", lp.width, lp.height, lp.channels, 64).init_like_reference(seed0 + i, gain=gain)
+              for i in range(n)]
+    critics = [PolicyNet("critic", lp.width, lp.height, lp.channels, 64).init_like_reference(seed0 + 500 + i)
+               for i in range(n)]
+    for net in actors + critics:
+        for b in (net.conv_b, net.fc1_b, net.fc2_b, net.head_b):
+            b.uniform_(-0.1, 0.1)
+    pol = FusedPolicy(lp, 64, n)
+    for i in range(n):
+        pol.set_weights(i, actors[i], critics[i])
+    return pol, actors, critics
+
+
+def replay_through_oracle(lp, N, buf):
+    orc = COracle(lp, N)
+    first = orc.observe()
+    o, r, d = orc.rollout(buf.actions.cpu().numpy().astype(np.uint8))
+    return np.concatenate([first[None], o]), r, d, orc
+
+
+@pytest.mark.parametrize("layout,N,T", [("simple", 384, 70), ("random1", 200, 45)])
+def test_selfplay_rollout_matches_oracle_and_torch(layout, N, T):
+    horizon = 30  # several auto-resets inside one rollout
+    lp = layouts.load_layout(layout, horizon)
+    pol, actors, critics = make_policies(lp, 1)
+    env = B200Overcooked(layout, N, 0, horizon=horizon, seed=5)
+    ro = PolicyRollout(env, pol, T, seed=123)
+    buf = ro.collect()
+    torch.cuda.synchronize()
+
+    obs, rew, done, orc = replay_through_oracle(lp, N, buf)
+    assert np.array_equal(buf.obs.cpu().numpy(), obs)
+    assert np.array_equal(buf.rewards.cpu().numpy(), rew) and np.array_equal(buf.dones.cpu().numpy(), done)
+    assert np.array_equal(env.get_state(), orc.state)
+    assert done.sum() == N * (T // horizon)
+
+    acts = buf.actions.cpu()
+    assert int(acts.min()) >= 0 and int(acts.max()) <= 5
+    rows = buf.obs.cpu().reshape(T + 1, 2 * N, lp.width, lp.height, lp.channels)
+    for t in list(range(0, T, 9)) + [T - 1]:
+        logits = actors[0].forward(rows[t])
+        ref_lp = log_softmax_sample(logits, acts[t].reshape(-1))
+        assert torch.allclose(buf.action_log_probs[t].cpu().reshape(-1), ref_lp, atol=ATOL_LOGP), t
+        ref_v = critics[0].forward(rows[t])[:, 0]
+        err = (buf.value_preds[t].cpu().reshape(-1) - ref_v).abs().max() / ref_v.abs().max()
+        assert float(err) < REL_TOL, t
+    ref_v = critics[0].forward(rows[T])[:, 0]
+    assert float((buf.value_preds[T].cpu().reshape(-1) - ref_v).abs().max() / ref_v.abs().max()) < REL_TOL
+    # sampled, not arg-max: a stochastic policy with gain 2 must not always pick the mode
+    logits0 = actors[0].forward(rows[0])
+    assert not torch.equal(acts[0].reshape(-1).long(), logits0.argmax(-1))
+
+    # device-side score keeping == oracle episode returns
+    rs, ep = env.episode_stats()
+    assert int(ep.sum()) == int(done.sum())
+    ret = np.zeros(N, dtype=np.int64)
+    total = 0
+    for t in range(T):
+        ret += rew[t, 0]
+        total += int(ret[done[t] != 0].sum())
+        ret[done[t] != 0] = 0
+    assert int(rs.sum()) == total
+
+    # the second rollout continues from the last observation (after_update semantics)
+    last = buf.obs[T].clone()
+    buf2 = ro.collect()
+    torch.cuda.synchronize()
+    assert torch.equal(buf2.obs[0], last)
+    assert ro.rollouts == 2 and env.step_count == 2 * T
+
+
+def test_shared_buffer_views_follow_the_reference_axis_order():
+    lp = layouts.load_layout("simple", 400)
+    pol, _, _ = make_policies(lp, 1)
+    N, T = 128, 6
+    env = B200Overcooked("simple", N, 0, horizon=400, seed=1)
+    buf = PolicyRollout(env, pol, T).collect()
+    torch.cuda.synchronize()
+    v = buf.shared_buffer_views()
+    assert v["obs"].shape == (T + 1, N, 2, 5, 4, 20) and v["share_obs"] is v["obs"]
+    assert v["actions"].shape == (T, N, 2, 1) and v["action_log_probs"].shape == (T, N, 2, 1)
+    assert v["value_preds"].shape == (T + 1, N, 2, 1) and v["rewards"].shape == (T, N, 2, 1)
+    assert v["masks_next"].shape == (T, N, 2, 1)
+    assert v["obs"].data_ptr() == buf.obs.data_ptr()  # a view, not a copy
+    assert torch.equal(v["actions"][3, 17, 1, 0], buf.actions[3, 1, 17])
+    assert torch.equal(v["obs"][2, 5, 1], buf.obs[2, 1, 5])
+
+
+def test_deterministic_rollout_graph_replay_equals_plain_launches():
+    lp = layouts.load_layout("random0", 25)
+    pol, _, _ = make_policies(lp, 1)
+    N, T = 256, 40
+    outs = []
+    for use_graph in (False, True):
+        env = B200Overcooked("random0", N, 0, horizon=25, seed=2)
+        ro = PolicyRollout(env, pol, T, use_graph=use_graph, seed=9)
+        a = ro.collect(deterministic=True)
+        first = (a.obs.clone(), a.actions.clone(), a.value_preds.clone(), a.rewards.clone(), a.dones.clone())
+        b = ro.collect(deterministic=True)
+        torch.cuda.synchronize()
+        outs.append((first, (b.obs.clone(), b.actions.clone(), b.value_preds.clone(), b.rewards.clone(), b.dones.clone()),
+                     env.get_state()))
+        env.close()
+    for k in range(2):
+        for x, y in zip(outs[0][k], outs[1][k]):
+            assert torch.equal(x, y)
+    assert np.array_equal(outs[0][2], outs[1][2])
+
+
+def test_sampled_graph_replays_draw_fresh_actions_and_stay_exact():
+    lp = layouts.load_layout("simple", 400)
+    pol, actors, _ = make_policies(lp, 1)
+    N, T = 256, 12
+    env = B200Overcooked("simple", N, 0, horizon=400, seed=4)
+    ro = PolicyRollout(env, pol, T, use_graph=True, seed=77)
+    orc = COracle(lp, N)
+    prev_actions = None
+    for k in range(3):
+        buf = ro.collect()
+        torch.cuda.synchronize()
+        o, r, d = orc.rollout(buf.actions.cpu().numpy().astype(np.uint8))
+        assert np.array_equal(buf.obs[1:].cpu().numpy(), o) and np.array_equal(buf.rewards.cpu().numpy(), r)
+        if prev_actions is not None:
+            assert not torch.equal(prev_actions[0], buf.actions[0])
+        prev_actions = buf.actions.clone()
+    assert np.array_equal(env.get_state(), orc.state)
+
+
+def test_crossplay_slices_use_the_named_policies_and_return_matrix_matches_oracle():
+    layout, horizon, wpp, n_pol = "random1", 40, 128, 3
+    lp = layouts.load_layout(layout, horizon)
+    pol, actors, _ = make_policies(lp, n_pol, gain=3.0)
+    pairs = sharding.all_pairs(n_pol)
+    table = pair_tile_policy(pairs, wpp)
+    assert table.tolist() == [p[0] for p in pairs] + [p[1] for p in pairs]
+
+    ev = CrossPlayEvaluator(layout, pol, pairs, worlds_per_pair=wpp, horizon=horizon, seed=3, chunk_steps=20,
+                            use_graph=True)
+    N = ev.env.num_envs
+    # record the whole episode by chunks to replay it
+    ev.env.n_reset()
+    ev.env.clear_episode_stats()
+    ev.rollout._primed = False
+    acts, obs = [], []
+    for _ in range(horizon // 20):
+        b = ev.rollout.collect()
+        torch.cuda.synchronize()
+        acts.append(b.actions.clone())
+        obs.append(b.obs[:-1].clone())
+    acts, obs = torch.cat(acts).cpu(), torch.cat(obs).cpu()
+    rs, ep = ev.env.episode_stats()
+    rs, ep = rs.view(len(pairs), wpp).sum(1), ep.view(len(pairs), wpp).sum(1)
+
+    # (1) environment side: oracle replay gives the same per-pair returns
+    orc = COracle(lp, N)
+    _, rew, done = orc.rollout(acts.numpy().astype(np.uint8), with_obs=False)
+    assert done[-1].all() and done[:-1].sum() == 0
+    ref_ret = rew[:, 0].sum(0).reshape(len(pairs), wpp).sum(1)
+    assert np.array_equal(rs.cpu().numpy(), ref_ret) and (ep.cpu().numpy() == wpp).all()
+
+    # (2) policy side: seat s of slice k acted with policy pairs[k][s]; the sampled actions follow
+    # that policy's distribution (mean log-prob under the right actor beats every wrong actor)
+    rows = obs.reshape(horizon, 2, len(pairs), wpp, lp.width, lp.height, lp.channels)
+    a = acts.reshape(horizon, 2, len(pairs), wpp)
+    for k in (1, 5, 6):
+        for seat in (0, 1):
+            o = rows[::4, seat, k].reshape(-1, lp.width, lp.height, lp.channels)
+            aa = a[::4, seat, k].reshape(-1)
+            scores = [float(log_softmax_sample(actors[q].forward(o), aa).mean()) for q in range(n_pol)]
+            assert int(np.argmax(scores)) == pairs[k][seat], (k, seat, scores)
+
+    # (3) run() + single-rank matrix assembly
+    rs2, ep2 = ev.run()
+    mean, eps = sharding.gather_pair_matrix(pairs, rs2, ep2, n_pol)
+    assert mean.shape == (n_pol, n_pol) and int(eps.sum()) == N
+    assert torch.isfinite(mean).all()
+    ev.close()
+
+
+def test_actor_only_rollout_and_argument_checks():
+    lp = layouts.load_layout("simple", 400)
+    pol, _, _ = make_policies(lp, 2)
+    env = B200Overcooked("simple", 256, 0, horizon=400, seed=1)
+    ro = PolicyRollout(env, pol, 5, with_critic=False, with_logp=False)
+    buf = ro.collect()
+    torch.cuda.synchronize()
+    assert buf.value_preds is None and buf.action_log_probs is None
+    o, r, _, _ = replay_through_oracle(lp, 256, buf)
+    assert np.array_equal(buf.obs.cpu().numpy(), o)
+    with pytest.raises(ValueError):
+        PolicyRollout(env, pol, 5, tile_policy=torch.zeros(3, dtype=torch.int32))
+    with pytest.raises(ValueError):
+        pair_tile_policy([(0, 1)], 100)
+    other = FusedPolicy(layouts.load_layout("random1", 400), 64, 1)
+    with pytest.raises(ValueError):
+        PolicyRollout(env, other, 5)
