@@ -7,9 +7,10 @@
 //
 // One persistent, warp-specialised kernel runs BOTH networks (even CTAs the actor, odd CTAs the
 // critic); a work unit is (tile of 128 observation rows, network):
-//   * loader warps (4): coalesced loads of one grid column of the tile ([128 rows] x H cells x
-//     20 B, software-prefetched in registers), transposed through a small staging buffer into
-//     per-cell [128 x 16] bf16 K-major operand blocks held in a ring of 4 grid columns.  The
+//   * loader warps (2 groups of 4, alternating grid columns): coalesced loads of one grid column
+//     of the tile ([128 rows] x H cells x 20 B, software-prefetched in registers), transposed
+//     through a small staging buffer into per-cell [128 x 16] bf16 K-major operand blocks held in
+//     a ring of 4 grid columns (int8 -> bf16 is one PRMT + one HADD2.BF16 per channel pair).  The
 //     convolution needs NO im2col: for output position (ox, oy) the k-slice of window cell
 //     (dx, dy) is the block of cell (ox+dx, oy+dy), so the conv is 9 x (hi, lo) tcgen05.mma
 //     (M128 N32 K16) per position pointing at different blocks; the 5 static terrain channels
@@ -18,10 +19,11 @@
 //     columns, FC1 and FC2: 2 x 64 columns each, double-buffered across units) and the issue
 //     order keeps the conv up to 3 positions ahead of the FC1 partial sums so the tensor pipe
 //     has work while the epilogue warps run;
-//   * epilogue warps (4): tcgen05.ld a conv position, bias + ReLU, split into bf16 hi + lo and
-//     store it as the A operand of the FC1 partial product of that position (2-stage ring);
-//     FC2 flows through the same ring as two more K=32 items fed from the FC1 accumulator;
-//     the tiny head (64 -> 6 | 1), softmax sampling and log-prob run in fp32 on CUDA cores;
+//   * epilogue warps (2 groups of 4, alternating items == A-operand ring stages): tcgen05.ld a
+//     conv position, bias + ReLU, split into bf16 hi + lo and store it as the A operand of the
+//     FC1 partial product of that position (2-stage ring); FC2 flows through the same ring as
+//     two more K=32 items fed from the FC1 accumulator; the tiny head (64 -> 6 | 1) is split by
+//     hidden halves over the two groups, softmax sampling and log-prob run in fp32 on CUDA cores;
 //   * one producer thread streams the FC weights as 8 KB chunks with cp.async.bulk
 //     (global -> shared, mbarrier complete_tx) into a ring; when the whole set fits the ring
 //     the chunks stay resident and are only re-fetched when a tile selects another policy;
@@ -49,7 +51,7 @@ namespace {
 constexpr int kRows = 128;     // rows (agents) per tile == UMMA M
 constexpr int kHid = 64;       // hidden size
 constexpr int kCo = 32;        // conv output channels (hidden / 2)
-constexpr int kSlots = 16;     // bf16 slots per cell: channels 0-9, 15-19, one zero pad
+constexpr int kSlots = 16;     // bf16 slots per cell: channels 0-9, 16-19, 15, one zero pad
 constexpr int kK1 = 9 * kSlots;  // conv K
 constexpr int kCellCols = kSlots / 2;  // TMEM columns of one cell block
 constexpr int kColRing = 4;    // grid columns resident per CTA (3 in use by the conv + 1 being loaded)
@@ -59,7 +61,10 @@ constexpr int kChunk = 8192;   // one FC weight chunk: [64 x 32] bf16 hi | lo
 constexpr int kA2Cols = 32;    // TMEM columns of one FC A-operand stage: [128 x 32] bf16 hi (16) | lo (16)
 constexpr int kMaxRing = 16;   // weight-ring slots (resident when >= chunks per unit)
 constexpr int kMaxH = 6;       // a grid column must fit one warp-wide load (5*H words <= 32)
-constexpr int kThreads = 320;  // warps 0-3 epilogue, 4-7 loader, 8 MMA issuer, 9 weight producer
+constexpr int kEpiWarps = 8;   // warps 0-7: two epilogue groups (group = warp / 4; TMEM lanes 32 (warp % 4) ..)
+constexpr int kLoadWarps = 8;  // warps 8-15: two loader groups
+constexpr int kWarpMma = kEpiWarps + kLoadWarps, kWarpProd = kWarpMma + 1;
+constexpr int kThreads = 32 * (kWarpProd + 1);  // 576
 constexpr int kTmemCols = 512;
 // TMEM map (32-bit columns x 128 lanes = rows of the tile): the A operands live here too, two bf16 per column
 constexpr int kColCells = 0;    // ring of 4 grid columns x H cells x 8 columns ([128 x 16] bf16 each), <= 192
@@ -117,14 +122,15 @@ struct PolicyParams {
 
 // shared-memory carve-up (byte offsets from a 128-byte aligned base)
 struct SmemLayout {
-    int stage, head, wring, bars, total;
+    int stage, head, wring, xbuf, bars, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int H, int npos, int ring, int stage_stride) {
     SmemLayout s;
     int o = 0;
-    s.stage = o, o += al128(4 * 32 * stage_stride * 4);
+    s.stage = o, o += al128(kLoadWarps * 32 * stage_stride * 4);
     s.head = o, o += blob_layout(npos).head_bytes;
     s.wring = o, o += ring * kChunk;
+    s.xbuf = o, o += 2 * kRows * 8 * 4;  // head partial sums of epilogue group 1, by unit parity
     s.bars = o, o += 512;
     s.total = o + 128;  // slack for aligning the dynamic base
     return s;
@@ -140,7 +146,7 @@ enum : int {
     B_W_FULL = 16,                       // [16] bulk copy complete_tx -> MMA
     B_W_EMPTY = 32,                      // [16] MMA commit -> producer
     B_HEAD_FULL = 48,                    //      bulk copy -> MMA, epilogue
-    B_HEAD_EMPTY = 49,                   // [2]  by unit parity: MMA commit + 128 epilogue arrivals -> producer
+    B_HEAD_EMPTY = 49,                   // [2]  by unit parity: MMA commit + 256 epilogue arrivals -> producer
     B_D2_FULL = 51,                      //      MMA commit -> epilogue
     B_D3_FULL = 52,                      //      MMA commit -> epilogue
     B_COUNT = 53
@@ -269,8 +275,15 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
     const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-// small unsigned int (observation byte) -> bf16 bits, exact
-__device__ __forceinline__ uint32_t byte_bf16(uint32_t b) { return __float_as_uint((float)b) >> 16; }
+// two observation bytes (each < 128) of `w` -> packed bf16 pair, exact: 0x43bb is bf16(128 + bb), so
+// one byte permute builds (128 + b_i, 128 + b_j) and one packed subtract removes the 128s.
+// `sel` picks byte i (0-3 of w; 4 = a zero byte) for the low half and byte j for the high half.
+__device__ __forceinline__ uint32_t bytes_bf16x2(uint32_t w, uint32_t sel) {
+    const uint32_t biased = __byte_perm(w, 0x00004300u, sel);
+    const __nv_bfloat162 v = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&biased), __float2bfloat162_rn(128.0f));
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+__host__ __device__ constexpr uint32_t pair_sel(int i, int j) { return (uint32_t)i | (5u << 4) | ((uint32_t)j << 8) | (5u << 12); }
 
 // ---------------------------------------------------------------- unit iteration shared by all roles
 struct UnitRange {
@@ -295,62 +308,72 @@ __device__ __forceinline__ bool blob_changed(const PolicyParams& prm, int t, int
 }
 
 // ---------------------------------------------------------------- roles
-// loader: global observations -> bf16 cell blocks, one grid column at a time
+// loader: global observations -> bf16 cell blocks, one grid column at a time; the two loader
+// groups take alternate columns of the CTA's column stream
 template <bool kProf>
 __device__ __forceinline__ void loader_role(long long* pw, const PolicyParams& prm, const UnitRange ur, uint32_t tmem, uint32_t* s_stage,
                                             uint32_t bars) {
-    const int lw = (threadIdx.x >> 5) - 4, lane = threadIdx.x & 31;
+    const int lwarp = (threadIdx.x >> 5) - kEpiWarps, lg = lwarp >> 2, lw = lwarp & 3, lane = threadIdx.x & 31;
     const int W = prm.W, H = prm.H, SC4 = prm.SC >> 2, seg = 5 * H, stride = prm.stage_stride;
-    uint32_t* stg = s_stage + lw * 32 * stride;
+    uint32_t* stg = s_stage + lwarp * 32 * stride;
     const uint32_t* obs32 = reinterpret_cast<const uint32_t*>(prm.obs);
     const uint32_t tcells = tmem + ((uint32_t)(lw * 32) << 16) + kColCells;  // this warp's 32 TMEM lanes (rows)
     uint32_t pre[32];
+    const bool active = lane < seg;
 
-    auto issue_loads = [&](int t, int x) {
-        const long long r0 = (long long)t * kRows + lw * 32;
+    // column c of the stream = grid column c % W of tile t0 + c / W; (lt, lx) track the column being
+    // prefetched incrementally (no runtime divisions in this latency-bound role)
+    const uint32_t ncols = (uint32_t)(ur.t1 - ur.t0) * (uint32_t)W;
+    int lt = ur.t0, lx = lg;
+    while (lx >= W) lx -= W, ++lt;
+    auto issue_loads = [&]() {
+        const long long r0 = (long long)lt * kRows + lw * 32;
+        if (r0 + 32 <= prm.M) {  // full 32-row slab: constant-stride addresses
+            const uint32_t* p = obs32 + r0 * SC4 + lx * seg + (active ? lane : 0);
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-            long long row = r0 + r;
-            row = row < prm.M ? row : prm.M - 1;
-            pre[r] = lane < seg ? __ldg(obs32 + row * SC4 + x * seg + lane) : 0u;
+            for (int r = 0; r < 32; ++r) pre[r] = active ? __ldg(p + r * SC4) : 0u;
+        } else {  // ragged tail: rows past M re-read the last row (their results are never stored)
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                long long row = r0 + r;
+                row = row < prm.M ? row : prm.M - 1;
+                pre[r] = active ? __ldg(obs32 + row * SC4 + lx * seg + lane) : 0u;
+            }
         }
+        lx += 2;
+        while (lx >= W) lx -= W, ++lt;
     };
-    if (ur.t0 < ur.t1) issue_loads(ur.t0, 0);
-    uint32_t gc = 0;  // running column counter: ring slot and phase
-    for (int t = ur.t0; t < ur.t1; ++t) {
-        for (int x = 0; x < W; ++x, ++gc) {
-            const long long tl0 = kProf ? clock64() : 0;
-            if (lane < seg) {
+    if ((uint32_t)lg < ncols) issue_loads();
+    for (uint32_t gc = lg; gc < ncols; gc += 2) {
+        const long long tl0 = kProf ? clock64() : 0;
+        if (active) {
 #pragma unroll
-                for (int r = 0; r < 32; ++r) stg[r * stride + lane] = pre[r];
-            }
-            __syncwarp();
-            if (kProf) pw[PW_LDG] += clock64() - tl0;
-            if (x + 1 < W) issue_loads(t, x + 1);
-            else if (t + 1 < ur.t1) issue_loads(t + 1, 0);
-            const int slot = gc % kColRing;
-            if (gc >= kColRing) {
-                mbar_wait_p<kProf>(bars + 8 * (B_COL_EMPTY + slot), ((gc / kColRing) - 1) & 1, pw[PW_COL_EMPTY]);
-                tc_fence_after();
-            }
-            const uint32_t* mine = stg + lane * stride;
-            for (int y = 0; y < H; ++y) {
-                uint32_t w[5];
-#pragma unroll
-                for (int q = 0; q < 5; ++q) w[q] = mine[y * 5 + q];
-                auto by = [&](int ch) { return (w[ch >> 2] >> ((ch & 3) * 8)) & 0xFFu; };
-                // chunk 0: channels 0..7 ; chunk 1: channels 8, 9, 15, 16, 17, 18, 19, pad
-                const uint4 c0 = make_uint4(byte_bf16(by(0)) | (byte_bf16(by(1)) << 16), byte_bf16(by(2)) | (byte_bf16(by(3)) << 16),
-                                            byte_bf16(by(4)) | (byte_bf16(by(5)) << 16), byte_bf16(by(6)) | (byte_bf16(by(7)) << 16));
-                const uint4 c1 = make_uint4(byte_bf16(by(8)) | (byte_bf16(by(9)) << 16), byte_bf16(by(15)) | (byte_bf16(by(16)) << 16),
-                                            byte_bf16(by(17)) | (byte_bf16(by(18)) << 16), byte_bf16(by(19)));
-                tmem_st8(tcells + (slot * H + y) * kCellCols, c0, c1);
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(bars + 8 * (B_COL_FULL + slot));
-            __syncwarp();  // the staging rows are rewritten by the next column
+            for (int r = 0; r < 32; ++r) stg[r * stride + lane] = pre[r];
         }
+        __syncwarp();
+        if (kProf) pw[PW_LDG] += clock64() - tl0;
+        if (gc + 2 < ncols) issue_loads();
+        const int slot = gc % kColRing;
+        if (gc >= kColRing) {
+            mbar_wait_p<kProf>(bars + 8 * (B_COL_EMPTY + slot), ((gc / kColRing) - 1) & 1, pw[PW_COL_EMPTY]);
+            tc_fence_after();
+        }
+        const uint32_t* mine = stg + lane * stride;
+        for (int y = 0; y < H; ++y) {
+            uint32_t w[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) w[q] = mine[y * 5 + q];
+            // chunk 0: channels 0..7 ; chunk 1: channels 8, 9, 16, 17, 18, 19, 15, pad (slot_channel[] on the host)
+            const uint4 c0 = make_uint4(bytes_bf16x2(w[0], pair_sel(0, 1)), bytes_bf16x2(w[0], pair_sel(2, 3)),
+                                        bytes_bf16x2(w[1], pair_sel(0, 1)), bytes_bf16x2(w[1], pair_sel(2, 3)));
+            const uint4 c1 = make_uint4(bytes_bf16x2(w[2], pair_sel(0, 1)), bytes_bf16x2(w[4], pair_sel(0, 1)),
+                                        bytes_bf16x2(w[4], pair_sel(2, 3)), bytes_bf16x2(w[3], pair_sel(3, 4)));
+            tmem_st8(tcells + (slot * H + y) * kCellCols, c0, c1);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bars + 8 * (B_COL_FULL + slot));
+        __syncwarp();  // the staging rows are rewritten by the next column
     }
 }
 
@@ -361,7 +384,9 @@ __device__ __forceinline__ void producer_role(long long* pw, const PolicyParams&
     const int R = prm.ring;
     const bool resident = R >= L.chunks;
     const int Reff = resident ? L.chunks : R;
-    uint32_t wc = 0, u = 0;
+    uint32_t u = 0;
+    int slot = 0;
+    uint32_t round = 0;  // completed passes over the ring
     for (int t = ur.t0; t < ur.t1; ++t, ++u) {
         const bool chg = blob_changed(prm, t, ur.t0);
         const uint8_t* blob = prm.blobs + ((size_t)tile_pol(prm, t) * 2 + ur.net) * prm.blob_stride;
@@ -376,9 +401,8 @@ __device__ __forceinline__ void producer_role(long long* pw, const PolicyParams&
             __syncwarp();
         }
         const bool load = !resident || chg;
-        for (int j = 0; j < L.chunks; ++j, ++wc) {
-            const int slot = wc % Reff;
-            if (wc >= (uint32_t)Reff) mbar_wait_p<kProf>(bars + 8 * (B_W_EMPTY + slot), ((wc / Reff) - 1) & 1, pw[PW_W_EMPTY]);
+        for (int j = 0; j < L.chunks; ++j) {
+            if (round > 0) mbar_wait_p<kProf>(bars + 8 * (B_W_EMPTY + slot), (round - 1) & 1, pw[PW_W_EMPTY]);
             if (load) {
                 if (elect_one()) {
                     mbar_arrive_expect_tx(bars + 8 * (B_W_FULL + slot), kChunk);
@@ -387,6 +411,7 @@ __device__ __forceinline__ void producer_role(long long* pw, const PolicyParams&
                 }
                 __syncwarp();
             }
+            if (++slot == Reff) slot = 0, ++round;
         }
     }
 }
@@ -403,14 +428,15 @@ __device__ __forceinline__ void mma_role(long long* pw, const PolicyParams& prm,
     const uint32_t a_wchi = a_head + L.wc_hi, a_wclo = a_head + L.wc_lo;
 
     // conv stream
-    int tc = ur.t0, pc = 0;
+    int tc = ur.t0, pc = 0, ox = 0, oy = 0;
     uint32_t gcb = 0;          // running column index of column 0 of unit tc
     uint32_t convs = 0;        // conv positions issued
     // item stream (FC1 positions, then the two FC2 halves of each unit)
     int ti = ur.t0, ji = 0;
     uint32_t fc1s = 0;         // FC1 items issued
     uint32_t items = 0;        // items issued (A2 ring counter)
-    uint32_t wc = 0;           // weight chunk counter
+    int slot = 0;              // weight-ring slot of the next chunk
+    uint32_t wround = 0;       // completed passes over the weight ring
     uint32_t ui = 0;           // unit counter of the item stream
     uint32_t head_gen = 0;     // head loads waited for so far (conv stream)
     uint32_t w_gen = 0;        // resident mode: ring fills waited for so far (item stream)
@@ -421,7 +447,6 @@ __device__ __forceinline__ void mma_role(long long* pw, const PolicyParams& prm,
         // loaded once the previous unit has drained completely)
         const bool conv_ok = tc < ur.t1 && (int)(convs - fc1s) < kConvAhead && (tc == ti || !blob_changed(prm, tc, ur.t0));
         if (conv_ok) {
-            const int ox = pc / PH, oy = pc - ox * PH;
             if (pc == 0 && blob_changed(prm, tc, ur.t0)) {
                 mbar_wait_p<kProf>(bars + 8 * B_HEAD_FULL, head_gen & 1, pw[PW_HEAD_FULL]);
                 ++head_gen;
@@ -458,7 +483,8 @@ __device__ __forceinline__ void mma_role(long long* pw, const PolicyParams& prm,
             __syncwarp();
             if (kProf) pw[PW_ISSUE_CONV] += clock64() - ti0;
             ++convs;
-            if (++pc == npos) pc = 0, ++tc, gcb += W;
+            if (++oy == PH) oy = 0, ++ox;
+            if (++pc == npos) pc = 0, ox = 0, ++tc, gcb += W;
             continue;
         }
         // ---- one FC item: D2 (+)= A2 x W1_j   or   D3 (+)= A2 x W2_half
@@ -467,9 +493,11 @@ __device__ __forceinline__ void mma_role(long long* pw, const PolicyParams& prm,
             if (resident && w_loaded) ++w_gen;
         }
         const int a2s = items & 1;
-        const int slot = wc % Reff;
         mbar_wait_p<kProf>(bars + 8 * (B_A2_FULL + a2s), (items >> 1) & 1, pw[PW_A2_FULL]);
-        if (w_loaded) mbar_wait_p<kProf>(bars + 8 * (B_W_FULL + slot), resident ? ((w_gen - 1) & 1) : ((wc / Reff) & 1), pw[PW_W_FULL]);
+        // the first FC2 product overwrites the FC1 accumulator: both halves must have been drained, i.e. the
+        // other epilogue group must have published item npos + 1 as well
+        if (ji == npos) mbar_wait_p<kProf>(bars + 8 * (B_A2_FULL + (a2s ^ 1)), ((items + 1) >> 1) & 1, pw[PW_A2_FULL]);
+        if (w_loaded) mbar_wait_p<kProf>(bars + 8 * (B_W_FULL + slot), resident ? ((w_gen - 1) & 1) : (wround & 1), pw[PW_W_FULL]);
         tc_fence_after();
         // FC2 accumulates into the columns of the (already drained) FC1 accumulator of the same unit
         const uint32_t dst = tmem + kColD2 + (ui & 1) * kHid;
@@ -492,19 +520,22 @@ __device__ __forceinline__ void mma_role(long long* pw, const PolicyParams& prm,
         }
         __syncwarp();
         if (kProf) pw[PW_ISSUE_FC] += clock64() - tf0;
-        ++items, ++wc;
+        ++items;
+        if (++slot == Reff) slot = 0, ++wround;
         if (ji < npos) ++fc1s;
         if (++ji == npos + 2) ji = 0, ++ti, ++ui;
     }
 }
 
-// epilogue: TMEM -> bias/ReLU -> bf16 hi/lo A operand; head, sampling and outputs
+// epilogue: TMEM -> bias/ReLU -> bf16 hi/lo A operand; head, sampling and outputs.  Two groups of four
+// warps: group g owns stage g of the A-operand ring, i.e. every other item of the CTA's item stream
+// (items of a unit: npos conv positions, then the two K halves of FC2's input).
 template <bool kProf>
 __device__ __forceinline__ void epilogue_role(long long* pw, const PolicyParams& prm, const UnitRange ur, const BlobLayout L, uint32_t tmem,
-                                              const uint8_t* s_head, uint32_t bars) {
-    const int tid = threadIdx.x, warp = tid >> 5;
+                                              const uint8_t* s_head, float* s_xbuf, uint32_t bars) {
+    const int warp = threadIdx.x >> 5, eg = warp >> 2, trow_id = (warp & 3) * 32 + (threadIdx.x & 31);
     const int npos = prm.npos;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 TMEM lanes
     const float* s_bias1 = reinterpret_cast<const float*>(s_head + L.bias1);
     const float* s_b1 = reinterpret_cast<const float*>(s_head + L.b1);
     const float* s_b2 = reinterpret_cast<const float*>(s_head + L.b2);
@@ -513,75 +544,80 @@ __device__ __forceinline__ void epilogue_role(long long* pw, const PolicyParams&
     unsigned long long offset = prm.offset;
     if (prm.d_offset != nullptr) offset += *prm.d_offset;
 
-    uint32_t d1c = 0, items = 0, u = 0, head_gen = 0;
+    uint32_t u = 0, head_gen = 0;
     for (int t = ur.t0; t < ur.t1; ++t, ++u) {
         if (blob_changed(prm, t, ur.t0)) {
             mbar_wait_p<kProf>(bars + 8 * B_HEAD_FULL, head_gen & 1, pw[PW_HEAD_FULL]);
             ++head_gen;
         }
-        float fc1[64];  // the whole FC1 row: FC2 reuses the accumulator columns, so it is drained in one go
-        for (int j = 0; j < npos + 2; ++j, ++items) {
+        const uint32_t item0 = u * (uint32_t)(npos + 2);
+        for (int j = (int)((item0 ^ (uint32_t)eg) & 1u); j < npos + 2; j += 2) {
+            const uint32_t item = item0 + (uint32_t)j;  // item & 1 == eg: the ring stage of this group
             float v[32];
             const float* bias;
             if (j < npos) {
+                const uint32_t d1c = u * (uint32_t)npos + (uint32_t)j;
                 const int st = d1c % kD1Stages;
                 mbar_wait_p<kProf>(bars + 8 * (B_D1_FULL + st), (d1c / kD1Stages) & 1, pw[PW_D1_FULL]);
                 tc_fence_after();
                 tmem_ld32(trow + kColD1 + st * kCo, v);
-                ++d1c;
                 bias = s_bias1 + j * kCo;
             } else {
-                if (j == npos) {
-                    mbar_wait_p<kProf>(bars + 8 * B_D2_FULL, u & 1, pw[PW_D2_FULL]);
-                    tc_fence_after();
-                    float lo32[32], hi32[32];
-                    tmem_ld32(trow + kColD2 + (u & 1) * kHid, lo32);
-                    tmem_ld32(trow + kColD2 + (u & 1) * kHid + 32, hi32);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) fc1[i] = lo32[i], fc1[32 + i] = hi32[i];
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = j == npos ? fc1[i] : fc1[32 + i];
+                mbar_wait_p<kProf>(bars + 8 * B_D2_FULL, u & 1, pw[PW_D2_FULL]);
+                tc_fence_after();
+                tmem_ld32(trow + kColD2 + (u & 1) * kHid + (j - npos) * 32, v);
                 bias = s_b1 + (j - npos) * 32;
             }
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[i], 0.0f);
-            const int a2s = items & 1;
-            if (items >= 2) {
-                mbar_wait_p<kProf>(bars + 8 * (B_A2_EMPTY + a2s), ((items >> 1) - 1) & 1, pw[PW_A2_EMPTY]);
+            if (item >= 2) {
+                mbar_wait_p<kProf>(bars + 8 * (B_A2_EMPTY + eg), ((item >> 1) - 1) & 1, pw[PW_A2_EMPTY]);
                 tc_fence_after();
             }
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
-            tmem_st16(trow + kColA2 + a2s * kA2Cols, hi);
-            tmem_st16(trow + kColA2 + a2s * kA2Cols + 16, lo);
+            tmem_st16(trow + kColA2 + eg * kA2Cols, hi);
+            tmem_st16(trow + kColA2 + eg * kA2Cols + 16, lo);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(bars + 8 * (B_A2_FULL + a2s));
+            mbar_arrive(bars + 8 * (B_A2_FULL + eg));
         }
 
-        // ---- FC2 epilogue + head (fp32 on CUDA cores)
+        // ---- FC2 epilogue + head (fp32 on CUDA cores): group g covers hidden units 32 g .. 32 g + 31
         float head[6];
 #pragma unroll
-        for (int a = 0; a < 6; ++a) head[a] = s_bh[a];
+        for (int a = 0; a < 6; ++a) head[a] = eg == 0 ? s_bh[a] : 0.0f;
         mbar_wait_p<kProf>(bars + 8 * B_D3_FULL, u & 1, pw[PW_D3_FULL]);
         tc_fence_after();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        {
             float v[32];
-            tmem_ld32(trow + kColD2 + (u & 1) * kHid + half * 32, v);
+            tmem_ld32(trow + kColD2 + (u & 1) * kHid + eg * 32, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const float h = fmaxf(v[i] + s_b2[half * 32 + i], 0.0f);
+                const float h = fmaxf(v[i] + s_b2[eg * 32 + i], 0.0f);
 #pragma unroll
-                for (int a = 0; a < 6; ++a) head[a] = fmaf(h, s_wh[a * kHid + half * 32 + i], head[a]);
+                for (int a = 0; a < 6; ++a) head[a] = fmaf(h, s_wh[a * kHid + eg * 32 + i], head[a]);
             }
         }
         tc_fence_before();
         mbar_arrive(bars + 8 * (B_HEAD_EMPTY + (u & 1)));  // done with the head block of this unit
 
-        const long long row = (long long)t * kRows + tid;
+        // group 1 hands its partial sums to group 0 (same rows: warps w and w + 4), double-buffered by unit parity
+        float* xrow = s_xbuf + ((u & 1) * kRows + trow_id) * 8;
+        if (eg == 1) {
+            *reinterpret_cast<float4*>(xrow) = make_float4(head[0], head[1], head[2], head[3]);
+            *reinterpret_cast<float2*>(xrow + 4) = make_float2(head[4], head[5]);
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
+        if (eg == 1) continue;
+        {
+            const float4 x0 = *reinterpret_cast<const float4*>(xrow);
+            const float2 x1 = *reinterpret_cast<const float2*>(xrow + 4);
+            head[0] += x0.x, head[1] += x0.y, head[2] += x0.z, head[3] += x0.w, head[4] += x1.x, head[5] += x1.y;
+        }
+
+        const long long row = (long long)t * kRows + trow_id;
         if (row < prm.M) {
             if (ur.net == 1) {
                 if (prm.values) prm.values[row] = head[0];
@@ -639,6 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) policy_fwd_kernel(const PolicyPar
     uint32_t* s_stage = reinterpret_cast<uint32_t*>(smem + sl.stage);
     uint8_t* s_head = smem + sl.head;
     uint8_t* s_wring = smem + sl.wring;
+    float* s_xbuf = reinterpret_cast<float*>(smem + sl.xbuf);
     uint64_t* s_bars = reinterpret_cast<uint64_t*>(smem + sl.bars);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bars + 60);
     const uint32_t bars = smem_addr(s_bars);
@@ -653,7 +690,7 @@ __global__ void __launch_bounds__(kThreads, 1) policy_fwd_kernel(const PolicyPar
         for (int i = 0; i < B_COUNT; ++i) {
             uint32_t count = 1;
             if ((i >= B_COL_FULL && i < B_COL_FULL + 4) || (i >= B_A2_FULL && i < B_A2_FULL + 2)) count = 128;
-            if (i >= B_HEAD_EMPTY && i < B_HEAD_EMPTY + 2) count = 129;
+            if (i >= B_HEAD_EMPTY && i < B_HEAD_EMPTY + 2) count = 32 * kEpiWarps + 1;
             mbar_init(bars + 8 * i, count);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -666,18 +703,19 @@ __global__ void __launch_bounds__(kThreads, 1) policy_fwd_kernel(const PolicyPar
 
     long long pw[kProf ? PW_COUNT : 1] = {};
     const long long t_begin = kProf ? clock64() : 0;
-    if (warp < 4) {
-        epilogue_role<kProf>(pw, prm, ur, L, tmem, s_head, bars);
-    } else if (warp < 8) {
+    if (warp < kEpiWarps) {
+        epilogue_role<kProf>(pw, prm, ur, L, tmem, s_head, s_xbuf, bars);
+    } else if (warp < kWarpMma) {
         loader_role<kProf>(pw, prm, ur, tmem, s_stage, bars);
-    } else if (warp == 8) {  // whole warp runs the control flow, one elected lane issues
+    } else if (warp == kWarpMma) {  // whole warp runs the control flow, one elected lane issues
         mma_role<kProf>(pw, prm, ur, L, tmem, smem_addr(s_head), smem_addr(s_wring), bars);
     } else {
         producer_role<kProf>(pw, prm, ur, L, smem_addr(s_head), smem_addr(s_wring), bars);
     }
-    if (kProf && prm.prof != nullptr && (tid == 0 || tid == 128 || tid == 256 || tid == 288)) {
+    if (kProf && prm.prof != nullptr &&
+        (tid == 0 || tid == 32 * kEpiWarps || tid == 32 * kWarpMma || tid == 32 * kWarpProd)) {
         pw[PW_TOTAL] = clock64() - t_begin;
-        const int role = tid == 0 ? 0 : tid == 128 ? 1 : tid == 256 ? 2 : 3;  // epilogue, loader, MMA, producer
+        const int role = tid == 0 ? 0 : tid == 32 * kEpiWarps ? 1 : tid == 32 * kWarpMma ? 2 : 3;  // epilogue, loader, MMA, producer
         for (int i = 0; i < PW_COUNT; ++i) prm.prof[((size_t)blockIdx.x * 4 + role) * PW_COUNT + i] = pw[i];
     }
     __syncwarp();
@@ -793,7 +831,7 @@ extern "C" int ocb_policy_set_weights(ocb_policy* p, int policy, int net, const 
     const BlobLayout& L = p->L;
     std::vector<uint8_t> blob((size_t)L.total, 0);
     const int npos = p->npos, H = p->H, PH = H - 2;
-    static const int slot_channel[kSlots] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 18, 19, -1};
+    static const int slot_channel[kSlots] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 16, 17, 18, 19, 15, -1};  // == loader_role
     for (int co = 0; co < kCo; ++co)
         for (int j = 0; j < 9; ++j)
             for (int s = 0; s < kSlots; ++s) {
