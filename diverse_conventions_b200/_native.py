@@ -63,6 +63,8 @@ PROTOTYPES = {
     "ocb_policy_debug_profile": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i]),
     "ocb_step_counter_device": (_vp, [_vp]),
     "ocb_rollout_policy": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _u64, _vp]),
+    "ocb_compute_returns": (_i, [_i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ocb_normalize_advantages": (_i, [_i, _vp, _sz, _vp, _vp]),
     "bb_create": (_i, [_i, _u32, _u64, _pp]),
     "bb_destroy": (_i, [_vp]),
     "bb_num_worlds": (_i, [_vp]),

@@ -49,6 +49,18 @@ class RolloutBuffer:
                    (self.obs, self.actions, self.action_log_probs, self.value_preds, self.rewards, self.dones)
                    if t is not None)
 
+    def compute_returns(self, gamma: float = 0.99, gae_lambda: float = 0.95, use_gae: bool = True, value_normalizer=None,
+                        normalize: bool = True):
+        """returns [T+1,P,N] and (normalised) advantages [T,P,N] of this rollout, on the device
+        (SharedReplayBuffer.compute_returns + the advantage normalisation of R_MAPPO.train; see returns.py)"""
+        from .returns import compute_returns
+        if self.value_preds is None:
+            raise ValueError("this buffer was collected without the critic")
+        self.returns, self.advantages = compute_returns(
+            self.value_preds, self.rewards, self.dones, gamma, gae_lambda, use_gae, value_normalizer, normalize,
+            getattr(self, "returns", None), getattr(self, "advantages", None))
+        return self.returns, self.advantages
+
     def shared_buffer_views(self) -> Dict[str, torch.Tensor]:
         """Zero-copy views with the reference's SharedReplayBuffer names and axis order
         (shared_buffer.py:45-76).  ``share_obs`` is ``obs`` (state == obs for Overcooked,

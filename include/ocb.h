@@ -243,6 +243,32 @@ int ocb_rollout_policy(ocb_env* env, ocb_policy* pol, int T, const int32_t* tile
                        int32_t* actions, float* logp, float* values, int32_t* reward, int32_t* done,
                        int deterministic, uint64_t seed, void* stream);
 
+/* ------------------------------------------------------- returns / GAE over the rollout buffer */
+/* SharedReplayBuffer.compute_returns (train/MAPPO/utils/shared_buffer.py:248-304) with the
+ * ValueNorm de-normalisation (train/MAPPO/utils/valuenorm.py:76-87) and the advantage
+ * normalisation at the top of R_MAPPO.train (train/MAPPO/r_mappo.py:174-182), directly over the
+ * seat-major buffers ocb_rollout_policy fills.  bad_masks are all ones for these envs
+ * (main_player.py:274), so the use_proper_time_limits branches reduce to the ones below. */
+typedef struct ocb_returns_cfg {
+    uint32_t struct_size; /* sizeof(ocb_returns_cfg) */
+    int32_t use_gae;      /* 1: GAE (default), 0: discounted sum of rewards */
+    double gamma;         /* config.py:251, default 0.99; doubles because the reference forms gamma * gae_lambda in */
+    double gae_lambda;    /* config.py:253, default 0.95;   Python floats before the fp32 tensor arithmetic */
+    float vn_mean;        /* ValueNorm.running_mean_var(): debiased mean (0 without a value normaliser) */
+    float vn_std;         /* sqrt of the debiased, clamped variance (1 without a value normaliser) */
+} ocb_returns_cfg;
+/* value_preds [T+1,P,N] f32 (slot T = bootstrap value), rewards [T,P,N] int32, done [T,N] int32
+ * (masks[t+1] = 1 - done[t]) -> returns [T+1,P,N] f32 (slot T = value_preds[T] without GAE, shared_buffer.py:297; untouched with GAE),
+ * advantages [T,P,N] f32 = returns - denormalised value_preds (un-normalised; may be NULL),
+ * adv_stats double[3] = (sum, sum of squares, count) of the advantages (may be NULL).
+ * All DEVICE pointers; fp32 arithmetic in the reference's operation order (bit-identical to torch
+ * on the CPU), statistics in fp64. */
+int ocb_compute_returns(int device, const ocb_returns_cfg* cfg, int T, int P, int N, const float* value_preds,
+                        const int32_t* rewards, const int32_t* done, float* returns, float* advantages,
+                        double* adv_stats, void* stream);
+/* advantages <- (advantages - mean) / (std + 1e-5), unbiased std, from adv_stats (r_mappo.py:180-182) */
+int ocb_normalize_advantages(int device, float* advantages, size_t n, const double* adv_stats, void* stream);
+
 /* ------------------------------------------------------- Balance-Beam */
 /* replaces BalanceBeamSimulator (src/balance_beam_env/mgr.cpp:191-233) behind
  * MadronaEnv.n_step / n_reset (vectorenv.py:306-343).
