@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--tma", type=int, default=-1, help="1/0 force the TMA bulk-store path, -1 = library default")
     ap.add_argument("--e2e-passes", type=int, default=3, help="passes of the host-buffer e2e measurement (<= --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-policy-rollout", action="store_true", help="skip the '+policy fwd' leg (BASELINE config 4)")
+    ap.add_argument("--policy-worlds", type=int, default=8192)
+    ap.add_argument("--policy-T", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -198,6 +201,69 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+
+def ncu_traffic_bytes(kernel_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel_name` from the newest committed
+    `ncu --set full` summary under profiles/ (None if there is none for this kernel)"""
+    import glob
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_full_*summary.json"))):
+        try:
+            with open(path) as f:
+                rows = json.load(f)
+            vals = []
+            for r in rows:
+                if kernel_name.replace(" ", "") not in r.get("Kernel Name", "").replace(" ", ""):
+                    continue
+                tot = 0.0
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    num, u = r[key].split()
+                    tot += float(num) * unit[u]
+                vals.append(tot)
+            if vals:
+                best = statistics.mean(vals)
+        except Exception:
+            continue
+    return best
+
+
+def policy_rollout_leg(args, lp, local, rank, world, dev, barrier):
+    import torch
+    import torch.distributed as dist
+    from diverse_conventions_b200.overcooked_env import B200Overcooked
+    from diverse_conventions_b200.policy import FusedPolicy, PolicyNet
+    from diverse_conventions_b200.rollout import PolicyRollout
+    N, T = args.policy_worlds, args.policy_T
+    pol = FusedPolicy(lp, 64, 1, gpu_id=local)
+    pol.set_weights(0, PolicyNet("actor", lp.width, lp.height, lp.channels, 64).init_like_reference(1),
+                    PolicyNet("critic", lp.width, lp.height, lp.channels, 64).init_like_reference(2))
+    env = B200Overcooked(args.layout, N, local, horizon=HORIZON, seed=1, world_offset=rank * N)
+    ro = PolicyRollout(env, pol, T, seed=1, use_graph=True)
+    for _ in range(3):
+        ro.collect()
+    barrier()
+    iters = 8
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ro.collect()
+        ro.buf.compute_returns()  # GAE + advantage normalisation over the buffer just written
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_rollout = float(ms.item()) / iters
+    out = {"metric": "agent-steps/sec (env+obs+policy fwd+buffer write+GAE)", "value": lp.num_players * N * world * T / (ms_rollout * 1e-3),
+           "unit": UNIT, "worlds_per_gpu": N, "T": T, "hidden": 64, "ms_per_rollout": ms_rollout,
+           "us_per_env_step": 1e3 * ms_rollout / T, "launches_per_rollout": 2 * T + 1 + 2,
+           "what": "MAPPO self-play rollout: fused actor+critic tcgen05 forward of both seats, sampling, env step, "
+                   "seat-major PPO buffer write, then returns/GAE; CUDA-graph replay, device-timed"}
+    env.close()
+    pol.close()
+    return out
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -272,6 +338,16 @@ def run_ours(args):
     except Exception:
         pass
 
+    # DRAM traffic per launch of the same kernel at the same shape, from the committed `ncu --set full` capture
+    traffic = ncu_traffic_bytes("oc_rollout_kernel<%d, %d>" % (P, env.get_tuning()["lanes_per_world"])) \
+        if (N, spl, args.layout) == (WORLDS_PER_GPU, 100, LAYOUT) else None
+
+    # '+policy fwd' leg of the metric (BASELINE config 4 on this layout): MAPPO self-play rollout, random-init
+    # actor + critic (hidden 64), on-device sampling, env step, PPO buffer write; one CUDA-graph replay per rollout
+    policy_leg = None
+    if not args.no_policy_rollout:
+        policy_leg = policy_rollout_leg(args, lp, local, rank, world, dev, barrier)
+
     # end-to-end: the reference-facing single-step call with host buffers
     E = max(min(args.e2e_passes, K), 1) * spl  # single-step calls
     h_act = torch.randint(0, 6, (P, N), dtype=torch.int32).pin_memory()
@@ -303,13 +379,14 @@ def run_ours(args):
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "oc_rollout_kernel<%d,%d>" % (P, env.get_tuning()["lanes_per_world"]),
+                             "traffic": traffic, "kernel": "oc_rollout_kernel<%d,%d>" % (P, env.get_tuning()["lanes_per_world"]),
                              "tuning": env.get_tuning(),
                              "bytes_per_world_step": bytes_ws, "world_steps_per_launch": N * k_launch,
                              "launch_ms": launch_ms, "peak_source": peak_src},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "call": "ocb_step_host (1 launch / step, obs+reward+done to pinned host memory)",
                         "calls": E, "value_without_obs_d2h_rank0": e2e_noobs},
+                "policy_rollout": policy_leg,
                 "gpu_launches": launches, "clocks": clocks,
                 "env_steps": K * spl, "us_per_env_step": 1e3 * ms_total / (K * spl)}
         if world == 1 and not args.no_cpu_baseline:

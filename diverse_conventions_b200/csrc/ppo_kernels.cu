@@ -22,8 +22,8 @@ using namespace ocb;
 
 namespace {
 
-constexpr int kGaeThreads = 128;
-constexpr int kGaeUnroll = 8;
+constexpr int kGaeThreads = 64;   // small blocks: P*N columns are few (32,768 at config 4), spread them over all SMs
+constexpr int kGaeUnroll = 16;    // steps per batch; two batches of loads are in flight per thread (software pipeline)
 
 struct GaeParams {
     const float* value_preds;  // [T+1][R]
@@ -39,55 +39,67 @@ struct GaeParams {
 
 __device__ __forceinline__ float denorm(float v, float std, float mean) { return __fadd_rn(__fmul_rn(v, std), mean); }
 
+struct GaeBatch {
+    float v[kGaeUnroll];
+    int32_t r[kGaeUnroll], d[kGaeUnroll];
+};
+// loads of steps t1-1 .. t1-kGaeUnroll (clamped at 0; clamped entries are never consumed)
+__device__ __forceinline__ void gae_load(GaeBatch& b, const float* vp, const int32_t* rw, const int32_t* dn, int t1, size_t R, size_t N) {
+#pragma unroll
+    for (int k = 0; k < kGaeUnroll; ++k) {
+        const int t = t1 - 1 - k;
+        const size_t tt = t >= 0 ? (size_t)t : 0;
+        b.v[k] = __ldcs(vp + tt * R);
+        b.r[k] = __ldcs(rw + tt * R);
+        b.d[k] = __ldg(dn + tt * N);
+    }
+}
+
 __global__ void __launch_bounds__(kGaeThreads) gae_kernel(const GaeParams p) {
     const int col = blockIdx.x * kGaeThreads + threadIdx.x;
     double s1 = 0.0, s2 = 0.0;
     if (col < p.R) {
         const int n = col % p.N;
-        const size_t R = (size_t)p.R;
+        const size_t R = (size_t)p.R, N = (size_t)p.N;
         const float* vp = p.value_preds + col;
         const int32_t* rw = p.rewards + col;
         const int32_t* dn = p.done + n;
         float* ret = p.returns + col;
         float* adv = p.advantages ? p.advantages + col : nullptr;
-        float v_next = vp[(size_t)p.T * R];
+        GaeBatch cur, nxt;
+        gae_load(cur, vp, rw, dn, p.T, R, N);
+        const float v_next = vp[(size_t)p.T * R];
         float gae = 0.0f;
         float ret_next = v_next;  // discounted-sum branch: returns[T] = next_value (shared_buffer.py:297)
         if (!p.use_gae) ret[(size_t)p.T * R] = v_next;  // the GAE branch never writes returns[T] (shared_buffer.py:277-287)
         float dn_next = denorm(v_next, p.vn_std, p.vn_mean);
         for (int t1 = p.T; t1 > 0; t1 -= kGaeUnroll) {
-            float v[kGaeUnroll], r[kGaeUnroll], m[kGaeUnroll];
-#pragma unroll
-            for (int k = 0; k < kGaeUnroll; ++k) {
-                const int t = t1 - 1 - k;
-                const bool ok = t >= 0;
-                const size_t tt = ok ? (size_t)t : 0;
-                v[k] = vp[tt * R];
-                r[k] = (float)rw[tt * R];
-                m[k] = dn[tt * (size_t)p.N] ? 0.0f : 1.0f;  // masks[t+1] = 1 - done[t] (main_player.py:254-258)
-            }
+            if (t1 > kGaeUnroll) gae_load(nxt, vp, rw, dn, t1 - kGaeUnroll, R, N);
 #pragma unroll
             for (int k = 0; k < kGaeUnroll; ++k) {
                 const int t = t1 - 1 - k;
                 if (t < 0) break;
-                const float dn0 = denorm(v[k], p.vn_std, p.vn_mean);
+                const float r = (float)cur.r[k];
+                const float m = cur.d[k] ? 0.0f : 1.0f;  // masks[t+1] = 1 - done[t] (main_player.py:254-258)
+                const float dn0 = denorm(cur.v[k], p.vn_std, p.vn_mean);
                 float out;
                 if (p.use_gae) {
                     // delta = r + gamma * denorm(v[t+1]) * mask - denorm(v[t]);  gae = delta + gamma*lambda * mask * gae
-                    const float delta = __fadd_rn(__fadd_rn(r[k], __fmul_rn(__fmul_rn(p.gamma, dn_next), m[k])), -dn0);
-                    gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(p.gl, m[k]), gae));
+                    const float delta = __fadd_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(p.gamma, dn_next), m)), -dn0);
+                    gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(p.gl, m), gae));
                     out = __fadd_rn(gae, dn0);
                 } else {
                     // returns[t] = returns[t+1] * gamma * mask + r
-                    out = __fadd_rn(__fmul_rn(__fmul_rn(ret_next, p.gamma), m[k]), r[k]);
+                    out = __fadd_rn(__fmul_rn(__fmul_rn(ret_next, p.gamma), m), r);
                     ret_next = out;
                 }
-                ret[(size_t)t * R] = out;
+                __stcs(ret + (size_t)t * R, out);
                 const float a = __fadd_rn(out, -dn0);
-                if (adv) adv[(size_t)t * R] = a;
+                if (adv) __stcs(adv + (size_t)t * R, a);
                 s1 += (double)a, s2 += (double)a * (double)a;
                 dn_next = dn0;
             }
+            cur = nxt;
         }
     }
     if (p.stats != nullptr) {
