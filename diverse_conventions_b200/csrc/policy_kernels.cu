@@ -35,6 +35,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -116,6 +117,7 @@ struct PolicyParams {
     const unsigned long long* d_offset;  // optional device-resident addend of `offset`
     int net_mask;             // 1 actor, 2 critic, 3 both (even CTAs actor, odd critic)
     int ring;                 // weight-ring slots in shared memory
+    int pair_ring;            // same for policy_pair_kernel (chunks of both networks)
     int stage_stride;         // words per row of the loader staging buffer (odd)
     long long* prof;          // diagnostic build: [ctas][4 roles][PW_COUNT] stall cycles
 };
@@ -527,6 +529,47 @@ __device__ __forceinline__ void mma_role(long long* pw, const PolicyParams& prm,
     }
 }
 
+// actor outputs of one row: raw logits, sampled (or arg-max) action and its log-prob
+// FixedCategorical(logits): sample / mode and log-prob (train/MAPPO/utils/distributions.py:14-28)
+__device__ __forceinline__ void emit_actor_row(const PolicyParams& prm, long long row, const float (&head)[6], unsigned long long offset) {
+    if (prm.logits) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) prm.logits[row * 6 + a] = head[a];
+    }
+    if (prm.actions || prm.logp) {
+        float mx = head[0];
+#pragma unroll
+        for (int a = 1; a < 6; ++a) mx = fmaxf(mx, head[a]);
+        float e[6], sum = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) e[a] = expf(head[a] - mx), sum += e[a];
+        int act = 0;
+        if (prm.deterministic) {
+#pragma unroll
+            for (int a = 1; a < 6; ++a) act = (head[a] > head[act]) ? a : act;
+        } else {
+            uint32_t r[4] = {(uint32_t)row, (uint32_t)offset, (uint32_t)(offset >> 32), 0x5A17u};
+            philox4x32_10(r, (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
+            const float uu = (float)(r[0] >> 8) * (1.0f / 16777216.0f) * sum;
+            float cum = 0.0f;
+            act = 5;  // inverse CDF; falls through to the last action on round-off
+            bool found = false;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                cum += e[a];
+                if (!found && uu < cum) act = a, found = true;
+            }
+        }
+        if (prm.actions) prm.actions[row] = act;
+        if (prm.logp) {
+            float la = head[0];
+#pragma unroll
+            for (int a = 1; a < 6; ++a) la = (act == a) ? head[a] : la;
+            prm.logp[row] = la - mx - logf(sum);
+        }
+    }
+}
+
 // epilogue: TMEM -> bias/ReLU -> bf16 hi/lo A operand; head, sampling and outputs.  Two groups of four
 // warps: group g owns stage g of the A-operand ring, i.e. every other item of the CTA's item stream
 // (items of a unit: npos conv positions, then the two K halves of FC2's input).
@@ -622,43 +665,7 @@ __device__ __forceinline__ void epilogue_role(long long* pw, const PolicyParams&
             if (ur.net == 1) {
                 if (prm.values) prm.values[row] = head[0];
             } else {
-                if (prm.logits) {
-#pragma unroll
-                    for (int a = 0; a < 6; ++a) prm.logits[row * 6 + a] = head[a];
-                }
-                if (prm.actions || prm.logp) {
-                    // FixedCategorical(logits): sample / mode and log-prob (train/MAPPO/utils/distributions.py:14-28)
-                    float mx = head[0];
-#pragma unroll
-                    for (int a = 1; a < 6; ++a) mx = fmaxf(mx, head[a]);
-                    float e[6], sum = 0.0f;
-#pragma unroll
-                    for (int a = 0; a < 6; ++a) e[a] = expf(head[a] - mx), sum += e[a];
-                    int act = 0;
-                    if (prm.deterministic) {
-#pragma unroll
-                        for (int a = 1; a < 6; ++a) act = (head[a] > head[act]) ? a : act;
-                    } else {
-                        uint32_t r[4] = {(uint32_t)row, (uint32_t)offset, (uint32_t)(offset >> 32), 0x5A17u};
-                        philox4x32_10(r, (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
-                        const float uu = (float)(r[0] >> 8) * (1.0f / 16777216.0f) * sum;
-                        float cum = 0.0f;
-                        act = 5;  // inverse CDF; falls through to the last action on round-off
-                        bool found = false;
-#pragma unroll
-                        for (int a = 0; a < 6; ++a) {
-                            cum += e[a];
-                            if (!found && uu < cum) act = a, found = true;
-                        }
-                    }
-                    if (prm.actions) prm.actions[row] = act;
-                    if (prm.logp) {
-                        float la = head[0];
-#pragma unroll
-                        for (int a = 1; a < 6; ++a) la = (act == a) ? head[a] : la;
-                        prm.logp[row] = la - mx - logf(sum);
-                    }
-                }
+                emit_actor_row(prm, row, head, offset);
             }
         }
     }
@@ -725,6 +732,370 @@ __global__ void __launch_bounds__(kThreads, 1) policy_fwd_kernel(const PolicyPar
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
 }
 
+// ================================================================ pair kernel: both networks of a tile in ONE CTA
+// The fused actor+critic forward (ocb_policy_forward / ocb_rollout_policy) runs this variant.  A work
+// unit is a tile of 128 rows; the CTA computes the actor AND the critic for it:
+//   * the observation columns are loaded and converted once for both networks (loader_role above);
+//   * the conv is ONE accumulate of N = 64 (actor channels 0-31 | critic channels 32-63): the two
+//     networks' conv weights sit back to back in shared memory and form one canonical K-major operand;
+//   * epilogue group g (warps 4g .. 4g+3) owns network g end to end: conv position -> bias/ReLU/split ->
+//     A operand stage g -> FC1 partial sums into D2[g]; FC2's two K halves go through the same stage and
+//     accumulate into the (by then drained) conv accumulator stage g; the whole head of network g is
+//     evaluated by group g (no cross-group reduction);
+//   * TMEM: cells 0-191 | conv accumulators 2 x 64 (later D3 of net 0 / net 1) | A stage 2 x 32 | D2 2 x 64.
+// Compared with the (tile, network) units of policy_fwd_kernel this doubles the work in flight per SM
+// (the pipeline is latency-bound: every hand-off is an mbarrier round trip), halves the loader work
+// and the number of conv MMA instructions, and lets 128 tiles (config 4: 8,192 worlds) run as ONE wave.
+constexpr int kPColD1 = 192;   // conv accumulators: stage s at + 64 s (actor 32 | critic 32); D3 of net g = stage g
+constexpr int kPColA2 = 320;   // A operand of net g at + 32 g (hi 16 | lo 16)
+constexpr int kPColD2 = 384;   // FC1 accumulator of net g at + 64 g
+constexpr int kPMaxRing = 24;  // weight-ring slots (chunks of both networks)
+constexpr int kPConvBytes = 9216;  // one network's conv weights, hi or lo
+constexpr int kPRestOff = 4 * kPConvBytes;  // per-network remainder of the head (bias1 .. bh) starts here
+enum : int {
+    PB_COL_FULL = B_COL_FULL,   // [4] shared with loader_role
+    PB_COL_EMPTY = B_COL_EMPTY, // [4]
+    PB_D1_FULL = 8,             // [2] MMA commit -> both epilogue groups
+    PB_A2_FULL = 10,            // [2] epilogue group g -> MMA (128 arrivals)
+    PB_A2_EMPTY = 12,           // [2] MMA commit -> epilogue group g
+    PB_D2_FULL = 14,            // [2] MMA commit -> epilogue group g
+    PB_D3_FULL = 16,            // [2] MMA commit -> epilogue group g
+    PB_D3_EMPTY = 18,           // [2] epilogue group g (128 arrivals) -> MMA: conv stage g may be overwritten
+    PB_HEAD_FULL = 20,          //     bulk copies -> MMA, epilogue
+    PB_HEAD_EMPTY = 21,         // [2] by tile parity: MMA commit + 256 epilogue arrivals -> producer
+    PB_W_FULL = 24,             // [24] bulk copy complete_tx -> MMA
+    PB_W_EMPTY = 48,            // [24] MMA commit -> producer
+    PB_COUNT = 72,
+    PB_TMEM_SLOT = 120          // 8-byte slot index that holds the TMEM base address
+};
+
+struct PairSmemLayout {
+    int stage, head, wring, bars, total;
+};
+__host__ __device__ inline PairSmemLayout pair_smem_layout(int npos, int ring, int stage_stride) {
+    PairSmemLayout s;
+    const BlobLayout L = blob_layout(npos);
+    int o = 0;
+    s.stage = o, o += al128(kLoadWarps * 32 * stage_stride * 4);
+    s.head = o, o += kPRestOff + 2 * (L.head_bytes - L.bias1);
+    s.wring = o, o += ring * kChunk;
+    s.bars = o, o += 1024;
+    s.total = o + 128;
+    return s;
+}
+
+template <bool kProf>
+__device__ __forceinline__ void pair_producer_role(long long* pw, const PolicyParams& prm, int t0, int t1, const BlobLayout L,
+                                                   uint32_t s_head, uint32_t s_wring, uint32_t bars) {
+    const int R = prm.pair_ring, nch = 2 * L.chunks;
+    const bool resident = R >= nch;
+    const int Reff = resident ? nch : R;
+    const uint32_t rest = (uint32_t)(L.head_bytes - L.bias1);
+    uint32_t u = 0, round = 0;
+    int slot = 0;
+    for (int t = t0; t < t1; ++t, ++u) {
+        const bool chg = blob_changed(prm, t, t0);
+        const uint8_t* blob_a = prm.blobs + (size_t)tile_pol(prm, t) * 2 * prm.blob_stride;
+        const uint8_t* blob_c = blob_a + prm.blob_stride;
+        if (chg) {
+            if (u > 0) mbar_wait_p<kProf>(bars + 8 * (PB_HEAD_EMPTY + ((u - 1) & 1)), ((u - 1) >> 1) & 1, pw[PW_HEAD_EMPTY]);
+            if (elect_one()) {
+                const uint32_t hb = bars + 8 * PB_HEAD_FULL;
+                mbar_arrive_expect_tx(hb, 4u * kPConvBytes + 2u * rest);
+                bulk_g2s(s_head, blob_a + L.wc_hi, kPConvBytes, hb);
+                bulk_g2s(s_head + kPConvBytes, blob_c + L.wc_hi, kPConvBytes, hb);
+                bulk_g2s(s_head + 2 * kPConvBytes, blob_a + L.wc_lo, kPConvBytes, hb);
+                bulk_g2s(s_head + 3 * kPConvBytes, blob_c + L.wc_lo, kPConvBytes, hb);
+                bulk_g2s(s_head + kPRestOff, blob_a + L.bias1, rest, hb);
+                bulk_g2s(s_head + kPRestOff + rest, blob_c + L.bias1, rest, hb);
+            }
+            __syncwarp();
+        }
+        const bool load = !resident || chg;
+        for (int j = 0; j < L.chunks; ++j) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {  // consumption order of pair_mma_role: (actor, j), (critic, j)
+                if (round > 0) mbar_wait_p<kProf>(bars + 8 * (PB_W_EMPTY + slot), (round - 1) & 1, pw[PW_W_EMPTY]);
+                if (load) {
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(bars + 8 * (PB_W_FULL + slot), kChunk);
+                        bulk_g2s(s_wring + slot * kChunk, (g ? blob_c : blob_a) + L.head_bytes + (size_t)j * kChunk, kChunk,
+                                 bars + 8 * (PB_W_FULL + slot));
+                    }
+                    __syncwarp();
+                }
+                if (++slot == Reff) slot = 0, ++round;
+            }
+        }
+    }
+}
+
+template <bool kProf>
+__device__ __forceinline__ void pair_mma_role(long long* pw, const PolicyParams& prm, int t0, int t1, const BlobLayout L, uint32_t tmem,
+                                              uint32_t a_head, uint32_t a_wring, uint32_t bars) {
+    const int W = prm.W, H = prm.H, PH = H - 2, npos = prm.npos;
+    const int R = prm.pair_ring, nch = 2 * L.chunks;
+    const bool resident = R >= nch;
+    const int Reff = resident ? nch : R;
+    const uint32_t idesc = make_idesc(kRows, kHid);  // N = 64 for the pair conv and for the FC layers
+    const uint32_t a_wchi = a_head, a_wclo = a_head + 2 * kPConvBytes;
+    uint32_t gcb = 0;            // running column index of grid column 0 of the tile
+    uint32_t item_par = 0;       // phase parity bit of the A stage per network (items issued so far, mod 2)
+    int slot = 0;
+    uint32_t wround = 0, head_gen = 0, w_gen = 0, u = 0;
+
+    for (int t = t0; t < t1; ++t, ++u, gcb += W) {
+        const bool chg = blob_changed(prm, t, t0);
+        if (chg) {
+            mbar_wait_p<kProf>(bars + 8 * PB_HEAD_FULL, head_gen & 1, pw[PW_HEAD_FULL]);
+            ++head_gen;
+        }
+        const bool w_loaded = !resident || chg;
+        if (resident && w_loaded) ++w_gen;
+        int cp = 0, ox = 0, oy = 0;  // next conv position of this tile
+
+        auto conv = [&]() {
+            if (oy == 0) {  // new window column(s)
+                for (int d = (ox == 0 ? 0 : 2); d < 3; ++d) {
+                    const uint32_t g = gcb + ox + d;
+                    mbar_wait_p<kProf>(bars + 8 * (PB_COL_FULL + g % kColRing), (g / kColRing) & 1, pw[PW_COL_FULL]);
+                }
+            }
+            // stage cp (< 2) still holds D3 of network cp of the previous tile until its head epilogue has read it
+            if (u > 0 && cp < 2) mbar_wait_p<kProf>(bars + 8 * (PB_D3_EMPTY + cp), (u - 1) & 1, pw[PW_D3_FULL]);
+            tc_fence_after();
+            const uint32_t d1 = tmem + kPColD1 + (cp & 1) * kHid;
+            const long long ti0 = kProf ? clock64() : 0;
+            if (elect_one()) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) {
+                    const int dx = j / 3, dy = j - dx * 3;
+                    const uint32_t ta = tmem + kColCells + (((gcb + ox + dx) % kColRing) * H + oy + dy) * kCellCols;
+                    umma_bf16_ts(d1, ta, make_desc(a_wchi + j * 256, 128, 2304), idesc, j > 0);
+                    umma_bf16_ts(d1, ta, make_desc(a_wclo + j * 256, 128, 2304), idesc, 1);
+                }
+                umma_commit(bars + 8 * (PB_D1_FULL + (cp & 1)));
+                if (oy == PH - 1) {  // the window leaves column ox (and the last two columns with the last window)
+                    umma_commit(bars + 8 * (PB_COL_EMPTY + (gcb + ox) % kColRing));
+                    if (ox == W - 3) {
+                        umma_commit(bars + 8 * (PB_COL_EMPTY + (gcb + ox + 1) % kColRing));
+                        umma_commit(bars + 8 * (PB_COL_EMPTY + (gcb + ox + 2) % kColRing));
+                    }
+                }
+                // last conv of the tile: the conv weights of the head are free once these MMAs complete
+                if (cp + 1 == npos) umma_commit(bars + 8 * (PB_HEAD_EMPTY + (u & 1)));
+            }
+            __syncwarp();
+            if (kProf) pw[PW_ISSUE_CONV] += clock64() - ti0;
+            ++cp;
+            if (++oy == PH) oy = 0, ++ox;
+        };
+        // one FC item of network g: D2[g] (+)= A[g] x W1_j (j < npos)   or   D3[g] (+)= A[g] x W2_half (j >= npos)
+        auto fc = [&](int g, int j) {
+            mbar_wait_p<kProf>(bars + 8 * (PB_A2_FULL + g), (item_par >> g) & 1, pw[PW_A2_FULL]);
+            if (w_loaded) mbar_wait_p<kProf>(bars + 8 * (PB_W_FULL + slot), resident ? ((w_gen - 1) & 1) : (wround & 1), pw[PW_W_FULL]);
+            tc_fence_after();
+            const uint32_t dst = tmem + (j < npos ? kPColD2 : kPColD1) + g * kHid;
+            const bool first = (j == 0 || j == npos);
+            const uint32_t a_hi = tmem + kPColA2 + g * kA2Cols, a_lo = a_hi + 16;
+            const uint32_t b_hi = a_wring + slot * kChunk, b_lo = b_hi + 4096;
+            const long long tf0 = kProf ? clock64() : 0;
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const uint64_t bhi = make_desc(b_hi + ks * 256, 128, 512), blo = make_desc(b_lo + ks * 256, 128, 512);
+                    umma_bf16_ts(dst, a_hi + ks * 8, bhi, idesc, (!first || ks != 0) ? 1u : 0u);
+                    umma_bf16_ts(dst, a_hi + ks * 8, blo, idesc, 1);
+                    umma_bf16_ts(dst, a_lo + ks * 8, bhi, idesc, 1);
+                }
+                umma_commit(bars + 8 * (PB_A2_EMPTY + g));
+                umma_commit(bars + 8 * (PB_W_EMPTY + slot));
+                if (j == npos - 1) umma_commit(bars + 8 * (PB_D2_FULL + g));
+                if (j == npos + 1) umma_commit(bars + 8 * (PB_D3_FULL + g));
+            }
+            __syncwarp();
+            if (kProf) pw[PW_ISSUE_FC] += clock64() - tf0;
+            item_par ^= 1u << g;
+            if (++slot == Reff) slot = 0, ++wround;
+        };
+
+        // static issue order: the conv runs two positions ahead of the FC1 partial sums (two accumulator stages);
+        // conv(p + 2) reuses the stage of position p, which both groups have drained once both FC1 items of
+        // position p could be issued
+        conv();
+        conv();
+        for (int p = 0; p < npos; ++p) {
+            fc(0, p);
+            fc(1, p);
+            if (p + 2 < npos) conv();
+        }
+        fc(0, npos), fc(1, npos);
+        fc(0, npos + 1), fc(1, npos + 1);
+    }
+}
+
+template <bool kProf>
+__device__ __forceinline__ void pair_epilogue_role(long long* pw, const PolicyParams& prm, int t0, int t1, const BlobLayout L, uint32_t tmem,
+                                                   const uint8_t* s_head, uint32_t bars) {
+    const int warp = threadIdx.x >> 5, g = warp >> 2, trow_id = (warp & 3) * 32 + (threadIdx.x & 31);
+    const int npos = prm.npos;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 TMEM lanes
+    const uint8_t* rest = s_head + kPRestOff + g * (L.head_bytes - L.bias1) - L.bias1;  // network g's bias1 .. bh, blob offsets
+    const float* s_bias1 = reinterpret_cast<const float*>(rest + L.bias1);
+    const float* s_b1 = reinterpret_cast<const float*>(rest + L.b1);
+    const float* s_b2 = reinterpret_cast<const float*>(rest + L.b2);
+    const float* s_wh = reinterpret_cast<const float*>(rest + L.wh);
+    const float* s_bh = reinterpret_cast<const float*>(rest + L.bh);
+    unsigned long long offset = prm.offset;
+    if (prm.d_offset != nullptr) offset += *prm.d_offset;
+    const uint32_t a2 = trow + kPColA2 + g * kA2Cols;
+
+    uint32_t u = 0, head_gen = 0, item = 0, d1_par = 0;  // d1_par: phase parity bit per conv accumulator stage
+    // bias + ReLU + hi/lo split of 32 activations -> A operand stage of this network
+    auto publish = [&](float (&v)[32], const float* bias) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[i], 0.0f);
+        if (item >= 1) {
+            mbar_wait_p<kProf>(bars + 8 * (PB_A2_EMPTY + g), (item - 1) & 1, pw[PW_A2_EMPTY]);
+            tc_fence_after();
+        }
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+        tmem_st16(a2, hi);
+        tmem_st16(a2 + 16, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bars + 8 * (PB_A2_FULL + g));
+        ++item;
+    };
+
+    for (int t = t0; t < t1; ++t, ++u) {
+        if (blob_changed(prm, t, t0)) {
+            mbar_wait_p<kProf>(bars + 8 * PB_HEAD_FULL, head_gen & 1, pw[PW_HEAD_FULL]);
+            ++head_gen;
+        }
+        for (int j = 0; j < npos; ++j) {
+            const int st = j & 1;
+            mbar_wait_p<kProf>(bars + 8 * (PB_D1_FULL + st), (d1_par >> st) & 1, pw[PW_D1_FULL]);
+            d1_par ^= 1u << st;
+            tc_fence_after();
+            float v[32];
+            tmem_ld32(trow + kPColD1 + st * kHid + g * kCo, v);
+            publish(v, s_bias1 + j * kCo);
+        }
+        mbar_wait_p<kProf>(bars + 8 * (PB_D2_FULL + g), u & 1, pw[PW_D2_FULL]);
+        tc_fence_after();
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tmem_ld32(trow + kPColD2 + g * kHid + half * 32, v);
+            publish(v, s_b1 + half * 32);
+        }
+
+        // ---- FC2 epilogue + head (fp32 on CUDA cores), all 64 hidden units of this network
+        mbar_wait_p<kProf>(bars + 8 * (PB_D3_FULL + g), u & 1, pw[PW_D3_FULL]);
+        tc_fence_after();
+        float head[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) head[a] = s_bh[a];
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tmem_ld32(trow + kPColD1 + g * kHid + half * 32, v);
+            if (half == 1) {  // both halves are in registers: the accumulator stage may be overwritten by the next tile
+                tc_fence_before();
+                mbar_arrive(bars + 8 * (PB_D3_EMPTY + g));
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float h = fmaxf(v[i] + s_b2[half * 32 + i], 0.0f);
+                if (g == 0) {
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) head[a] = fmaf(h, s_wh[a * kHid + half * 32 + i], head[a]);
+                } else {
+                    head[0] = fmaf(h, s_wh[half * 32 + i], head[0]);
+                }
+            }
+        }
+        mbar_arrive(bars + 8 * (PB_HEAD_EMPTY + (u & 1)));  // done with the head block of this tile
+
+        const long long row = (long long)t * kRows + trow_id;
+        if (row < prm.M) {
+            if (g == 1) {
+                if (prm.values) prm.values[row] = head[0];
+            } else {
+                emit_actor_row(prm, row, head, offset);
+            }
+        }
+    }
+}
+
+template <bool kProf>
+__global__ void __launch_bounds__(kThreads, 1) policy_pair_kernel(const PolicyParams prm) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const BlobLayout L = blob_layout(prm.npos);
+    const PairSmemLayout sl = pair_smem_layout(prm.npos, prm.pair_ring, prm.stage_stride);
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(smem + sl.stage);
+    uint8_t* s_head = smem + sl.head;
+    uint8_t* s_wring = smem + sl.wring;
+    uint64_t* s_bars = reinterpret_cast<uint64_t*>(smem + sl.bars);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bars + PB_TMEM_SLOT);
+    const uint32_t bars = smem_addr(s_bars);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)),
+                     "r"((uint32_t)kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < PB_COUNT; ++i) {
+            uint32_t count = 1;
+            if ((i >= PB_COL_FULL && i < PB_COL_FULL + 4) || (i >= PB_A2_FULL && i < PB_A2_FULL + 2) ||
+                (i >= PB_D3_EMPTY && i < PB_D3_EMPTY + 2))
+                count = 128;
+            if (i >= PB_HEAD_EMPTY && i < PB_HEAD_EMPTY + 2) count = 32 * kEpiWarps + 1;
+            mbar_init(bars + 8 * i, count);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    // tiles of this CTA
+    UnitRange ur;
+    ur.net = 0;
+    ur.t0 = (int)(((long long)blockIdx.x * prm.tiles) / gridDim.x);
+    ur.t1 = (int)(((long long)(blockIdx.x + 1) * prm.tiles) / gridDim.x);
+
+    long long pw[kProf ? PW_COUNT : 1] = {};
+    const long long t_begin = kProf ? clock64() : 0;
+    if (warp < kEpiWarps) {
+        pair_epilogue_role<kProf>(pw, prm, ur.t0, ur.t1, L, tmem, s_head, bars);
+    } else if (warp < kWarpMma) {
+        loader_role<kProf>(pw, prm, ur, tmem, s_stage, bars);
+    } else if (warp == kWarpMma) {
+        pair_mma_role<kProf>(pw, prm, ur.t0, ur.t1, L, tmem, smem_addr(s_head), smem_addr(s_wring), bars);
+    } else {
+        pair_producer_role<kProf>(pw, prm, ur.t0, ur.t1, L, smem_addr(s_head), smem_addr(s_wring), bars);
+    }
+    if (kProf && prm.prof != nullptr &&
+        (tid == 0 || tid == 32 * kEpiWarps || tid == 32 * kWarpMma || tid == 32 * kWarpProd)) {
+        pw[PW_TOTAL] = clock64() - t_begin;
+        const int role = tid == 0 ? 0 : tid == 32 * kEpiWarps ? 1 : tid == 32 * kWarpMma ? 2 : 3;
+        for (int i = 0; i < PW_COUNT; ++i) prm.prof[((size_t)blockIdx.x * 4 + role) * PW_COUNT + i] = pw[i];
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+}
+
 // ---------------------------------------------------------------- host-side packing
 uint16_t bf16_bits(float x) {
     uint32_t u;
@@ -754,6 +1125,9 @@ struct ocb_policy {
     int W, H, S, SC, C, npos, n_policies;
     int sm_count, ring, stage_stride;
     size_t smem_bytes;
+    int pair_ring;            // 0: the pair kernel is not usable for this layout
+    size_t pair_smem_bytes;
+    int use_pair;             // run ocb_policy_forward through policy_pair_kernel (env OCB_POLICY_PAIR=0 disables)
     std::vector<uint8_t> terrain;
     BlobLayout L;
     uint8_t* d_blobs;
@@ -801,15 +1175,28 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
     }
     p->ring = ring;
     p->smem_bytes = (size_t)smem_layout(p->H, p->npos, ring, p->stage_stride).total;
+    // pair kernel (both networks per CTA): ring over the chunks of both networks
+    {
+        const int pfixed = pair_smem_layout(p->npos, 0, p->stage_stride).total;
+        int pring = (kSmemBudget - pfixed) / kChunk;
+        if (pring > kPMaxRing) pring = kPMaxRing;
+        if (pring > 2 * p->L.chunks) pring = 2 * p->L.chunks;
+        p->pair_ring = pring >= 4 ? pring : 0;
+        p->pair_smem_bytes = p->pair_ring ? (size_t)pair_smem_layout(p->npos, p->pair_ring, p->stage_stride).total : 0;
+        const char* e = getenv("OCB_POLICY_PAIR");
+        p->use_pair = p->pair_ring != 0 && !(e != nullptr && e[0] == '0');
+    }
     DeviceGuard guard(device);
     const size_t bytes = (size_t)n_policies * 2 * p->L.total;
     cudaError_t err = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (err == cudaSuccess) err = cudaMalloc(&p->d_blobs, bytes);
     if (err == cudaSuccess) err = cudaMemset(p->d_blobs, 0, bytes);
-    if (err == cudaSuccess)
-        err = cudaFuncSetAttribute(policy_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
-    if (err == cudaSuccess)
-        err = cudaFuncSetAttribute(policy_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes);
+    // the opt-in limit is per function, not per handle: always raise it to the full budget
+    const int smem_max = kSmemBudget + 128;
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err != cudaSuccess) {
         cudaGetLastError();
         ocb_policy_destroy(p);
@@ -898,20 +1285,30 @@ static int policy_launch(ocb_policy* p, int net_mask, const int8_t* obs, int M, 
     prm.deterministic = deterministic, prm.seed = seed, prm.offset = offset;
     prm.d_offset = reinterpret_cast<const unsigned long long*>(d_offset);
     prm.net_mask = net_mask, prm.ring = p->ring, prm.stage_stride = p->stage_stride;
-    // persistent grid: one CTA per SM; with both networks even CTAs run the actor, odd ones the critic
-    int ctas;
-    if (net_mask == 3) {
-        const int per_net = prm.tiles < p->sm_count / 2 ? prm.tiles : p->sm_count / 2;
-        ctas = 2 * per_net;
-    } else {
-        ctas = prm.tiles < p->sm_count ? prm.tiles : p->sm_count;
-    }
+    prm.pair_ring = p->pair_ring;
     prm.prof = prof;
-    if (ctas_out) *ctas_out = ctas;
-    if (prof != nullptr)
-        policy_fwd_kernel<true><<<ctas, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(prm);
-    else
-        policy_fwd_kernel<false><<<ctas, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(prm);
+    // persistent grid: one CTA per SM
+    int ctas;
+    if (net_mask == 3 && p->use_pair) {  // both networks of a tile in one CTA
+        ctas = prm.tiles < p->sm_count ? prm.tiles : p->sm_count;
+        if (ctas_out) *ctas_out = ctas;
+        if (prof != nullptr)
+            policy_pair_kernel<true><<<ctas, kThreads, p->pair_smem_bytes, (cudaStream_t)stream>>>(prm);
+        else
+            policy_pair_kernel<false><<<ctas, kThreads, p->pair_smem_bytes, (cudaStream_t)stream>>>(prm);
+    } else {
+        if (net_mask == 3) {  // (tile, network) units: even CTAs run the actor, odd ones the critic
+            const int per_net = prm.tiles < p->sm_count / 2 ? prm.tiles : p->sm_count / 2;
+            ctas = 2 * per_net;
+        } else {
+            ctas = prm.tiles < p->sm_count ? prm.tiles : p->sm_count;
+        }
+        if (ctas_out) *ctas_out = ctas;
+        if (prof != nullptr)
+            policy_fwd_kernel<true><<<ctas, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(prm);
+        else
+            policy_fwd_kernel<false><<<ctas, kThreads, p->smem_bytes, (cudaStream_t)stream>>>(prm);
+    }
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "policy kernel launch failed: %s", cudaGetErrorString(err));
     p->calls += 1;

@@ -43,8 +43,9 @@ def main():
                                                            prof.ctypes.data_as(ctypes.c_void_p), 256))
     p = prof[:ctas]
     print(json.dumps({"layout": args.layout, "ctas": ctas, "info": pol.info()}))
-    for net, nm in ((0, "actor CTAs"), (1, "critic CTAs")):
-        sel = p[net::2]
+    pair = os.environ.get("OCB_POLICY_PAIR", "1") != "0"  # pair kernel: every CTA runs both networks
+    for net, nm in (((0, "all CTAs (pair kernel; epilogue = actor group)"),) if pair else ((0, "actor CTAs"), (1, "critic CTAs"))):
+        sel = p if pair else p[net::2]
         print(nm, "mean cycles over", len(sel), "CTAs")
         for r, rn in enumerate(ROLES):
             m = sel[:, r, :].mean(axis=0)
