@@ -39,7 +39,7 @@ def main():
     total = sum(x[0] for x in lines)
     print("total samples", total)
     sel = [x for x in lines if args.file is None or (x[1] or "").endswith(args.file)]
-    for s, f, ln, src, st, ie in sorted(sel, reverse=True)[:args.top]:
+    for s, f, ln, src, st, ie in sorted(sel, key=lambda x: -x[0])[:args.top]:
         top = ", ".join("%s %d" % kv for kv in sorted(st.items(), key=lambda kv: -kv[1])[:3])
         print("%6d %5.1f%%  %s:%d  [%s] inst=%s\n         %s" % (s, 100.0 * s / max(total, 1), (f or "?").split("/")[-1], ln, top, ie, src[:120]))
 
