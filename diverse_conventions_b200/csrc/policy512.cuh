@@ -1,0 +1,446 @@
+// policy512.cuh — MAPPO actor / critic forward for hidden_size 512 (the argparse default,
+// train/config.py:199; every train/*.sh uses 64, which policy_kernels.cu fuses into one kernel).
+// Textually included inside the anonymous namespace of policy_kernels.cu, after the shared helpers.
+//
+//   obs int8 [M, W, H, 20] -> Conv3x3(20->256) -> ReLU -> FC(256 npos -> 512) -> ReLU -> FC(512 -> 512) -> ReLU -> head
+//
+// At this width the layers are GEMM-sized (2.66 MFLOP per row and network), the activations of a
+// 128-row tile no longer fit on one SM (conv output 128 x 1536 for cramped_room), so the forward is
+// three persistent tcgen05 kernels per launch that hand the activations over in HBM / L2:
+//   conv512_kernel : loader_role (shared with the h=64 kernels) -> per-cell bf16 blocks in TMEM -> per
+//                    position two N=128 accumulates (A from TMEM, B = resident conv weights, 147 KB of shared
+//                    memory) -> bias/ReLU -> hi/lo split -> stores in the packed operand layout of FC1;
+//   gemm512_kernel : C[128 x 512] = A[128 x K] W^T; A and W arrive as pre-packed [rows x 32] canonical
+//                    K-major blocks (hi | lo), one 16 KB + one 64 KB cp.async.bulk per K step into a 2-stage
+//                    ring, 12 tcgen05.mma (SS mode, M128 N256 K16; 3 products hi.hi + hi.lo + lo.hi) per step,
+//                    the whole 512-column accumulator in TMEM; epilogue = bias/ReLU/split -> packed stores
+//                    (FC1) or the head, sampling and outputs (FC2).
+// Every operand block is stored in HBM exactly as the MMA reads it from shared memory (8-row x 16-byte
+// core matrices, no swizzle), so all copies are 1-D bulk copies and the epilogue stores are full 128-byte
+// segments.  Precision scheme as for h=64: bf16 hi + lo operands, fp32 accumulate (~1e-5 relative).
+
+constexpr int kH5 = 512;                       // hidden size
+constexpr int kCo5 = 256;                      // conv output channels
+constexpr int kCw5 = kCo5 * kK1 * 2;           // 73,728 B: conv weights [256 x 144] bf16 canonical, hi (or lo)
+constexpr int kKc = 32;                        // K extent of one packed block
+constexpr int kABlk = 2 * kRows * kKc * 2;     // 16 KB: activations [128 x 32] bf16 canonical, hi | lo
+constexpr int kWBlk = 2 * kH5 * kKc * 2;       // 64 KB: weights [512 x 32] bf16 canonical, hi | lo
+constexpr int kKc2 = kH5 / kKc;                // 16 K blocks of FC2
+constexpr int kGStages = 2;                    // operand ring of gemm512_kernel
+constexpr int kGWarpMma = kEpiWarps, kGWarpProd = kEpiWarps + 1;
+constexpr int kGThreads = 32 * (kEpiWarps + 2);  // 320
+constexpr int kC5ColD1 = 192;                  // conv accumulators: half h at + 128 h
+
+// packed weight blob of one network (device): all offsets are multiples of 128
+struct Blob5 {
+    size_t wc_hi, wc_lo, bias1, w1, b1, w2, b2, wh, bh, total;
+    int kc1;  // K blocks of FC1 = 256 npos / 32
+};
+__host__ __device__ inline Blob5 blob5_layout(int npos) {
+    Blob5 L;
+    size_t o = 0;
+    L.kc1 = kCo5 * npos / kKc;
+    L.wc_hi = o, o += kCw5;
+    L.wc_lo = o, o += kCw5;
+    L.bias1 = o, o += (size_t)npos * kCo5 * 4;
+    L.w1 = o, o += (size_t)L.kc1 * kWBlk;
+    L.b1 = o, o += kH5 * 4;
+    L.w2 = o, o += (size_t)kKc2 * kWBlk;
+    L.b2 = o, o += kH5 * 4;
+    L.wh = o, o += 8 * kH5 * 4;
+    L.bh = o, o += 128;
+    L.total = o;
+    return L;
+}
+
+struct P5Params {
+    PolicyParams base;  // geometry, observations, outputs, unit mapping (blobs / blob_stride address Blob5 blobs)
+    uint8_t* a1;        // conv output = FC1 operand: [2 nets][tiles][kc1][kABlk]
+    uint8_t* a2;        // FC1 output = FC2 operand:  [2 nets][tiles][kKc2][kABlk]
+    int kc1;
+};
+
+// A and B from shared memory (SS mode)
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+
+// thread `r` (tile row) stores 32 consecutive K values (hi/lo packed pairs) into block `blk` of the packed
+// operand layout: [r/8][k8][r%8][8 x bf16]; a warp writes full 128-byte segments
+__device__ __forceinline__ void store_packed32(uint8_t* blk, int r, const uint32_t (&hi)[16], const uint32_t (&lo)[16]) {
+    uint8_t* p = blk + (r >> 3) * (kKc / 8 * 128) + (r & 7) * 16;
+#pragma unroll
+    for (int k8 = 0; k8 < 4; ++k8) {
+        *reinterpret_cast<uint4*>(p + k8 * 128) = make_uint4(hi[4 * k8], hi[4 * k8 + 1], hi[4 * k8 + 2], hi[4 * k8 + 3]);
+        *reinterpret_cast<uint4*>(p + k8 * 128 + kABlk / 2) = make_uint4(lo[4 * k8], lo[4 * k8 + 1], lo[4 * k8 + 2], lo[4 * k8 + 3]);
+    }
+}
+
+// ---------------------------------------------------------------- conv512_kernel
+enum : int {
+    C5_COL_FULL = B_COL_FULL,    // [4] shared with loader_role
+    C5_COL_EMPTY = B_COL_EMPTY,  // [4]
+    C5_D1_FULL = 8,              // [2] MMA commit -> epilogue group h
+    C5_D1_EMPTY = 10,            // [2] epilogue group h (128 arrivals) -> MMA
+    C5_W_FULL = 12,              //     bulk copies -> MMA, epilogue
+    C5_W_EMPTY = 13,             // [2] by unit parity: MMA commit + 256 epilogue arrivals -> producer
+    C5_COUNT = 15,
+    C5_TMEM_SLOT = 24
+};
+struct C5Smem {
+    int stage, wc, bias1, bars, total;
+};
+__host__ __device__ inline C5Smem c5_smem_layout(int npos, int stage_stride) {
+    C5Smem s;
+    int o = 0;
+    s.stage = o, o += al128(kLoadWarps * 32 * stage_stride * 4);
+    s.wc = o, o += 2 * kCw5;
+    s.bias1 = o, o += npos * kCo5 * 4;
+    s.bars = o, o += 256;
+    s.total = o + 128;
+    return s;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv512_kernel(const P5Params q) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
+    const PolicyParams& prm = q.base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int npos = prm.npos;
+    const Blob5 L = blob5_layout(npos);
+    const C5Smem sl = c5_smem_layout(npos, prm.stage_stride);
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(smem + sl.stage);
+    uint8_t* s_wc = smem + sl.wc;
+    const float* s_bias1 = reinterpret_cast<const float*>(smem + sl.bias1);
+    uint64_t* s_bars = reinterpret_cast<uint64_t*>(smem + sl.bars);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bars + C5_TMEM_SLOT);
+    const uint32_t bars = smem_addr(s_bars);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)),
+                     "r"((uint32_t)kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < C5_COUNT; ++i) {
+            uint32_t count = 1;
+            if ((i >= C5_COL_FULL && i < C5_COL_FULL + 4) || (i >= C5_D1_EMPTY && i < C5_D1_EMPTY + 2)) count = 128;
+            if (i >= C5_W_EMPTY && i < C5_W_EMPTY + 2) count = 32 * kEpiWarps + 1;
+            mbar_init(bars + 8 * i, count);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const UnitRange ur = my_units(prm);
+    long long pw[1] = {};
+
+    if (warp < kEpiWarps) {
+        // ---- epilogue: group g drains accumulator half g (conv channels 128 g .. 128 g + 127)
+        const int g = warp >> 2, r = (warp & 3) * 32 + (tid & 31);
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t u = 0, gen = 0, cnt = 0;
+        for (int t = ur.t0; t < ur.t1; ++t, ++u) {
+            if (blob_changed(prm, t, ur.t0)) {
+                mbar_wait(bars + 8 * C5_W_FULL, gen & 1);
+                ++gen;
+            }
+            uint8_t* blk0 = q.a1 + ((size_t)ur.net * prm.tiles + t) * q.kc1 * kABlk;
+            for (int p = 0; p < npos; ++p, ++cnt) {
+                mbar_wait(bars + 8 * (C5_D1_FULL + g), cnt & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int b = 0; b < 4; ++b) {
+                    float v[32];
+                    tmem_ld32(trow + kC5ColD1 + g * 128 + b * 32, v);
+                    if (b == 3) {  // the half is in registers: the MMA may overwrite it with the next position
+                        tc_fence_before();
+                        mbar_arrive(bars + 8 * (C5_D1_EMPTY + g));
+                    }
+                    const float* bias = s_bias1 + p * kCo5 + g * 128 + b * 32;
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        split2(fmaxf(v[2 * i] + bias[2 * i], 0.0f), fmaxf(v[2 * i + 1] + bias[2 * i + 1], 0.0f), hi[i], lo[i]);
+                    store_packed32(blk0 + (size_t)(p * 8 + g * 4 + b) * kABlk, r, hi, lo);
+                }
+            }
+            mbar_arrive(bars + 8 * (C5_W_EMPTY + (u & 1)));  // done with bias1 of this unit
+        }
+    } else if (warp < kWarpMma) {
+        loader_role<false>(pw, prm, ur, tmem, s_stage, bars);
+    } else if (warp == kWarpMma) {
+        // ---- MMA issuer
+        const int W = prm.W, H = prm.H, PH = H - 2;
+        const uint32_t idesc = make_idesc(kRows, 128);
+        const uint32_t a_wchi = smem_addr(s_wc), a_wclo = a_wchi + kCw5;
+        uint32_t gcb = 0, u = 0, gen = 0, cnt = 0;
+        for (int t = ur.t0; t < ur.t1; ++t, ++u, gcb += W) {
+            if (blob_changed(prm, t, ur.t0)) {
+                mbar_wait(bars + 8 * C5_W_FULL, gen & 1);
+                ++gen;
+            }
+            int ox = 0, oy = 0;
+            for (int p = 0; p < npos; ++p, ++cnt) {
+                if (oy == 0) {  // new window column(s)
+                    for (int d = (ox == 0 ? 0 : 2); d < 3; ++d) {
+                        const uint32_t gcol = gcb + ox + d;
+                        mbar_wait(bars + 8 * (C5_COL_FULL + gcol % kColRing), (gcol / kColRing) & 1);
+                    }
+                }
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    if (cnt > 0) mbar_wait(bars + 8 * (C5_D1_EMPTY + h), (cnt - 1) & 1);
+                    tc_fence_after();
+                    const uint32_t d1 = tmem + kC5ColD1 + h * 128;
+                    const uint32_t boff = (uint32_t)h * (128 / 8) * 2304;  // 16 row groups of the canonical [256 x 144] operand
+                    if (elect_one()) {
+#pragma unroll
+                        for (int j = 0; j < 9; ++j) {
+                            const int dx = j / 3, dy = j - dx * 3;
+                            const uint32_t ta = tmem + kColCells + (((gcb + ox + dx) % kColRing) * H + oy + dy) * kCellCols;
+                            umma_bf16_ts(d1, ta, make_desc(a_wchi + boff + j * 256, 128, 2304), idesc, j > 0);
+                            umma_bf16_ts(d1, ta, make_desc(a_wclo + boff + j * 256, 128, 2304), idesc, 1);
+                        }
+                        umma_commit(bars + 8 * (C5_D1_FULL + h));
+                        if (h == 1) {
+                            if (oy == PH - 1) {  // the window leaves column ox (and the last two columns with the last window)
+                                umma_commit(bars + 8 * (C5_COL_EMPTY + (gcb + ox) % kColRing));
+                                if (ox == W - 3) {
+                                    umma_commit(bars + 8 * (C5_COL_EMPTY + (gcb + ox + 1) % kColRing));
+                                    umma_commit(bars + 8 * (C5_COL_EMPTY + (gcb + ox + 2) % kColRing));
+                                }
+                            }
+                            if (p + 1 == npos) umma_commit(bars + 8 * (C5_W_EMPTY + (u & 1)));
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (++oy == PH) oy = 0, ++ox;
+            }
+        }
+    } else {
+        // ---- producer: conv weights + per-position bias, resident until a tile selects another policy
+        uint32_t u = 0;
+        const uint32_t s_dst = smem_addr(s_wc);
+        for (int t = ur.t0; t < ur.t1; ++t, ++u) {
+            if (!blob_changed(prm, t, ur.t0)) continue;
+            if (u > 0) mbar_wait(bars + 8 * (C5_W_EMPTY + ((u - 1) & 1)), ((u - 1) >> 1) & 1);
+            if (elect_one()) {
+                const uint8_t* blob = prm.blobs + ((size_t)tile_pol(prm, t) * 2 + ur.net) * prm.blob_stride;
+                const uint32_t bias_bytes = (uint32_t)npos * kCo5 * 4;
+                const uint32_t wb = bars + 8 * C5_W_FULL;
+                mbar_arrive_expect_tx(wb, 2u * kCw5 + bias_bytes);
+                constexpr int kPiece = kCw5 / 4;  // 18,432 B
+#pragma unroll 1
+                for (int i = 0; i < 8; ++i) bulk_g2s(s_dst + i * kPiece, blob + L.wc_hi + (size_t)i * kPiece, kPiece, wb);
+                bulk_g2s(s_dst + 2 * kCw5, blob + L.bias1, bias_bytes, wb);
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+}
+
+// ---------------------------------------------------------------- gemm512_kernel
+enum : int { G5_FULL = 0, G5_EMPTY = 2, G5_D_FULL = 4, G5_D_EMPTY = 5, G5_COUNT = 6, G5_TMEM_SLOT = 8 };
+struct G5Smem {
+    int stages, xbuf, bias, wh, bars, total;
+};
+__host__ __device__ inline G5Smem g5_smem_layout() {
+    G5Smem s;
+    int o = 0;
+    s.stages = o, o += kGStages * (kABlk + kWBlk);
+    s.xbuf = o, o += kRows * 8 * 4;
+    s.bias = o, o += kH5 * 4;
+    s.wh = o, o += 8 * kH5 * 4 + 128;  // head weights [8][512] + head bias
+    s.bars = o, o += 128;
+    s.total = o + 128;
+    return s;
+}
+
+// kHead = false: FC1 (A = q.a1, K blocks = kc1, W = w1, bias b1) -> q.a2 in the packed layout
+// kHead = true : FC2 (A = q.a2, 16 K blocks, W = w2, bias b2) -> head, sampling, outputs
+template <bool kHead>
+__global__ void __launch_bounds__(kGThreads, 1) gemm512_kernel(const P5Params q) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
+    const PolicyParams& prm = q.base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const Blob5 L = blob5_layout(prm.npos);
+    const G5Smem sl = g5_smem_layout();
+    float* s_xbuf = reinterpret_cast<float*>(smem + sl.xbuf);
+    float* s_bias = reinterpret_cast<float*>(smem + sl.bias);
+    float* s_wh = reinterpret_cast<float*>(smem + sl.wh);
+    uint64_t* s_bars = reinterpret_cast<uint64_t*>(smem + sl.bars);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bars + G5_TMEM_SLOT);
+    const uint32_t bars = smem_addr(s_bars);
+    const uint32_t s_stage0 = smem_addr(smem + sl.stages);
+    const int KC = kHead ? kKc2 : q.kc1;
+    const size_t w_off = kHead ? L.w2 : L.w1;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)),
+                     "r"((uint32_t)kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < G5_COUNT; ++i) mbar_init(bars + 8 * i, i == G5_D_EMPTY ? 32 * kEpiWarps : 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const UnitRange ur = my_units(prm);
+
+    if (warp < kEpiWarps) {
+        // ---- epilogue: group g drains accumulator columns 256 g .. 256 g + 255
+        const int g = warp >> 2, r = (warp & 3) * 32 + (tid & 31), et = tid;  // et: 0..255
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        unsigned long long offset = prm.offset;
+        if (kHead && prm.d_offset != nullptr) offset += *prm.d_offset;
+        uint32_t u = 0;
+        for (int t = ur.t0; t < ur.t1; ++t, ++u) {
+            if (blob_changed(prm, t, ur.t0)) {  // stage this network's bias (and head) while the K loop runs
+                const uint8_t* blob = prm.blobs + ((size_t)tile_pol(prm, t) * 2 + ur.net) * prm.blob_stride;
+                asm volatile("bar.sync 2, 256;" ::: "memory");  // everybody is done with the previous set
+                const float* gb = reinterpret_cast<const float*>(blob + (kHead ? L.b2 : L.b1));
+                for (int i = et; i < kH5; i += 256) s_bias[i] = gb[i];
+                if (kHead) {
+                    const float* gw = reinterpret_cast<const float*>(blob + L.wh);
+                    for (int i = et; i < 8 * kH5 + 8; i += 256) s_wh[i] = gw[i];  // wh [8][512] then bh (contiguous in the blob)
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+            }
+            mbar_wait(bars + 8 * G5_D_FULL, u & 1);
+            tc_fence_after();
+            float head[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            uint8_t* blk0 = q.a2 + ((size_t)ur.net * prm.tiles + t) * kKc2 * kABlk;
+#pragma unroll 1
+            for (int b = 0; b < 8; ++b) {
+                float v[32];
+                tmem_ld32(trow + g * 256 + b * 32, v);
+                if (b == 7) {  // the accumulator is in registers: the MMA may start the next unit
+                    tc_fence_before();
+                    mbar_arrive(bars + 8 * G5_D_EMPTY);
+                }
+                const int n0 = g * 256 + b * 32;
+                if (!kHead) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        split2(fmaxf(v[2 * i] + s_bias[n0 + 2 * i], 0.0f), fmaxf(v[2 * i + 1] + s_bias[n0 + 2 * i + 1], 0.0f), hi[i], lo[i]);
+                    store_packed32(blk0 + (size_t)(n0 / kKc) * kABlk, r, hi, lo);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float h = fmaxf(v[i] + s_bias[n0 + i], 0.0f);
+                        if (ur.net == 0) {
+#pragma unroll
+                            for (int a = 0; a < 6; ++a) head[a] = fmaf(h, s_wh[a * kH5 + n0 + i], head[a]);
+                        } else {
+                            head[0] = fmaf(h, s_wh[n0 + i], head[0]);
+                        }
+                    }
+                }
+            }
+            if (kHead) {
+                // group 1 hands its partial sums to group 0 (same rows: warps w and w + 4), double-buffered by unit parity
+                float* xrow = s_xbuf + (size_t)r * 8;
+                if (g == 1) {
+                    *reinterpret_cast<float4*>(xrow) = make_float4(head[0], head[1], head[2], head[3]);
+                    *reinterpret_cast<float2*>(xrow + 4) = make_float2(head[4], head[5]);
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(3 + (warp & 3)) : "memory");
+                if (g == 0) {
+                    const float4 x0 = *reinterpret_cast<const float4*>(xrow);
+                    const float2 x1 = *reinterpret_cast<const float2*>(xrow + 4);
+                    const float* bh = s_wh + 8 * kH5;
+                    head[0] += x0.x + bh[0], head[1] += x0.y + bh[1], head[2] += x0.z + bh[2], head[3] += x0.w + bh[3];
+                    head[4] += x1.x + bh[4], head[5] += x1.y + bh[5];
+                    const long long row = (long long)t * kRows + r;
+                    if (row < prm.M) {
+                        if (ur.net == 1) {
+                            if (prm.values) prm.values[row] = head[0];
+                        } else {
+                            emit_actor_row(prm, row, head, offset);
+                        }
+                    }
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(3 + (warp & 3)) : "memory");  // xbuf is rewritten by the next unit
+            }
+        }
+    } else if (warp == kGWarpMma) {
+        // ---- MMA issuer
+        const uint32_t idesc = make_idesc(kRows, 256);
+        uint32_t it = 0, u = 0;
+        for (int t = ur.t0; t < ur.t1; ++t, ++u) {
+            if (u > 0) mbar_wait(bars + 8 * G5_D_EMPTY, (u - 1) & 1);
+            for (int kc = 0; kc < KC; ++kc, ++it) {
+                const uint32_t s = it % kGStages;
+                mbar_wait(bars + 8 * (G5_FULL + s), (it / kGStages) & 1);
+                tc_fence_after();
+                const uint32_t a_hi = s_stage0 + s * (kABlk + kWBlk), a_lo = a_hi + kABlk / 2;
+                const uint32_t b_hi = a_hi + kABlk, b_lo = b_hi + kWBlk / 2;
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint64_t dahi = make_desc(a_hi + ks * 256, 128, 512), dalo = make_desc(a_lo + ks * 256, 128, 512);
+#pragma unroll
+                        for (int nh = 0; nh < 2; ++nh) {
+                            const uint32_t dst = tmem + nh * 256;
+                            const uint32_t boff = (uint32_t)nh * (256 / 8) * 512 + ks * 256;  // 32 row groups per N half
+                            const uint64_t dbhi = make_desc(b_hi + boff, 128, 512), dblo = make_desc(b_lo + boff, 128, 512);
+                            umma_bf16_ss(dst, dahi, dbhi, idesc, (kc | ks) != 0 ? 1u : 0u);
+                            umma_bf16_ss(dst, dahi, dblo, idesc, 1);
+                            umma_bf16_ss(dst, dalo, dbhi, idesc, 1);
+                        }
+                    }
+                    umma_commit(bars + 8 * (G5_EMPTY + s));
+                    if (kc + 1 == KC) umma_commit(bars + 8 * G5_D_FULL);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---- producer: one activation block and one weight block per K step
+        const uint8_t* A = kHead ? q.a2 : q.a1;
+        uint32_t it = 0;
+        for (int t = ur.t0; t < ur.t1; ++t) {
+            const uint8_t* blob = prm.blobs + ((size_t)tile_pol(prm, t) * 2 + ur.net) * prm.blob_stride;
+            const uint8_t* a_src = A + ((size_t)ur.net * prm.tiles + t) * KC * kABlk;
+            for (int kc = 0; kc < KC; ++kc, ++it) {
+                const uint32_t s = it % kGStages;
+                if (it >= kGStages) mbar_wait(bars + 8 * (G5_EMPTY + s), ((it / kGStages) - 1) & 1);
+                if (elect_one()) {
+                    const uint32_t fb = bars + 8 * (G5_FULL + s);
+                    const uint32_t dst = s_stage0 + s * (kABlk + kWBlk);
+                    mbar_arrive_expect_tx(fb, kABlk + kWBlk);
+                    bulk_g2s(dst, a_src + (size_t)kc * kABlk, kABlk, fb);
+                    const uint8_t* w_src = blob + w_off + (size_t)kc * kWBlk;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) bulk_g2s(dst + kABlk + i * (kWBlk / 4), w_src + (size_t)i * (kWBlk / 4), kWBlk / 4, fb);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+}

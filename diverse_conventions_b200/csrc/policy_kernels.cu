@@ -1096,6 +1096,8 @@ __global__ void __launch_bounds__(kThreads, 1) policy_pair_kernel(const PolicyPa
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
 }
 
+#include "policy512.cuh"
+
 // ---------------------------------------------------------------- host-side packing
 uint16_t bf16_bits(float x) {
     uint32_t u;
@@ -1132,11 +1134,17 @@ struct ocb_policy {
     BlobLayout L;
     uint8_t* d_blobs;
     uint64_t calls;
+    // hidden_size 512 (policy512.cuh): packed blobs in d_blobs, activation scratch sized for the largest M seen
+    int hidden;
+    Blob5 L5;
+    uint8_t* d_scratch;
+    size_t scratch_tiles;
 };
 
 extern "C" int ocb_policy_destroy(ocb_policy* p) {
     if (p == nullptr) return OCB_OK;
     DeviceGuard guard(p->device);
+    cudaFree(p->d_scratch);
     cudaFree(p->d_blobs);
     delete p;
     return OCB_OK;
@@ -1146,7 +1154,8 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
     if (out == nullptr || cfg == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL argument");
     *out = nullptr;
     if (cfg->struct_size != sizeof(ocb_config)) return fail(OCB_ERR_INVALID_ARG, "ocb_config ABI mismatch");
-    if (hidden != kHid) return fail(OCB_ERR_UNSUPPORTED, "the fused policy kernel supports hidden_size 64 only (got %d)", hidden);
+    if (hidden != kHid && hidden != kH5)
+        return fail(OCB_ERR_UNSUPPORTED, "the policy kernels support hidden_size 64 and 512 (got %d)", hidden);
     if (cfg->num_players != 2) return fail(OCB_ERR_UNSUPPORTED, "the fused policy kernel supports 2 players only");
     if (cfg->width < 3 || cfg->height < 3) return fail(OCB_ERR_BAD_LAYOUT, "grid smaller than the 3x3 convolution");
     if ((cfg->width - 2) * (cfg->height - 2) < 2) return fail(OCB_ERR_UNSUPPORTED, "the fused policy kernel needs at least two conv positions");
@@ -1161,9 +1170,12 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
     if (p == nullptr) return fail(OCB_ERR_INVALID_ARG, "out of host memory");
     p->device = device, p->W = cfg->width, p->H = cfg->height, p->S = p->W * p->H, p->C = 20, p->SC = p->S * 20;
     p->npos = (p->W - 2) * (p->H - 2), p->n_policies = n_policies, p->calls = 0, p->d_blobs = nullptr;
+    p->hidden = hidden, p->d_scratch = nullptr, p->scratch_tiles = 0, p->L5 = blob5_layout(p->npos);
+    p->ring = 0, p->smem_bytes = 0, p->pair_ring = 0, p->pair_smem_bytes = 0, p->use_pair = 0;
     p->terrain.assign(cfg->terrain, cfg->terrain + p->S);
     p->L = blob_layout(p->npos);
     p->stage_stride = (5 * p->H) | 1;
+    if (hidden == kHid) {
     // weight ring: as many 8 KB chunks as fit; all of them (resident weights) when possible
     const int fixed = smem_layout(p->H, p->npos, 0, p->stage_stride).total;
     int ring = (kSmemBudget - fixed) / kChunk;
@@ -1186,8 +1198,12 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
         const char* e = getenv("OCB_POLICY_PAIR");
         p->use_pair = p->pair_ring != 0 && !(e != nullptr && e[0] == '0');
     }
+    } else if (c5_smem_layout(p->npos, p->stage_stride).total > kSmemBudget + 128) {
+        delete p;
+        return fail(OCB_ERR_UNSUPPORTED, "layout too large for the hidden-512 conv kernel (%d x %d)", cfg->width, cfg->height);
+    }
     DeviceGuard guard(device);
-    const size_t bytes = (size_t)n_policies * 2 * p->L.total;
+    const size_t bytes = (size_t)n_policies * 2 * (hidden == kHid ? (size_t)p->L.total : p->L5.total);
     cudaError_t err = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (err == cudaSuccess) err = cudaMalloc(&p->d_blobs, bytes);
     if (err == cudaSuccess) err = cudaMemset(p->d_blobs, 0, bytes);
@@ -1197,12 +1213,111 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
     if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(conv512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(gemm512_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(gemm512_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err != cudaSuccess) {
         cudaGetLastError();
         ocb_policy_destroy(p);
         return fail(OCB_ERR_CUDA, "ocb_policy_create: %s", cudaGetErrorString(err));
     }
     *out = p;
+    return OCB_OK;
+}
+
+// hidden 512: weights in the reference's layouts (conv_w [256,20,3,3], fc1_w [512, 256*npos] with column
+// co*npos + pos, fc2_w [512,512], head_w [head_out,512]) -> Blob5 (policy512.cuh)
+static int set_weights512(ocb_policy* p, int policy, int net, const float* conv_w, const float* conv_b, const float* fc1_w,
+                          const float* fc1_b, const float* fc2_w, const float* fc2_b, const float* head_w, const float* head_b) {
+    const Blob5& L = p->L5;
+    std::vector<uint8_t> blob(L.total, 0);
+    const int npos = p->npos, PH = p->H - 2;
+    static const int slot_channel[kSlots] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 16, 17, 18, 19, 15, -1};  // == loader_role
+    for (int co = 0; co < kCo5; ++co)
+        for (int j = 0; j < 9; ++j)
+            for (int s = 0; s < kSlots; ++s) {
+                const int ch = slot_channel[s];
+                const float w = ch < 0 ? 0.0f : conv_w[((co * 20 + ch) * 3 + j / 3) * 3 + j % 3];
+                put_split(blob.data() + L.wc_hi, blob.data() + L.wc_lo, canon_off(co, j * kSlots + s, kK1), w);
+            }
+    float* bias1 = reinterpret_cast<float*>(blob.data() + L.bias1);
+    for (int pos = 0; pos < npos; ++pos) {
+        const int ox = pos / PH, oy = pos % PH;
+        for (int co = 0; co < kCo5; ++co) {
+            double acc = conv_b[co];
+            for (int dx = 0; dx < 3; ++dx)
+                for (int dy = 0; dy < 3; ++dy) {
+                    const int t = p->terrain[(oy + dy) * p->W + ox + dx];
+                    if (t >= 1 && t <= 5) acc += conv_w[((co * 20 + 10 + (t - 1)) * 3 + dx) * 3 + dy];
+                }
+            bias1[pos * kCo5 + co] = (float)acc;
+        }
+    }
+    // FC1: packed K index k = pos * 256 + co; block kc holds k in [32 kc, 32 kc + 32)
+    const int K1 = kCo5 * npos;
+    for (int n = 0; n < kH5; ++n) {
+        for (int k = 0; k < K1; ++k) {
+            const int pos = k / kCo5, co = k % kCo5;
+            uint8_t* blk = blob.data() + L.w1 + (size_t)(k / kKc) * kWBlk;
+            put_split(blk, blk + kWBlk / 2, canon_off(n, k % kKc, kKc), fc1_w[(size_t)n * K1 + (size_t)co * npos + pos]);
+        }
+        for (int k = 0; k < kH5; ++k) {
+            uint8_t* blk = blob.data() + L.w2 + (size_t)(k / kKc) * kWBlk;
+            put_split(blk, blk + kWBlk / 2, canon_off(n, k % kKc, kKc), fc2_w[(size_t)n * kH5 + k]);
+        }
+    }
+    memcpy(blob.data() + L.b1, fc1_b, kH5 * 4);
+    memcpy(blob.data() + L.b2, fc2_b, kH5 * 4);
+    const int head_out = net == 0 ? 6 : 1;
+    memcpy(blob.data() + L.wh, head_w, (size_t)head_out * kH5 * 4);
+    memcpy(blob.data() + L.wh + 8 * kH5 * 4, head_b, (size_t)head_out * 4);  // bh follows wh
+    DeviceGuard guard(p->device);
+    cudaError_t err = cudaMemcpy(p->d_blobs + ((size_t)policy * 2 + net) * L.total, blob.data(), L.total, cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OCB_ERR_CUDA, "ocb_policy_set_weights: %s", cudaGetErrorString(err));
+    }
+    return OCB_OK;
+}
+
+// the three launches of the hidden-512 forward
+static int policy_launch512(ocb_policy* p, PolicyParams& prm, cudaStream_t stream) {
+    const size_t tiles = (size_t)prm.tiles;
+    if (tiles > p->scratch_tiles) {  // grow the activation scratch (not possible while the stream is being captured)
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream, &cs);
+        if (cs != cudaStreamCaptureStatusNone)
+            return fail(OCB_ERR_INVALID_ARG, "hidden-512 scratch must grow: run one forward of this size before capturing a graph");
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaFree(p->d_scratch);
+        p->d_scratch = nullptr, p->scratch_tiles = 0;
+        const size_t bytes = 2 * tiles * ((size_t)p->L5.kc1 + kKc2) * kABlk;
+        if (e == cudaSuccess) e = cudaMalloc(&p->d_scratch, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(OCB_ERR_CUDA, "hidden-512 scratch (%zu bytes): %s", bytes, cudaGetErrorString(e));
+        }
+        p->scratch_tiles = tiles;
+    }
+    P5Params q;
+    prm.blobs = p->d_blobs, prm.blob_stride = p->L5.total;
+    q.base = prm;
+    q.kc1 = p->L5.kc1;
+    q.a1 = p->d_scratch;
+    q.a2 = p->d_scratch + 2 * tiles * (size_t)p->L5.kc1 * kABlk;
+    int ctas;
+    if (prm.net_mask == 3) {
+        const int per_net = prm.tiles < p->sm_count / 2 ? prm.tiles : p->sm_count / 2;
+        ctas = 2 * per_net;
+    } else {
+        ctas = prm.tiles < p->sm_count ? prm.tiles : p->sm_count;
+    }
+    conv512_kernel<<<ctas, kThreads, c5_smem_layout(p->npos, p->stage_stride).total, stream>>>(q);
+    gemm512_kernel<false><<<ctas, kGThreads, g5_smem_layout().total, stream>>>(q);
+    gemm512_kernel<true><<<ctas, kGThreads, g5_smem_layout().total, stream>>>(q);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "hidden-512 policy launch failed: %s", cudaGetErrorString(err));
+    p->calls += 1;
     return OCB_OK;
 }
 
@@ -1215,6 +1330,7 @@ extern "C" int ocb_policy_set_weights(ocb_policy* p, int policy, int net, const 
     if (p == nullptr || !conv_w || !conv_b || !fc1_w || !fc1_b || !fc2_w || !fc2_b || !head_w || !head_b)
         return fail(OCB_ERR_INVALID_ARG, "NULL argument");
     if (policy < 0 || policy >= p->n_policies || net < 0 || net > 1) return fail(OCB_ERR_INVALID_ARG, "bad policy / net index");
+    if (p->hidden == kH5) return set_weights512(p, policy, net, conv_w, conv_b, fc1_w, fc1_b, fc2_w, fc2_b, head_w, head_b);
     const BlobLayout& L = p->L;
     std::vector<uint8_t> blob((size_t)L.total, 0);
     const int npos = p->npos, H = p->H, PH = H - 2;
@@ -1287,6 +1403,11 @@ static int policy_launch(ocb_policy* p, int net_mask, const int8_t* obs, int M, 
     prm.net_mask = net_mask, prm.ring = p->ring, prm.stage_stride = p->stage_stride;
     prm.pair_ring = p->pair_ring;
     prm.prof = prof;
+    if (p->hidden == kH5) {
+        if (prof != nullptr) return fail(OCB_ERR_UNSUPPORTED, "the role profile exists for hidden 64 only");
+        if (ctas_out) *ctas_out = 0;
+        return policy_launch512(p, prm, (cudaStream_t)stream);
+    }
     // persistent grid: one CTA per SM
     int ctas;
     if (net_mask == 3 && p->use_pair) {  // both networks of a tile in one CTA

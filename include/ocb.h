@@ -179,7 +179,10 @@ int ocb_set_world_offset(ocb_env* env, uint32_t world0);
 /* ------------------------------------------------------- policy forward (MAPPO actor / critic) */
 /* Fused tensor-core forward of the reference's CNN actor / critic (R_Actor / R_Critic,
  * train/MAPPO/r_actor_critic.py:12-71,142-197; CNNLayer train/MAPPO/utils/cnn.py:22-42;
- * Categorical head train/MAPPO/utils/distributions.py:55-68) for hidden_size 64, 2 players.
+ * Categorical head train/MAPPO/utils/distributions.py:55-68), 2 players, hidden_size 64 (every
+ * train/*.sh; one fused kernel) or 512 (argparse default train/config.py:199; three GEMM-sized
+ * launches).  Shapes below are for hidden h: conv_w [h/2,20,3,3], fc1_w [h, (h/2)(W-2)(H-2)],
+ * fc2_w [h,h], head_w [6|1, h].
  * A handle holds n_policies (actor, critic) weight sets for one layout. */
 typedef struct ocb_policy ocb_policy;
 int ocb_policy_create(const ocb_config* cfg, int device, int hidden, int n_policies, ocb_policy** out);

@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--policies", type=int, default=16)
     ap.add_argument("--worlds-per-pair", type=int, default=1024)
+    ap.add_argument("--hidden", type=int, default=64, choices=[64, 512])
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -65,9 +66,9 @@ def main():
     if args.mode == "selfplay":
         for layout in args.layouts.split(","):
             lp = layouts.load_layout(layout, 400)
-            pol = FusedPolicy(lp, 64, 1, gpu_id=local)
-            pol.set_weights(0, PolicyNet("actor", lp.width, lp.height, lp.channels, 64).init_like_reference(1),
-                            PolicyNet("critic", lp.width, lp.height, lp.channels, 64).init_like_reference(2))
+            pol = FusedPolicy(lp, args.hidden, 1, gpu_id=local)
+            pol.set_weights(0, PolicyNet("actor", lp.width, lp.height, lp.channels, args.hidden).init_like_reference(1),
+                            PolicyNet("critic", lp.width, lp.height, lp.channels, args.hidden).init_like_reference(2))
             env = B200Overcooked(layout, args.worlds, local, horizon=400, seed=1, world_offset=rank * args.worlds)
             ro = PolicyRollout(env, pol, args.T, seed=1, use_graph=bool(args.graph))
             ro.collect()
@@ -76,7 +77,7 @@ def main():
             rs, ep = sharding.reduce_episode_stats(*env.episode_stats())
             if rank == 0:
                 agent_steps = 2 * args.worlds * world * args.T
-                print(json.dumps({"mode": "selfplay", "layout": layout, "n_gpus": world, "worlds_per_gpu": args.worlds,
+                print(json.dumps({"mode": "selfplay", "layout": layout, "hidden": args.hidden, "n_gpus": world, "worlds_per_gpu": args.worlds,
                                   "T": args.T, "graph": bool(args.graph), "ms_per_rollout": round(ms, 4),
                                   "us_per_env_step": round(1e3 * ms / args.T, 3),
                                   "agent_steps_per_s": round(agent_steps / (ms * 1e-3)),
@@ -89,9 +90,9 @@ def main():
         layout = "random1"
         lp = layouts.load_layout(layout, 400)
         n = args.policies
-        pol = FusedPolicy(lp, 64, n, gpu_id=local)
+        pol = FusedPolicy(lp, args.hidden, n, gpu_id=local)
         for i in range(n):  # seeds 1 + 100 i (seed_skip, train/config.py:315)
-            pol.set_weights(i, PolicyNet("actor", lp.width, lp.height, lp.channels, 64).init_like_reference(1 + 100 * i),
+            pol.set_weights(i, PolicyNet("actor", lp.width, lp.height, lp.channels, args.hidden).init_like_reference(1 + 100 * i),
                             None)
         pairs = sharding.pair_shard(sharding.all_pairs(n), rank, world)
         ev = CrossPlayEvaluator(layout, pol, pairs, worlds_per_pair=args.worlds_per_pair, horizon=400, gpu_id=local,
