@@ -1280,25 +1280,32 @@ static int set_weights512(ocb_policy* p, int policy, int net, const float* conv_
     return OCB_OK;
 }
 
+// activation scratch of the hidden-512 forward for `tiles` row tiles (grow only)
+static int reserve512(ocb_policy* p, size_t tiles, cudaStream_t stream) {
+    if (tiles <= p->scratch_tiles) return OCB_OK;
+    // growing is not possible while the stream is being captured
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cs);
+    if (cs != cudaStreamCaptureStatusNone)
+        return fail(OCB_ERR_INVALID_ARG, "hidden-512 scratch must grow: call ocb_policy_reserve before capturing a graph");
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaFree(p->d_scratch);
+    p->d_scratch = nullptr, p->scratch_tiles = 0;
+    const size_t bytes = 2 * tiles * ((size_t)p->L5.kc1 + kKc2) * kABlk;
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_scratch, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OCB_ERR_CUDA, "hidden-512 scratch (%zu bytes): %s", bytes, cudaGetErrorString(e));
+    }
+    p->scratch_tiles = tiles;
+    return OCB_OK;
+}
+
 // the three launches of the hidden-512 forward
 static int policy_launch512(ocb_policy* p, PolicyParams& prm, cudaStream_t stream) {
     const size_t tiles = (size_t)prm.tiles;
-    if (tiles > p->scratch_tiles) {  // grow the activation scratch (not possible while the stream is being captured)
-        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        cudaStreamIsCapturing(stream, &cs);
-        if (cs != cudaStreamCaptureStatusNone)
-            return fail(OCB_ERR_INVALID_ARG, "hidden-512 scratch must grow: run one forward of this size before capturing a graph");
-        cudaError_t e = cudaDeviceSynchronize();
-        if (e == cudaSuccess) e = cudaFree(p->d_scratch);
-        p->d_scratch = nullptr, p->scratch_tiles = 0;
-        const size_t bytes = 2 * tiles * ((size_t)p->L5.kc1 + kKc2) * kABlk;
-        if (e == cudaSuccess) e = cudaMalloc(&p->d_scratch, bytes);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            return fail(OCB_ERR_CUDA, "hidden-512 scratch (%zu bytes): %s", bytes, cudaGetErrorString(e));
-        }
-        p->scratch_tiles = tiles;
-    }
+    const int rrc = reserve512(p, tiles, stream);
+    if (rrc != OCB_OK) return rrc;
     P5Params q;
     prm.blobs = p->d_blobs, prm.blob_stride = p->L5.total;
     q.base = prm;
@@ -1319,6 +1326,14 @@ static int policy_launch512(ocb_policy* p, PolicyParams& prm, cudaStream_t strea
     if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "hidden-512 policy launch failed: %s", cudaGetErrorString(err));
     p->calls += 1;
     return OCB_OK;
+}
+
+// pre-size internal scratch for forwards of up to M rows (no-op for hidden 64, which has none)
+extern "C" int ocb_policy_reserve(ocb_policy* p, int M) {
+    if (p == nullptr || M < 1) return fail(OCB_ERR_INVALID_ARG, "bad handle / M");
+    if (p->hidden != kH5) return OCB_OK;
+    DeviceGuard guard(p->device);
+    return reserve512(p, (size_t)((M + kRows - 1) / kRows), nullptr);
 }
 
 // weights in the reference's layouts (HOST fp32): conv_w [32,20,3,3], conv_b [32], fc1_w [64, 32*npos]

@@ -144,6 +144,7 @@ class PolicyRollout:
     def _capture(self, deterministic: bool):
         """capture the 2T+1 launches once; replays read the sampling offset from the device step
         counter, so they draw fresh actions"""
+        _native.check(self._lib.ocb_policy_reserve(self.policy._h, self.env.num_players * self.env.num_envs))
         torch.cuda.synchronize(self.env.sim_device)
         # capture does not execute: the env state is untouched, only the launch sequence is recorded
         g = torch.cuda.CUDAGraph()

@@ -218,6 +218,9 @@ int ocb_policy_forward(ocb_policy* pol, const int8_t* obs, int M, const int32_t*
 /* launch shape in effect: weight-ring slots in shared memory, FC weight chunks per (tile, network)
  * unit (ring >= chunks means the weights stay resident), dynamic shared memory per CTA */
 int ocb_policy_info(const ocb_policy* pol, int* ring_slots, int* chunks_per_unit, int* smem_bytes);
+/* pre-size the handle's internal activation scratch (hidden 512 only) for forwards of up to M rows:
+ * required before a forward of a new, larger M is captured into a CUDA graph */
+int ocb_policy_reserve(ocb_policy* pol, int M);
 
 /* diagnostic: one fused forward with the instrumented kernel build; h_prof (HOST) int64
  * [max_ctas][4 roles: epilogue, loader, MMA issuer, producer][16] = total cycles and cycles stalled

@@ -109,7 +109,7 @@ def test_sampling_follows_the_softmax_and_is_reproducible():
 def test_unsupported_shapes_fail_loudly():
     from diverse_conventions_b200 import _native
     with pytest.raises(_native.NativeError):
-        FusedPolicy(layouts.load_layout("simple", 400), hidden=512)
+        FusedPolicy(layouts.load_layout("simple", 400), hidden=128)
     with pytest.raises(_native.NativeError):
         FusedPolicy(layouts.load_layout("multiplayer_schelling", 400), hidden=64)  # 4 players
     with pytest.raises(_native.NativeError):
