@@ -64,6 +64,7 @@ PROTOTYPES = {
     "ocb_policy_debug_profile": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i]),
     "ocb_step_counter_device": (_vp, [_vp]),
     "ocb_rollout_policy": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _u64, _vp]),
+    "ocb_rollout_policy_fused": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _u64, _vp]),
     "ocb_compute_returns": (_i, [_i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ocb_normalize_advantages": (_i, [_i, _vp, _sz, _vp, _vp]),
     "bb_create": (_i, [_i, _u32, _u64, _pp]),
@@ -115,6 +116,9 @@ def lib(build_if_missing: bool = True):
             raise ImportError("libocb.so ABI version mismatch")
         _lib = L
     return _lib
+
+
+OCB_ERR_UNSUPPORTED = -6
 
 
 def check(code: int) -> int:

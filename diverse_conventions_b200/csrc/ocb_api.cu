@@ -12,6 +12,7 @@
 #include "oc_core.cuh"
 #include "oc_kernels.h"
 #include "oc_tables.h"
+#include "policy_internal.h"
 #include "ocb.h"
 
 using namespace ocb;
@@ -462,4 +463,22 @@ extern "C" int ocb_rollout_policy(ocb_env* e, ocb_policy* pol, int T, const int3
     // bootstrap value of the observation after the last step (MainPlayer.compute_one,
     // train/MAPPO/main_player.py:293-307)
     return ocb_policy_value(pol, obs_slab + (size_t)T * obs_step, M, tile_policy, values + (size_t)T * PN, stream);
+}
+
+// The same rollout as ocb_rollout_policy (self-play of ONE policy, critic required) in one persistent
+// launch (csrc/rollout_fused.cuh): bit-identical buffers, no per-step launches.  Also writes obs_slab[0].
+extern "C" int ocb_rollout_policy_fused(ocb_env* e, ocb_policy* pol, int T, int policy_index, int8_t* obs_slab,
+                                        int32_t* actions, float* logp, float* values, int32_t* reward, int32_t* done,
+                                        int deterministic, uint64_t seed, void* stream) {
+    if (e == nullptr || pol == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL handle");
+    if (e->P != 2) return fail(OCB_ERR_UNSUPPORTED, "the policy rollout supports 2 players");
+    DeviceGuard guard(e->device);
+    RolloutParams p = base_params(e);
+    const int rc = ocb_policy_rollout_fused_launch(pol, policy_index, p, e->h_tables.W, e->h_tables.H, T, obs_slab, actions, logp,
+                                                   values, reward, done, deterministic, seed,
+                                                   reinterpret_cast<const uint64_t*>(e->d_step_counter),
+                                                   reinterpret_cast<uint64_t*>(e->d_step_counter), stream);
+    if (rc != OCB_OK) return rc;
+    e->step_count += (uint64_t)T;
+    return OCB_OK;
 }

@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm512_kernel(const P5Params q)
                         if (ur.net == 1) {
                             if (prm.values) prm.values[row] = head[0];
                         } else {
-                            emit_actor_row(prm, row, head, offset);
+                            emit_actor_row(prm, row, (uint32_t)row, head, offset);
                         }
                     }
                 }

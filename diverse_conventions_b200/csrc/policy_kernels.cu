@@ -43,7 +43,9 @@
 
 #include "api_common.h"
 #include "oc_core.cuh"
+#include "oc_device.cuh"
 #include "ocb.h"
+#include "policy_internal.h"
 
 using namespace ocb;
 
@@ -531,24 +533,27 @@ __device__ __forceinline__ void mma_role(long long* pw, const PolicyParams& prm,
 
 // actor outputs of one row: raw logits, sampled (or arg-max) action and its log-prob
 // FixedCategorical(logits): sample / mode and log-prob (train/MAPPO/utils/distributions.py:14-28)
-__device__ __forceinline__ void emit_actor_row(const PolicyParams& prm, long long row, const float (&head)[6], unsigned long long offset) {
+// `store` indexes the output arrays, `rng_row` keys the sampling counter (they differ in the fused
+// rollout, where a step's outputs land at step * rows + row); returns the action
+__device__ __forceinline__ int emit_actor_row(const PolicyParams& prm, long long store, uint32_t rng_row, const float (&head)[6],
+                                              unsigned long long offset, bool force_sample = false) {
     if (prm.logits) {
 #pragma unroll
-        for (int a = 0; a < 6; ++a) prm.logits[row * 6 + a] = head[a];
+        for (int a = 0; a < 6; ++a) prm.logits[store * 6 + a] = head[a];
     }
-    if (prm.actions || prm.logp) {
+    int act = 0;
+    if (prm.actions || prm.logp || force_sample) {
         float mx = head[0];
 #pragma unroll
         for (int a = 1; a < 6; ++a) mx = fmaxf(mx, head[a]);
         float e[6], sum = 0.0f;
 #pragma unroll
         for (int a = 0; a < 6; ++a) e[a] = expf(head[a] - mx), sum += e[a];
-        int act = 0;
         if (prm.deterministic) {
 #pragma unroll
             for (int a = 1; a < 6; ++a) act = (head[a] > head[act]) ? a : act;
         } else {
-            uint32_t r[4] = {(uint32_t)row, (uint32_t)offset, (uint32_t)(offset >> 32), 0x5A17u};
+            uint32_t r[4] = {rng_row, (uint32_t)offset, (uint32_t)(offset >> 32), 0x5A17u};
             philox4x32_10(r, (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
             const float uu = (float)(r[0] >> 8) * (1.0f / 16777216.0f) * sum;
             float cum = 0.0f;
@@ -560,14 +565,15 @@ __device__ __forceinline__ void emit_actor_row(const PolicyParams& prm, long lon
                 if (!found && uu < cum) act = a, found = true;
             }
         }
-        if (prm.actions) prm.actions[row] = act;
+        if (prm.actions) prm.actions[store] = act;
         if (prm.logp) {
             float la = head[0];
 #pragma unroll
             for (int a = 1; a < 6; ++a) la = (act == a) ? head[a] : la;
-            prm.logp[row] = la - mx - logf(sum);
+            prm.logp[store] = la - mx - logf(sum);
         }
     }
+    return act;
 }
 
 // epilogue: TMEM -> bias/ReLU -> bf16 hi/lo A operand; head, sampling and outputs.  Two groups of four
@@ -665,7 +671,7 @@ __device__ __forceinline__ void epilogue_role(long long* pw, const PolicyParams&
             if (ur.net == 1) {
                 if (prm.values) prm.values[row] = head[0];
             } else {
-                emit_actor_row(prm, row, head, offset);
+                emit_actor_row(prm, row, (uint32_t)row, head, offset);
             }
         }
     }
@@ -934,9 +940,10 @@ __device__ __forceinline__ void pair_mma_role(long long* pw, const PolicyParams&
     }
 }
 
-template <bool kProf>
+// `out(t, trow_id, g, head)` consumes the head outputs of row trow_id of tile t (g = 0: six logits, g = 1: head[0] = value)
+template <bool kProf, class Out>
 __device__ __forceinline__ void pair_epilogue_role(long long* pw, const PolicyParams& prm, int t0, int t1, const BlobLayout L, uint32_t tmem,
-                                                   const uint8_t* s_head, uint32_t bars) {
+                                                   const uint8_t* s_head, uint32_t bars, Out&& out) {
     const int warp = threadIdx.x >> 5, g = warp >> 2, trow_id = (warp & 3) * 32 + (threadIdx.x & 31);
     const int npos = prm.npos;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 TMEM lanes
@@ -946,8 +953,6 @@ __device__ __forceinline__ void pair_epilogue_role(long long* pw, const PolicyPa
     const float* s_b2 = reinterpret_cast<const float*>(rest + L.b2);
     const float* s_wh = reinterpret_cast<const float*>(rest + L.wh);
     const float* s_bh = reinterpret_cast<const float*>(rest + L.bh);
-    unsigned long long offset = prm.offset;
-    if (prm.d_offset != nullptr) offset += *prm.d_offset;
     const uint32_t a2 = trow + kPColA2 + g * kA2Cols;
 
     uint32_t u = 0, head_gen = 0, item = 0, d1_par = 0;  // d1_par: phase parity bit per conv accumulator stage
@@ -1019,17 +1024,27 @@ __device__ __forceinline__ void pair_epilogue_role(long long* pw, const PolicyPa
             }
         }
         mbar_arrive(bars + 8 * (PB_HEAD_EMPTY + (u & 1)));  // done with the head block of this tile
-
+        out(t, trow_id, g, head);
+    }
+}
+// output stage of the plain forward: rows are tile-major
+struct PairForwardOut {
+    const PolicyParams& prm;
+    unsigned long long offset;
+    __device__ __forceinline__ PairForwardOut(const PolicyParams& p) : prm(p), offset(p.offset) {
+        if (p.d_offset != nullptr) offset += *p.d_offset;
+    }
+    __device__ __forceinline__ void operator()(int t, int trow_id, int g, const float (&head)[6]) const {
         const long long row = (long long)t * kRows + trow_id;
         if (row < prm.M) {
             if (g == 1) {
                 if (prm.values) prm.values[row] = head[0];
             } else {
-                emit_actor_row(prm, row, head, offset);
+                emit_actor_row(prm, row, (uint32_t)row, head, offset);
             }
         }
     }
-}
+};
 
 template <bool kProf>
 __global__ void __launch_bounds__(kThreads, 1) policy_pair_kernel(const PolicyParams prm) {
@@ -1075,7 +1090,7 @@ __global__ void __launch_bounds__(kThreads, 1) policy_pair_kernel(const PolicyPa
     long long pw[kProf ? PW_COUNT : 1] = {};
     const long long t_begin = kProf ? clock64() : 0;
     if (warp < kEpiWarps) {
-        pair_epilogue_role<kProf>(pw, prm, ur.t0, ur.t1, L, tmem, s_head, bars);
+        pair_epilogue_role<kProf>(pw, prm, ur.t0, ur.t1, L, tmem, s_head, bars, PairForwardOut(prm));
     } else if (warp < kWarpMma) {
         loader_role<kProf>(pw, prm, ur, tmem, s_stage, bars);
     } else if (warp == kWarpMma) {
@@ -1097,6 +1112,7 @@ __global__ void __launch_bounds__(kThreads, 1) policy_pair_kernel(const PolicyPa
 }
 
 #include "policy512.cuh"
+#include "rollout_fused.cuh"
 
 // ---------------------------------------------------------------- host-side packing
 uint16_t bf16_bits(float x) {
@@ -1213,6 +1229,7 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
     if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(conv512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(gemm512_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(gemm512_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
@@ -1507,4 +1524,44 @@ extern "C" int ocb_policy_debug_profile(ocb_policy* p, const int8_t* obs, int M,
         return fail(OCB_ERR_CUDA, "ocb_policy_debug_profile: %s", cudaGetErrorString(err));
     }
     return ctas;
+}
+
+// ---------------------------------------------------------------- fused self-play rollout (rollout_fused.cuh)
+int ocb_policy_rollout_fused_launch(ocb_policy* p, int policy_index, const RolloutParams& envp, int env_w, int env_h, int T,
+                                    int8_t* obs_slab, int32_t* actions, float* logp, float* values, int32_t* reward,
+                                    int32_t* done, int deterministic, uint64_t seed, const uint64_t* d_offset,
+                                    uint64_t* d_counter, void* stream) {
+    if (p == nullptr) return fail(OCB_ERR_INVALID_ARG, "policy is NULL");
+    if (p->hidden != kHid) return fail(OCB_ERR_UNSUPPORTED, "the fused rollout kernel exists for hidden_size 64 only");
+    if (policy_index < 0 || policy_index >= p->n_policies) return fail(OCB_ERR_INVALID_ARG, "policy index out of range");
+    if (env_w != p->W || env_h != p->H) return fail(OCB_ERR_INVALID_ARG, "env and policy were built for different layouts");
+    if (T < 1 || obs_slab == nullptr || actions == nullptr || values == nullptr)
+        return fail(OCB_ERR_INVALID_ARG, "T >= 1, obs_slab, actions and values are required");
+    const int fixed = fused_smem_layout(p->npos, 0, p->S, p->SC).total;
+    int ring = (kSmemBudget - fixed) / kChunk;
+    if (ring > kPMaxRing) ring = kPMaxRing;
+    if (ring > 2 * p->L.chunks) ring = 2 * p->L.chunks;
+    if (fixed > kSmemBudget || ring < 4)
+        return fail(OCB_ERR_UNSUPPORTED, "layout too large for the fused rollout kernel (%d x %d)", p->W, p->H);
+    DeviceGuard guard(p->device);
+    FusedParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.pol.blobs = p->d_blobs + (size_t)policy_index * 2 * (size_t)p->L.total, fp.pol.blob_stride = (size_t)p->L.total;
+    fp.pol.W = p->W, fp.pol.H = p->H, fp.pol.S = p->S, fp.pol.SC = p->SC, fp.pol.npos = p->npos;
+    fp.pol.M = kRows, fp.pol.tiles = 1;
+    fp.pol.deterministic = deterministic, fp.pol.seed = seed, fp.pol.offset = 0;
+    fp.pol.d_offset = reinterpret_cast<const unsigned long long*>(d_offset);
+    fp.pol.net_mask = 3, fp.pol.pair_ring = ring, fp.pol.stage_stride = p->stage_stride;
+    fp.env = envp;
+    fp.T = T, fp.wtiles = (envp.N + kFWorlds - 1) / kFWorlds;
+    fp.obs_slab = obs_slab, fp.actions = actions, fp.logp = logp, fp.values = values, fp.reward = reward, fp.done = done;
+    const int ctas = fp.wtiles < p->sm_count ? fp.wtiles : p->sm_count;
+    const size_t smem = (size_t)fused_smem_layout(p->npos, ring, p->S, p->SC).total;
+    rollout_fused_kernel<<<ctas, kFThreads, smem, (cudaStream_t)stream>>>(fp);
+    if (d_counter != nullptr)
+        counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(d_counter), (unsigned long long)T);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "fused rollout launch failed: %s", cudaGetErrorString(err));
+    p->calls += 1;
+    return OCB_OK;
 }

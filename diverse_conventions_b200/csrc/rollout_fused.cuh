@@ -1,0 +1,324 @@
+// rollout_fused.cuh — the whole T-step self-play rollout in ONE persistent launch (included by
+// policy_kernels.cu inside its anonymous namespace, after the pair kernel whose roles it reuses).
+//
+// The 2T+1-launch rollout (ocb_rollout_policy) is bound by its dependent launches: per env step a
+// policy launch and an env launch, each of which fills and drains the GPU for one tile per SM.
+// Here a CTA owns a tile of 64 worlds (= 128 agent rows: seat 0 rows 0-63, seat 1 rows 64-127) for
+// all T steps and nothing leaves the SM between the env step and the policy forward:
+//   * two env warps (one world per lane) keep the world state in registers / shared memory and the
+//     2 x 64 observation planes resident in shared memory (oc_core.cuh, as in oc_rollout_kernel);
+//     per step they wait for the tile's sampled actions, run the transition, rewrite the touched
+//     plane bytes and stream the planes to the PPO buffer with TMA bulk stores;
+//   * the loader warps of the policy pipeline read the planes straight from shared memory (no HBM
+//     / L2 round trip of the observations) and feed the tcgen05 conv as in policy_pair_kernel;
+//   * MMA issuer and weight producer are the pair kernel's roles, running over "virtual tiles"
+//     (world tile k, step u), u = 0..T (u = T is the bootstrap value pass);
+//   * the actor epilogue group samples the 128 actions, writes them (and log-probs, values) to the
+//     buffer and hands them to the env warps through shared memory + an mbarrier.
+// Bit-identical to the 2T+1-launch path: same MMA sequence per row tile, same sampling counters
+// (row = seat * N + world, offset = device step counter + u).
+#pragma once
+
+struct FusedParams {
+    PolicyParams pol;    // blobs of the selected policy, geometry, pair_ring, sampling parameters
+    RolloutParams env;   // tables, template, world state arrays, N, use_tma
+    int T;
+    int wtiles;          // ceil(N / 64) world tiles
+    int8_t* obs_slab;    // [T+1][2][N][SC]
+    int32_t* actions;    // [T][2][N]
+    float* logp;         // [T][2][N] or nullptr
+    float* values;       // [T+1][2][N]
+    int32_t* reward;     // [T][2][N] or nullptr
+    int32_t* done;       // [T][N] or nullptr
+};
+
+constexpr int kFEnvWarps = 2;
+constexpr int kFWarpEnv = kWarpProd + 1;                    // warps 18, 19
+constexpr int kFThreads = kThreads + 32 * kFEnvWarps;       // 640
+constexpr int kFWorlds = 32 * kFEnvWarps;                   // worlds per CTA tile
+enum : int {
+    FB_OBS_FULL = PB_COUNT,      // env warps (64 arrivals) -> loaders: planes of virtual tile vt are complete
+    FB_OBS_EMPTY = PB_COUNT + 1, // loaders (256 arrivals) -> env warps: planes of vt have been consumed
+    FB_ACT_FULL = PB_COUNT + 2,  // actor epilogue group (128 arrivals) -> env warps
+    FB_COUNT = PB_COUNT + 3
+};
+constexpr int kFActSlot = 80;  // 8-byte slots 80..95 of the barrier block hold the tile's 128 sampled actions (bytes)
+static_assert((int)FB_COUNT <= kFActSlot && kFActSlot + 16 <= (int)PB_TMEM_SLOT, "barrier block overflow");
+
+struct FusedSmemLayout {
+    int head, wring, bars, act, tables, tmpl, envw;
+    int view_stride, env_warp_bytes, total;
+};
+__host__ __device__ inline FusedSmemLayout fused_smem_layout(int npos, int ring, int S, int SC) {
+    FusedSmemLayout s;
+    const BlobLayout L = blob_layout(npos);
+    int o = 0;
+    s.head = o, o += kPRestOff + 2 * (L.head_bytes - L.bias1);
+    s.wring = o, o += ring * kChunk;
+    s.bars = o, o += 1024;
+    s.act = s.bars + 8 * kFActSlot;  // 128 action bytes inside the barrier block
+    s.tables = o, o += (int)align16(sizeof(Tables));
+    s.tmpl = o, o += (int)align16((size_t)SC);
+    s.envw = o;
+    s.view_stride = (int)align16((size_t)32 * SC);
+    s.env_warp_bytes = 2 * s.view_stride + (int)align16((size_t)S * 32 * 2);
+    o += kFEnvWarps * s.env_warp_bytes;
+    s.total = o + 128;
+    return s;
+}
+
+// loaders: shared-memory planes -> bf16 cell blocks in TMEM.  Thread (lw, lane) owns row 32 lw + lane
+// = seat lw / 2, env warp lw % 2, world `lane`; the two groups take alternate columns of the stream.
+__device__ __forceinline__ void fused_loader_role(const FusedParams& fp, uint32_t nvt, uint32_t tmem, const uint8_t* s_env,
+                                                  const FusedSmemLayout& sl, uint32_t bars) {
+    const int lwarp = (threadIdx.x >> 5) - kEpiWarps, lg = lwarp >> 2, lw = lwarp & 3, lane = threadIdx.x & 31;
+    const int W = fp.pol.W, H = fp.pol.H, seg = 5 * H;
+    const uint32_t* myrow = reinterpret_cast<const uint32_t*>(s_env + (lw & 1) * sl.env_warp_bytes + (lw >> 1) * sl.view_stride +
+                                                              lane * fp.pol.SC);
+    const uint32_t tcells = tmem + ((uint32_t)(lw * 32) << 16) + kColCells;
+    const uint32_t ncols = nvt * (uint32_t)W;
+    uint32_t lt = 0;  // virtual tile of the column
+    int lx = lg;      // grid column inside it
+    bool fresh = true;  // first column of this group in tile lt
+    for (uint32_t gc = lg; gc < ncols; gc += 2) {
+        if (fresh) {
+            mbar_wait(bars + 8 * FB_OBS_FULL, lt & 1);
+            fresh = false;
+        }
+        const int slot = gc % kColRing;
+        if (gc >= kColRing) {
+            mbar_wait(bars + 8 * (PB_COL_EMPTY + slot), ((gc / kColRing) - 1) & 1);
+            tc_fence_after();
+        }
+        const uint32_t* mine = myrow + lx * seg;
+        for (int y = 0; y < H; ++y) {
+            uint32_t w[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) w[q] = mine[y * 5 + q];
+            const uint4 c0 = make_uint4(bytes_bf16x2(w[0], pair_sel(0, 1)), bytes_bf16x2(w[0], pair_sel(2, 3)),
+                                        bytes_bf16x2(w[1], pair_sel(0, 1)), bytes_bf16x2(w[1], pair_sel(2, 3)));
+            const uint4 c1 = make_uint4(bytes_bf16x2(w[2], pair_sel(0, 1)), bytes_bf16x2(w[4], pair_sel(0, 1)),
+                                        bytes_bf16x2(w[4], pair_sel(2, 3)), bytes_bf16x2(w[3], pair_sel(3, 4)));
+            tmem_st8(tcells + (slot * H + y) * kCellCols, c0, c1);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bars + 8 * (PB_COL_FULL + slot));
+        lx += 2;
+        if (lx >= W) {  // this group's last column of the tile: its plane reads are done
+            mbar_arrive(bars + 8 * FB_OBS_EMPTY);
+            lx -= W, ++lt, fresh = true;
+        }
+    }
+}
+
+// env warps: one world per lane, state in registers / shared memory across the T steps
+__device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s_env, const FusedSmemLayout& sl, const Tables& tb,
+                                               const uint8_t* tmpl, const uint8_t* s_act, uint32_t bars) {
+    constexpr int P = 2;
+    const int ew = (threadIdx.x >> 5) - kFWarpEnv, lane = threadIdx.x & 31;
+    const Consts c = load_consts(tb);
+    const int SC = tb.SC, S = tb.S, N = fp.env.N, T = fp.T;
+    const int view_stride = sl.view_stride;
+    uint8_t* planes = s_env + ew * sl.env_warp_bytes;                                          // [P][32][SC]
+    uint16_t* myobjs = reinterpret_cast<uint16_t*>(planes + (size_t)P * view_stride) + lane;  // [S][32]
+    uint8_t* myplanes = planes + lane * SC;
+    const uint32_t planes_s = smem_addr(planes);
+    const size_t PN = (size_t)P * N, obs_view_stride = (size_t)N * SC, obs_step_stride = PN * SC;
+    uint32_t vt = 0, acts = 0;
+    bool tma_pending = false;
+
+    for (int kt = blockIdx.x; kt < fp.wtiles; kt += gridDim.x) {
+        const int n0 = kt * kFWorlds + ew * 32, n = n0 + lane;
+        const bool valid = n < N;
+        const int nl = valid ? n : N - 1;
+        const int nvalid = max(0, min(32, N - n0));
+        const int nbytes = nvalid * SC;
+        int8_t* obs_ptr = fp.obs_slab + (size_t)n0 * SC;
+        const bool tma_ok = fp.env.use_tma && nbytes > 0 && ((nbytes & 15) == 0) && ((reinterpret_cast<uintptr_t>(obs_ptr) & 15u) == 0) &&
+                            ((obs_view_stride & 15u) == 0);
+        int32_t* rew_ptr = fp.reward ? fp.reward + n : nullptr;
+        int32_t* done_ptr = fp.done ? fp.done + n : nullptr;
+
+        World<P> w;
+        load_world<P, 1>(tb, c, fp.env, nl, 0, myobjs, w);
+        int cur_return = fp.env.cur_return[nl];
+        long long ret_add = 0;
+        int ep_add = 0;
+
+        for (int u = 0; u <= T; ++u, ++vt) {
+            bool full = true;
+            int oldslot[P] = {0, 0};
+            uint32_t dirty[P] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+            if (u > 0) {
+                mbar_wait(bars + 8 * FB_ACT_FULL, acts & 1);
+                ++acts;
+                int act[P];
+                act[0] = s_act[ew * 32 + lane], act[1] = s_act[kFWorlds + ew * 32 + lane];
+#pragma unroll
+                for (int i = 0; i < P; ++i) oldslot[i] = w.slot[i];
+                const int r = step_world<P>(tb, c, w, myobjs, 32, act, dirty);
+                const bool done = w.timestep >= c.horizon;
+                cur_return += r;
+                if (done) {
+                    ret_add += cur_return;
+                    ep_add += 1;
+                    cur_return = 0;
+                    reset_world<P>(tb, w);
+                    for (int idx = 0; idx < c.n_objcells; ++idx) myobjs[(int)tb.objcells[idx] * 32] = 0;
+                }
+                if (rew_ptr != nullptr) {
+                    if (valid) rew_ptr[0] = r, rew_ptr[N] = r;
+                    rew_ptr += PN;
+                }
+                if (done_ptr != nullptr) {
+                    if (valid) *done_ptr = done ? 1 : 0;
+                    done_ptr += N;
+                }
+                full = done;
+            }
+            // the planes still hold virtual tile vt - 1: its loaders and its bulk store must be done with them
+            if (vt > 0) mbar_wait(bars + 8 * FB_OBS_EMPTY, (vt - 1) & 1);
+            if (tma_pending) {
+                if (lane == 0) bulk_wait_read_all();
+                tma_pending = false;
+            }
+            __syncwarp();
+            obs_phase1<P, 1>(tb, myplanes, view_stride, tmpl, full, 0, oldslot);
+            obs_phase2<P, 1>(tb, c, myplanes, view_stride, myobjs, 32, full, 0, w, dirty);
+            mbar_arrive(bars + 8 * FB_OBS_FULL);  // release: the loaders may read this lane's planes
+            int8_t* dst = obs_ptr + (size_t)u * obs_step_stride;
+            if (tma_ok) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int v = 0; v < P; ++v) bulk_store_s2g(dst + v * obs_view_stride, planes_s + v * view_stride, (uint32_t)nbytes);
+                    bulk_commit();
+                }
+                tma_pending = true;
+            } else if (nbytes > 0) {
+                __syncwarp();
+#pragma unroll
+                for (int v = 0; v < P; ++v) warp_copy_out(dst + v * obs_view_stride, planes + v * view_stride, nbytes, lane);
+            }
+        }
+        // world state back to HBM (the next launch, or ocb_get_state, continues from it)
+        if (valid) {
+            fp.env.players[n] = player_pack(w.pos[0], w.orient[0], w.held[0]);
+            fp.env.players[(size_t)N + n] = player_pack(w.pos[1], w.orient[1], w.held[1]);
+            for (int cell = 0; cell < S; ++cell) fp.env.objs[(size_t)cell * N + n] = myobjs[cell * 32];
+            fp.env.timestep[n] = w.timestep;
+            fp.env.cur_return[n] = cur_return;
+            if (ep_add) {
+                fp.env.ret_sum[n] += ret_add;
+                fp.env.episodes[n] += ep_add;
+            }
+        }
+        __syncwarp();
+    }
+    if (tma_pending && lane == 0) bulk_wait_read_all();
+}
+
+// output stage of the epilogue in the fused rollout
+struct FusedOut {
+    const FusedParams& fp;
+    uint8_t* s_act;
+    uint32_t bars;
+    unsigned long long base;
+    int u, kt;
+    __device__ __forceinline__ FusedOut(const FusedParams& f, uint8_t* sa, uint32_t b) : fp(f), s_act(sa), bars(b), u(0), kt(blockIdx.x) {
+        base = f.pol.offset;
+        if (f.pol.d_offset != nullptr) base += *f.pol.d_offset;
+    }
+    __device__ __forceinline__ void operator()(int, int trow_id, int g, const float (&head)[6]) {
+        const int N = fp.env.N, wl = trow_id & (kFWorlds - 1), seat = trow_id >> 6;
+        const int n = kt * kFWorlds + wl;
+        const long long row = (long long)seat * N + n;               // row of one step's [2][N] block
+        const long long store = (long long)u * 2 * N + row;
+        if (g == 1) {
+            if (n < N) fp.values[store] = head[0];
+        } else if (u < fp.T) {
+            PolicyParams op = fp.pol;  // output pointers of this step; rows past N sample but store nothing
+            const bool valid = n < N;
+            op.actions = valid ? fp.actions : nullptr, op.logp = valid ? fp.logp : nullptr, op.logits = nullptr;
+            const int act = emit_actor_row(op, store, (uint32_t)row, head, base + (unsigned long long)u, true);
+            s_act[trow_id] = (uint8_t)act;
+            mbar_arrive(bars + 8 * FB_ACT_FULL);
+        }
+        if (++u > fp.T) u = 0, kt += gridDim.x;
+    }
+};
+
+__global__ void __launch_bounds__(kFThreads, 1) rollout_fused_kernel(const FusedParams fp) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const PolicyParams& prm = fp.pol;
+    const BlobLayout L = blob_layout(prm.npos);
+    const FusedSmemLayout sl = fused_smem_layout(prm.npos, prm.pair_ring, prm.S, prm.SC);
+    uint8_t* s_head = smem + sl.head;
+    uint8_t* s_wring = smem + sl.wring;
+    uint64_t* s_bars = reinterpret_cast<uint64_t*>(smem + sl.bars);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bars + PB_TMEM_SLOT);
+    uint8_t* s_act = smem + sl.act;
+    Tables* s_tables = reinterpret_cast<Tables*>(smem + sl.tables);
+    uint8_t* s_tmpl = smem + sl.tmpl;
+    uint8_t* s_env = smem + sl.envw;
+    const uint32_t bars = smem_addr(s_bars);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)),
+                     "r"((uint32_t)kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < FB_COUNT; ++i) {
+            uint32_t count = 1;
+            if ((i >= PB_COL_FULL && i < PB_COL_FULL + 4) || (i >= PB_A2_FULL && i < PB_A2_FULL + 2) ||
+                (i >= PB_D3_EMPTY && i < PB_D3_EMPTY + 2))
+                count = 128;
+            if (i >= PB_HEAD_EMPTY && i < PB_HEAD_EMPTY + 2) count = 32 * kEpiWarps + 1;
+            if (i == FB_OBS_FULL) count = 32 * kFEnvWarps;
+            if (i == FB_OBS_EMPTY) count = 32 * kLoadWarps;
+            if (i == FB_ACT_FULL) count = 128;
+            mbar_init(bars + 8 * i, count);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {  // static layout tables and the observation template
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(fp.env.tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_tables);
+        for (int i = tid; i < (int)(sizeof(Tables) / 4); i += kFThreads) dst[i] = src[i];
+        for (int i = tid; i < prm.SC; i += kFThreads) s_tmpl[i] = fp.env.tmpl[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    // virtual tiles of this CTA: (world tile k, step u), u = 0..T, world tiles blockIdx.x, + gridDim.x, ...
+    const int nk = ((int)blockIdx.x < fp.wtiles) ? (fp.wtiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int nvt = nk * (fp.T + 1);
+
+    long long pw[1] = {};
+    if (warp < kEpiWarps) {
+        pair_epilogue_role<false>(pw, prm, 0, nvt, L, tmem, s_head, bars, FusedOut(fp, s_act, bars));
+    } else if (warp < kWarpMma) {
+        fused_loader_role(fp, (uint32_t)nvt, tmem, s_env, sl, bars);
+    } else if (warp == kWarpMma) {
+        pair_mma_role<false>(pw, prm, 0, nvt, L, tmem, smem_addr(s_head), smem_addr(s_wring), bars);
+    } else if (warp == kWarpProd) {
+        pair_producer_role<false>(pw, prm, 0, nvt, L, smem_addr(s_head), smem_addr(s_wring), bars);
+    } else {
+        fused_env_role(fp, s_env, sl, *s_tables, s_tmpl, s_act, bars);
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+}
+
+// device step counter += k, after the rollout kernel (every CTA reads the counter at its start)
+__global__ void counter_add_kernel(unsigned long long* ctr, unsigned long long k) { *ctr += k; }

@@ -87,7 +87,11 @@ class PolicyRollout:
     everybody (plain self-play, train/trainer.py:41-44)."""
 
     def __init__(self, env: B200Overcooked, policy: FusedPolicy, T: int, tile_policy: Optional[torch.Tensor] = None,
-                 with_critic: bool = True, with_logp: bool = True, seed: int = 0, use_graph: bool = False):
+                 with_critic: bool = True, with_logp: bool = True, seed: int = 0, use_graph: bool = False,
+                 fused: Optional[bool] = None, policy_index: int = 0):
+        """``fused``: run the rollout as ONE persistent launch (``ocb_rollout_policy_fused``: self-play of weight
+        set ``policy_index``, hidden 64, critic on); ``None`` = use it whenever it applies, ``False`` = always the
+        2T+1-launch path.  Both paths fill bit-identical buffers."""
         if env.num_players != 2:
             raise ValueError("the policy rollout supports 2 players")
         if env.sim_device != policy.device:
@@ -103,6 +107,15 @@ class PolicyRollout:
         self.tile_policy = tile_policy
         self.buf = RolloutBuffer(env, T, with_critic, with_logp)
         self._lib = _native.lib()
+        self.policy_index = policy_index
+        can_fuse = tile_policy is None and with_critic and policy.hidden == 64
+        if fused and not can_fuse:
+            raise ValueError("the fused rollout needs self-play of one policy (no tile_policy), hidden 64 and the critic")
+        self.fused = can_fuse if fused is None else bool(fused)
+        self._fused_required = bool(fused)
+        if tile_policy is None and policy_index != 0 and not self.fused:
+            self.tile_policy = tile_policy = torch.full(((M + TILE - 1) // TILE,), policy_index, dtype=torch.int32,
+                                                        device=env.sim_device)
         self._primed = False
         self._graphs = {}
         self.use_graph = use_graph
@@ -112,6 +125,14 @@ class PolicyRollout:
     def _issue(self, deterministic: bool):
         b, env = self.buf, self.env
         stream = ctypes.c_void_p(torch.cuda.current_stream(env.sim_device).cuda_stream)
+        if self.fused:
+            rc = self._lib.ocb_rollout_policy_fused(
+                env._h, self.policy._h, self.T, self.policy_index, _ptr(b.obs), _ptr(b.actions), _ptr(b.action_log_probs),
+                _ptr(b.value_preds), _ptr(b.rewards), _ptr(b.dones), int(deterministic), self.seed, stream)
+            if rc != _native.OCB_ERR_UNSUPPORTED or self._fused_required:
+                _native.check(rc)
+                return
+            self.fused = False  # layout too large for the fused kernel: per-step launches from here on
         _native.check(self._lib.ocb_rollout_policy(
             env._h, self.policy._h, self.T, _ptr(self.tile_policy), _ptr(b.obs), _ptr(b.actions),
             _ptr(b.action_log_probs), _ptr(b.value_preds), _ptr(b.rewards), _ptr(b.dones), int(deterministic),

@@ -249,6 +249,17 @@ int ocb_rollout_policy(ocb_env* env, ocb_policy* pol, int T, const int32_t* tile
                        int32_t* actions, float* logp, float* values, int32_t* reward, int32_t* done,
                        int deterministic, uint64_t seed, void* stream);
 
+/* ocb_rollout_policy for self-play of ONE weight set (policy_index of the handle; hidden 64, critic
+ * required: values != NULL) as a single persistent launch: each CTA owns 64 worlds (128 agent rows)
+ * for all T steps, the env step and the actor+critic forward hand over through shared memory, and
+ * only the rollout-buffer writes touch HBM.  Buffers are bit-identical to ocb_rollout_policy's
+ * (same sampling counters); obs_slab[0] is written by the kernel (no ocb_observe needed).
+ * OCB_ERR_UNSUPPORTED when the layout does not fit the kernel's shared memory — callers then use
+ * ocb_rollout_policy.  Replaces the same reference loop (train/MAPPO/main_player.py:91-112,211-261). */
+int ocb_rollout_policy_fused(ocb_env* env, ocb_policy* pol, int T, int policy_index, int8_t* obs_slab, int32_t* actions,
+                             float* logp, float* values, int32_t* reward, int32_t* done, int deterministic,
+                             uint64_t seed, void* stream);
+
 /* ------------------------------------------------------- returns / GAE over the rollout buffer */
 /* SharedReplayBuffer.compute_returns (train/MAPPO/utils/shared_buffer.py:248-304) with the
  * ValueNorm de-normalisation (train/MAPPO/utils/valuenorm.py:76-87) and the advantage

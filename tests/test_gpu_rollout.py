@@ -46,13 +46,15 @@ def replay_through_oracle(lp, N, buf):
     return np.concatenate([first[None], o]), r, d, orc
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("layout,N,T", [("simple", 384, 70), ("random1", 200, 45)])
-def test_selfplay_rollout_matches_oracle_and_torch(layout, N, T):
+def test_selfplay_rollout_matches_oracle_and_torch(layout, N, T, fused):
     horizon = 30  # several auto-resets inside one rollout
     lp = layouts.load_layout(layout, horizon)
     pol, actors, critics = make_policies(lp, 1)
     env = B200Overcooked(layout, N, 0, horizon=horizon, seed=5)
-    ro = PolicyRollout(env, pol, T, seed=123)
+    ro = PolicyRollout(env, pol, T, seed=123, fused=fused)
+    assert ro.fused == fused
     buf = ro.collect()
     torch.cuda.synchronize()
 
@@ -114,14 +116,15 @@ def test_shared_buffer_views_follow_the_reference_axis_order():
     assert torch.equal(v["obs"][2, 5, 1], buf.obs[2, 1, 5])
 
 
-def test_deterministic_rollout_graph_replay_equals_plain_launches():
+@pytest.mark.parametrize("fused", [False, True])
+def test_deterministic_rollout_graph_replay_equals_plain_launches(fused):
     lp = layouts.load_layout("random0", 25)
     pol, _, _ = make_policies(lp, 1)
     N, T = 256, 40
     outs = []
     for use_graph in (False, True):
         env = B200Overcooked("random0", N, 0, horizon=25, seed=2)
-        ro = PolicyRollout(env, pol, T, use_graph=use_graph, seed=9)
+        ro = PolicyRollout(env, pol, T, use_graph=use_graph, seed=9, fused=fused)
         a = ro.collect(deterministic=True)
         first = (a.obs.clone(), a.actions.clone(), a.value_preds.clone(), a.rewards.clone(), a.dones.clone())
         b = ro.collect(deterministic=True)
@@ -135,12 +138,13 @@ def test_deterministic_rollout_graph_replay_equals_plain_launches():
     assert np.array_equal(outs[0][2], outs[1][2])
 
 
-def test_sampled_graph_replays_draw_fresh_actions_and_stay_exact():
+@pytest.mark.parametrize("fused", [False, True])
+def test_sampled_graph_replays_draw_fresh_actions_and_stay_exact(fused):
     lp = layouts.load_layout("simple", 400)
     pol, actors, _ = make_policies(lp, 1)
     N, T = 256, 12
     env = B200Overcooked("simple", N, 0, horizon=400, seed=4)
-    ro = PolicyRollout(env, pol, T, use_graph=True, seed=77)
+    ro = PolicyRollout(env, pol, T, use_graph=True, seed=77, fused=fused)
     orc = COracle(lp, N)
     prev_actions = None
     for k in range(3):
@@ -152,6 +156,55 @@ def test_sampled_graph_replays_draw_fresh_actions_and_stay_exact():
             assert not torch.equal(prev_actions[0], buf.actions[0])
         prev_actions = buf.actions.clone()
     assert np.array_equal(env.get_state(), orc.state)
+
+
+@pytest.mark.parametrize("layout,N,T,horizon,index", [
+    ("simple", 64 * 150 + 37, 9, 7, 0),   # more world tiles than SMs (two per CTA on some) + a ragged last tile
+    ("simple", 1000, 33, 12, 1),          # second weight set of the handle
+    ("unident_s", 300, 21, 10, 0),        # 9 x 5 grid: weights streamed through the ring
+    ("random3", 130, 17, 400, 0),         # 8 x 5 grid, no reset inside the rollout
+])
+def test_fused_rollout_is_bit_identical_to_the_per_step_launches(layout, N, T, horizon, index):
+    """the single persistent launch (ocb_rollout_policy_fused) and the 2T+1 launches of ocb_rollout_policy fill the
+    same buffers: same observations / rewards / dones, same sampled actions, same log-probs and values (bitwise),
+    same final state and episode statistics, over two consecutive rollouts"""
+    lp = layouts.load_layout(layout, horizon)
+    pol, _, _ = make_policies(lp, 2)
+    res = []
+    for fused in (False, True):
+        env = B200Overcooked(layout, N, 0, horizon=horizon, seed=8)
+        ro = PolicyRollout(env, pol, T, seed=31, fused=fused, policy_index=index)
+        out = []
+        for _ in range(2):
+            b = ro.collect()
+            torch.cuda.synchronize()
+            out.append([x.clone() for x in (b.obs, b.actions, b.action_log_probs, b.value_preds, b.rewards, b.dones)])
+        assert ro.fused == fused
+        rs, ep = env.episode_stats()
+        res.append((out, env.get_state(), rs.clone(), ep.clone(), env.step_count))
+        env.close()
+    names = ("obs", "actions", "logp", "values", "rewards", "dones")
+    for k in range(2):
+        for name, x, y in zip(names, res[0][0][k], res[1][0][k]):
+            assert torch.equal(x, y), (k, name)
+    assert np.array_equal(res[0][1], res[1][1])
+    assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3]) and res[0][4] == res[1][4] == 2 * T
+
+
+def test_fused_rollout_falls_back_when_the_layout_does_not_fit():
+    """scenario3 (10 x 6): the resident observation planes leave no room for the weight ring"""
+    from diverse_conventions_b200 import _native
+    lp = layouts.load_layout("scenario3", 50)
+    pol, _, _ = make_policies(lp, 1)
+    env = B200Overcooked("scenario3", 96, 0, horizon=50, seed=1)
+    with pytest.raises(_native.NativeError):
+        PolicyRollout(env, pol, 4, fused=True).collect()
+    ro = PolicyRollout(env, pol, 4)  # fused=None: use it when it applies
+    buf = ro.collect()
+    torch.cuda.synchronize()
+    assert ro.fused is False
+    o, r, d, _ = replay_through_oracle(lp, 96, buf)
+    assert np.array_equal(buf.obs.cpu().numpy(), o) and np.array_equal(buf.rewards.cpu().numpy(), r)
 
 
 def test_crossplay_slices_use_the_named_policies_and_return_matrix_matches_oracle():

@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--policies", type=int, default=16)
     ap.add_argument("--worlds-per-pair", type=int, default=1024)
     ap.add_argument("--hidden", type=int, default=64, choices=[64, 512])
+    ap.add_argument("--fused", type=int, default=-1, help="1: one persistent launch per rollout, 0: 2T+1 launches, -1: auto")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -70,7 +71,7 @@ def main():
             pol.set_weights(0, PolicyNet("actor", lp.width, lp.height, lp.channels, args.hidden).init_like_reference(1),
                             PolicyNet("critic", lp.width, lp.height, lp.channels, args.hidden).init_like_reference(2))
             env = B200Overcooked(layout, args.worlds, local, horizon=400, seed=1, world_offset=rank * args.worlds)
-            ro = PolicyRollout(env, pol, args.T, seed=1, use_graph=bool(args.graph))
+            ro = PolicyRollout(env, pol, args.T, seed=1, use_graph=bool(args.graph), fused=None if args.fused < 0 else bool(args.fused))
             ro.collect()
             ro.collect()
             ms = timed(ro.collect, args.iters, world, dev)
@@ -78,7 +79,7 @@ def main():
             if rank == 0:
                 agent_steps = 2 * args.worlds * world * args.T
                 print(json.dumps({"mode": "selfplay", "layout": layout, "hidden": args.hidden, "n_gpus": world, "worlds_per_gpu": args.worlds,
-                                  "T": args.T, "graph": bool(args.graph), "ms_per_rollout": round(ms, 4),
+                                  "T": args.T, "graph": bool(args.graph), "fused": bool(ro.fused), "ms_per_rollout": round(ms, 4),
                                   "us_per_env_step": round(1e3 * ms / args.T, 3),
                                   "agent_steps_per_s": round(agent_steps / (ms * 1e-3)),
                                   "buffer_mb": round(ro.buf.nbytes() / 2**20, 1),
