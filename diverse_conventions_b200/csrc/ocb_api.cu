@@ -462,7 +462,10 @@ extern "C" int ocb_rollout_policy(ocb_env* e, ocb_policy* pol, int T, const int3
     if (values == nullptr) return OCB_OK;
     // bootstrap value of the observation after the last step (MainPlayer.compute_one,
     // train/MAPPO/main_player.py:293-307)
-    return ocb_policy_value(pol, obs_slab + (size_t)T * obs_step, M, tile_policy, values + (size_t)T * PN, stream);
+    // (through the same fused actor+critic kernel as the steps above, so that the value head sums in the same order
+    // everywhere and ocb_rollout_policy_fused can reproduce the buffer bit for bit)
+    return ocb_policy_forward(pol, obs_slab + (size_t)T * obs_step, M, tile_policy, nullptr, nullptr, nullptr,
+                              values + (size_t)T * PN, 1, 0, 0, nullptr, stream);
 }
 
 // The same rollout as ocb_rollout_policy (self-play of ONE policy, critic required) in one persistent
