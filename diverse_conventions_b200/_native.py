@@ -67,6 +67,9 @@ PROTOTYPES = {
     "ocb_rollout_policy_fused": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _u64, _vp]),
     "ocb_compute_returns": (_i, [_i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ocb_normalize_advantages": (_i, [_i, _vp, _sz, _vp, _vp]),
+    "ocb_policy_evaluate": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ocb_minibatch_gather": (_i, [_i, _vp, _i, _i, _vp, _vp, _i, _i, _pp, _pp, _i, _pp, _pp, _vp]),
+    "ocb_ppo_loss": (_i, [_i, _vp, _i] + [_vp] * 15),
     "bb_create": (_i, [_i, _u32, _u64, _pp]),
     "bb_destroy": (_i, [_vp]),
     "bb_num_worlds": (_i, [_vp]),

@@ -23,4 +23,13 @@ struct DeviceGuard {
     }
 };
 
+// A handle may be destroyed (e.g. by a garbage collector) while ANOTHER stream of this thread is being
+// captured into a CUDA graph; cudaFree is a "potentially unsafe" call that would invalidate a
+// global-mode capture.  Relaxed mode for the scope of the frees keeps the capture intact.
+struct CaptureRelaxed {
+    cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+    CaptureRelaxed() { cudaThreadExchangeStreamCaptureMode(&mode); }
+    ~CaptureRelaxed() { cudaThreadExchangeStreamCaptureMode(&mode); }
+};
+
 }  // namespace ocb

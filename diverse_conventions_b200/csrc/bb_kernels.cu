@@ -221,6 +221,7 @@ static int bb_launch(bb_env* e, BBParams& p, void* stream) {
 extern "C" int bb_destroy(bb_env* e) {
     if (e == nullptr) return OCB_OK;
     DeviceGuard guard(e->device);
+    CaptureRelaxed relaxed;  // safe while another stream is being captured
     cudaFree(e->d_state);
     cudaFree(e->d_episode);
     delete e;

@@ -103,6 +103,7 @@ extern "C" int ocb_device_count(void) {
 extern "C" int ocb_destroy(ocb_env* e) {
     if (e == nullptr) return OCB_OK;
     DeviceGuard guard(e->device);
+    CaptureRelaxed relaxed;  // safe while another stream is being captured
     cudaFree(e->d_tables);
     cudaFree(e->d_tmpl);
     cudaFree(e->d_players);

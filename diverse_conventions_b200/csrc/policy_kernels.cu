@@ -110,6 +110,9 @@ struct PolicyParams {
     const int8_t* obs;        // [M][SC]
     int M, tiles;
     const int32_t* tile_policy;  // [tiles] or nullptr
+    const int32_t* row_index;    // [M] source row of each forward row (obs / given_actions are indexed by it) or nullptr
+    const int32_t* given_actions;  // evaluate_actions: log-prob of the stored action of the source row instead of sampling
+    float* entropy;              // [M] entropy of the action distribution, or nullptr
     float* logits;            // [M][6] or nullptr
     int32_t* actions;         // [M] or nullptr
     float* logp;              // [M] or nullptr
@@ -332,7 +335,16 @@ __device__ __forceinline__ void loader_role(long long* pw, const PolicyParams& p
     while (lx >= W) lx -= W, ++lt;
     auto issue_loads = [&]() {
         const long long r0 = (long long)lt * kRows + lw * 32;
-        if (r0 + 32 <= prm.M) {  // full 32-row slab: constant-stride addresses
+        if (prm.row_index != nullptr) {  // minibatch rows picked out of the rollout buffer (ocb_policy_evaluate)
+            long long mine = r0 + lane;
+            mine = mine < prm.M ? mine : prm.M - 1;
+            const int src = __ldg(prm.row_index + mine);
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const long long row = __shfl_sync(0xffffffffu, src, r);
+                pre[r] = active ? __ldg(obs32 + row * SC4 + lx * seg + lane) : 0u;
+            }
+        } else if (r0 + 32 <= prm.M) {  // full 32-row slab: constant-stride addresses
             const uint32_t* p = obs32 + r0 * SC4 + lx * seg + (active ? lane : 0);
 #pragma unroll
             for (int r = 0; r < 32; ++r) pre[r] = active ? __ldg(p + r * SC4) : 0u;
@@ -542,14 +554,25 @@ __device__ __forceinline__ int emit_actor_row(const PolicyParams& prm, long long
         for (int a = 0; a < 6; ++a) prm.logits[store * 6 + a] = head[a];
     }
     int act = 0;
-    if (prm.actions || prm.logp || force_sample) {
+    if (prm.actions || prm.logp || prm.entropy || force_sample) {
         float mx = head[0];
 #pragma unroll
         for (int a = 1; a < 6; ++a) mx = fmaxf(mx, head[a]);
         float e[6], sum = 0.0f;
 #pragma unroll
         for (int a = 0; a < 6; ++a) e[a] = expf(head[a] - mx), sum += e[a];
-        if (prm.deterministic) {
+        if (prm.entropy) {  // -sum p log p with log p = (x - max) - log(sum) (torch Categorical.entropy on normalised logits)
+            const float ls = logf(sum);
+            float ent = 0.0f;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) ent -= (e[a] / sum) * (head[a] - mx - ls);
+            prm.entropy[store] = ent;
+        }
+        if (prm.given_actions) {
+            const long long src = prm.row_index ? (long long)prm.row_index[store] : store;
+            act = prm.given_actions[src];
+            act = act < 0 ? 0 : (act > 5 ? 5 : act);
+        } else if (prm.deterministic) {
 #pragma unroll
             for (int a = 1; a < 6; ++a) act = (head[a] > head[act]) ? a : act;
         } else {
@@ -1160,6 +1183,7 @@ struct ocb_policy {
 extern "C" int ocb_policy_destroy(ocb_policy* p) {
     if (p == nullptr) return OCB_OK;
     DeviceGuard guard(p->device);
+    CaptureRelaxed relaxed;  // safe while another stream is being captured
     cudaFree(p->d_scratch);
     cudaFree(p->d_blobs);
     delete p;
@@ -1417,9 +1441,17 @@ extern "C" int ocb_policy_set_weights(ocb_policy* p, int policy, int net, const 
     return OCB_OK;
 }
 
+// evaluate_actions extras of ocb_policy_evaluate
+struct EvalArgs {
+    const int32_t* row_index;
+    const int32_t* given_actions;
+    float* entropy;
+};
+
 static int policy_launch(ocb_policy* p, int net_mask, const int8_t* obs, int M, const int32_t* tile_policy, float* logits,
                          int32_t* actions, float* logp, float* values, int deterministic, uint64_t seed, uint64_t offset,
-                         const uint64_t* d_offset, void* stream, long long* prof = nullptr, int* ctas_out = nullptr) {
+                         const uint64_t* d_offset, void* stream, long long* prof = nullptr, int* ctas_out = nullptr,
+                         const EvalArgs* ev = nullptr) {
     if (p == nullptr || obs == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL argument");
     if (M < 1) return fail(OCB_ERR_INVALID_ARG, "M must be >= 1");
     if ((reinterpret_cast<uintptr_t>(obs) & 3u) != 0) return fail(OCB_ERR_INVALID_ARG, "obs must be 4-byte aligned");
@@ -1435,6 +1467,7 @@ static int policy_launch(ocb_policy* p, int net_mask, const int8_t* obs, int M, 
     prm.net_mask = net_mask, prm.ring = p->ring, prm.stage_stride = p->stage_stride;
     prm.pair_ring = p->pair_ring;
     prm.prof = prof;
+    if (ev != nullptr) prm.row_index = ev->row_index, prm.given_actions = ev->given_actions, prm.entropy = ev->entropy;
     if (p->hidden == kH5) {
         if (prof != nullptr) return fail(OCB_ERR_UNSUPPORTED, "the role profile exists for hidden 64 only");
         if (ctas_out) *ctas_out = 0;
@@ -1491,6 +1524,18 @@ extern "C" int ocb_policy_forward(ocb_policy* p, const int8_t* obs, int M, const
                                   uint64_t offset, const uint64_t* d_offset, void* stream) {
     if (values == nullptr) return fail(OCB_ERR_INVALID_ARG, "values is NULL");
     return policy_launch(p, 3, obs, M, tile_policy, logits, actions, logp, values, deterministic, seed, offset, d_offset, stream);
+}
+
+// evaluate_actions over minibatch rows picked out of the rollout buffer in place (R_Actor.evaluate_actions
+// r_actor_critic.py:73-109 + R_Critic.forward 178-197): same kernels as ocb_policy_forward, the loader follows `rows`,
+// the actor epilogue scores the stored action and emits the entropy instead of sampling
+extern "C" int ocb_policy_evaluate(ocb_policy* p, const int8_t* obs, const int32_t* rows, int B, const int32_t* tile_policy,
+                                   const int32_t* actions_src, float* logp, float* entropy, float* logits, float* values,
+                                   void* stream) {
+    if (actions_src == nullptr || logp == nullptr) return fail(OCB_ERR_INVALID_ARG, "actions_src and logp are required");
+    const EvalArgs ev = {rows, actions_src, entropy};
+    return policy_launch(p, values != nullptr ? 3 : 1, obs, B, tile_policy, logits, nullptr, logp, values, 0, 0, 0, nullptr, stream,
+                         nullptr, nullptr, &ev);
 }
 
 extern "C" int ocb_policy_info(const ocb_policy* p, int* ring_slots, int* chunks_per_unit, int* smem_bytes) {

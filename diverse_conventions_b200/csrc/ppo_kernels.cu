@@ -14,6 +14,7 @@
 // bit-identical to torch's CPU result; the mean / std reduction runs in fp64.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "api_common.h"
 #include "ocb.h"
@@ -186,5 +187,317 @@ extern "C" int ocb_normalize_advantages(int device, float* advantages, size_t n,
     normalize_adv_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(advantages, n, adv_stats);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "normalize kernel launch failed: %s", cudaGetErrorString(err));
+    return OCB_OK;
+}
+
+// =====================================================================================================
+// PPO minibatch: gather, loss
+//
+// Reference: SharedReplayBuffer.feed_forward_generator (train/MAPPO/utils/shared_buffer.py:306-366: randperm +
+// fancy indexing of twelve [T*N*P, ...] tensors, fp32 observations twice) and R_MAPPO.cal_value_loss / ppo_update
+// (train/MAPPO/r_mappo.py:52-127).  Here a minibatch is a list of agent-row indices into the seat-major
+// buffer; observations stay int8 and are either consumed in place (ocb_policy_evaluate) or copied once.
+namespace {
+
+constexpr int kMaxF32Fields = 8, kMaxI32Fields = 4;
+
+struct GatherParams {
+    const int32_t* rows;  // [B] or nullptr
+    int B, words;         // 4-byte words per observation row
+    const uint32_t* obs;
+    void* obs_out;
+    int obs_out_f32;
+    int n_f32, n_i32;
+    const float* src_f32[kMaxF32Fields];
+    float* out_f32[kMaxF32Fields];
+    const int32_t* src_i32[kMaxI32Fields];
+    int32_t* out_i32[kMaxI32Fields];
+};
+
+// The output is one dense run of B * S*C bytes: thread i owns output chunks i, i + threads, ... (a chunk = one
+// 16-byte vector when rows are 16-byte multiples, else one 4-byte word) and keeps kU independent loads in flight;
+// the source row of a chunk is one index load (L1/L2-resident: consecutive chunks share it) plus a division.
+template <typename V, int kU, bool kF32Out>
+__global__ void __launch_bounds__(256) minibatch_gather_kernel(const GatherParams p) {
+    const unsigned cpr = (unsigned)p.words / (sizeof(V) / 4);  // chunks per row
+    const size_t total = (size_t)p.B * cpr, nthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool small = total <= 0xffffffffull;  // 32-bit division on the common path
+    if (p.obs_out != nullptr) {
+        const V* in = reinterpret_cast<const V*>(p.obs);
+        for (size_t c0 = tid; c0 < total; c0 += nthreads * kU) {
+            V v[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const size_t c = c0 + (size_t)u * nthreads;
+                if (c < total) {
+                    const unsigned b = small ? (unsigned)c / cpr : (unsigned)(c / cpr), off = (unsigned)(c - (size_t)b * cpr);
+                    const size_t src = p.rows ? (size_t)__ldg(p.rows + b) : (size_t)b;
+                    v[u] = __ldcs(in + src * cpr + off);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const size_t c = c0 + (size_t)u * nthreads;
+                if (c < total) {
+                    if constexpr (kF32Out) {  // V is one 4-byte word -> one float4
+                        const uint32_t w = v[u];
+                        __stcs(reinterpret_cast<float4*>(p.obs_out) + c,
+                               make_float4((float)(int8_t)(w & 0xff), (float)(int8_t)((w >> 8) & 0xff),
+                                           (float)(int8_t)((w >> 16) & 0xff), (float)(int8_t)(w >> 24)));
+                    } else {
+                        __stcs(reinterpret_cast<V*>(p.obs_out) + c, v[u]);
+                    }
+                }
+            }
+        }
+    }
+    // scalar fields: one (row, field) pair per thread-iteration, field-major so the stores coalesce
+    const int nf = p.n_f32 + p.n_i32;
+    for (size_t i = tid; i < (size_t)nf * p.B; i += nthreads) {
+        const int f = (int)(i / p.B), b = (int)(i - (size_t)f * p.B);
+        const size_t src = p.rows ? (size_t)__ldg(p.rows + b) : (size_t)b;
+        if (f < p.n_f32) p.out_f32[f][b] = __ldg(p.src_f32[f] + src);
+        else p.out_i32[f - p.n_f32][b] = __ldg(p.src_i32[f - p.n_f32] + src);
+    }
+}
+
+struct LossParams {
+    const int32_t* rows;
+    int B;
+    const float *logp_new, *entropy, *values_new;
+    const float *old_logp, *adv, *value_preds, *returns, *active;
+    float* vn_state;
+    float *imp_weights, *dlogp, *dvalues;
+    double* stats;  // [OCB_PPO_STATS]
+    float clip, delta;
+    int clipped_vl, huber, valuenorm, value_masks, policy_masks;
+    float vn_w, vn_omw, vn_eps;  // beta, 1 - beta (formed in double, narrowed like torch's scalar operands), epsilon
+};
+// scratch slots of stats[]
+enum { S_RET = 8, S_RET2 = 9, S_ACT = 10, S_PL = 11, S_VL = 12, S_ENT = 13, S_RATIO = 14, S_TICKET = 15 };
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    v = (l < (int)(blockDim.x >> 5)) ? sh[l] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// true in exactly one thread of the last block to get here (after its atomics are visible)
+__device__ __forceinline__ bool last_block(double* ticket_slot) {
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long* t = reinterpret_cast<unsigned long long*>(ticket_slot);
+        s_last = atomicAdd(t, 1ull) + 1ull == (unsigned long long)gridDim.x;
+    }
+    __syncthreads();
+    return s_last && threadIdx.x == 0;
+}
+
+// pass 1: batch statistics of the returns (ValueNorm.update, valuenorm.py:43-60) and the active-mask sum;
+// the last block folds them into the running ValueNorm state
+__global__ void __launch_bounds__(256) ppo_stats_kernel(const LossParams p) {
+    __shared__ double sh[8];
+    double s1 = 0.0, s2 = 0.0, sa = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.B; i += gridDim.x * blockDim.x) {
+        const size_t src = p.rows ? (size_t)__ldg(p.rows + i) : (size_t)i;
+        const float r = __ldg(p.returns + src);
+        s1 += (double)r, s2 += (double)__fmul_rn(r, r);
+        sa += p.active ? (double)__ldg(p.active + src) : 1.0;
+    }
+    s1 = block_sum(s1, sh), s2 = block_sum(s2, sh), sa = block_sum(sa, sh);
+    if (threadIdx.x == 0) atomicAdd(p.stats + S_RET, s1), atomicAdd(p.stats + S_RET2, s2), atomicAdd(p.stats + S_ACT, sa);
+    if (last_block(p.stats + S_TICKET)) {
+        const double n = (double)p.B;
+        const double m1 = atomicAdd(p.stats + S_RET, 0.0) / n, m2 = atomicAdd(p.stats + S_RET2, 0.0) / n;
+        p.stats[5] = m1, p.stats[6] = m2, p.stats[7] = n;
+        p.stats[4] = atomicAdd(p.stats + S_ACT, 0.0);
+        if (p.valuenorm && p.vn_state != nullptr) {  // running.mul_(w).add_(batch * (1 - w)), fp32 like torch
+            p.vn_state[0] = __fadd_rn(__fmul_rn(p.vn_state[0], p.vn_w), __fmul_rn((float)m1, p.vn_omw));
+            p.vn_state[1] = __fadd_rn(__fmul_rn(p.vn_state[1], p.vn_w), __fmul_rn((float)m2, p.vn_omw));
+            p.vn_state[2] = __fadd_rn(__fmul_rn(p.vn_state[2], p.vn_w), __fmul_rn(1.0f, p.vn_omw));
+        }
+        *reinterpret_cast<unsigned long long*>(p.stats + S_TICKET) = 0ull;  // pass 2 reuses the ticket
+    }
+}
+
+// huber_loss / mse_loss of train/MAPPO/utils/util.py:46-53 (including its zero branch for e < -d) and d/de
+__device__ __forceinline__ float value_err_loss(float e, float d, int huber, float& de) {
+    if (!huber) {
+        de = e;
+        return __fmul_rn(e, e) * 0.5f;
+    }
+    const float a = fabsf(e) <= d ? 1.0f : 0.0f, b = e > d ? 1.0f : 0.0f;
+    de = a * e + b * d;
+    return a * __fmul_rn(e, e) * 0.5f + b * d * (fabsf(e) - d * 0.5f);
+}
+
+// pass 2: per-row surrogate / value loss / gradients, fp64 block reductions; the last block writes the means
+__global__ void __launch_bounds__(256) ppo_loss_kernel(const LossParams p) {
+    __shared__ double sh[8];
+    float vmean = 0.0f, vstd = 1.0f;
+    if (p.valuenorm && p.vn_state != nullptr) {  // ValueNorm.running_mean_var (valuenorm.py:34-41)
+        const float deb = fmaxf(p.vn_state[2], p.vn_eps);
+        const float m = p.vn_state[0] / deb, msq = p.vn_state[1] / deb;
+        vmean = m, vstd = sqrtf(fmaxf(__fsub_rn(msq, __fmul_rn(m, m)), 1e-2f));
+    }
+    const double sum_act = p.stats[4], nB = (double)p.B;
+    const bool pmask = p.policy_masks && p.active != nullptr, vmask = p.value_masks && p.active != nullptr;
+    const float pden = (float)(pmask ? sum_act : nB), vden = (float)(vmask ? sum_act : nB);
+    const float lo = 1.0f - p.clip, hi = 1.0f + p.clip;
+    double s_pl = 0.0, s_vl = 0.0, s_ent = 0.0, s_ratio = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.B; i += gridDim.x * blockDim.x) {
+        const size_t src = p.rows ? (size_t)__ldg(p.rows + i) : (size_t)i;
+        const float act = p.active ? __ldg(p.active + src) : 1.0f;
+        // ---- actor surrogate (r_mappo.py:110-122)
+        const float ratio = expf(__fsub_rn(p.logp_new[i], __ldg(p.old_logp + src)));
+        const float adv = __ldg(p.adv + src);
+        const float surr1 = __fmul_rn(ratio, adv);
+        const bool inside = ratio >= lo && ratio <= hi;
+        const float surr2 = __fmul_rn(fminf(fmaxf(ratio, lo), hi), adv);
+        const float m = fminf(surr1, surr2);
+        const float pw = pmask ? act : 1.0f;
+        s_pl += (double)(m * pw);
+        s_ent += (double)(p.entropy ? p.entropy[i] * pw : 0.0f);
+        s_ratio += (double)ratio;
+        if (p.imp_weights) p.imp_weights[i] = ratio;
+        if (p.dlogp) {  // torch.min splits the gradient on ties; clamp passes it inside [lo, hi] (bounds included)
+            float g;
+            if (surr1 < surr2) g = surr1;
+            else if (surr1 == surr2) g = 0.5f * surr1 + (inside ? 0.5f * surr1 : 0.0f);
+            else g = 0.0f;
+            p.dlogp[i] = -g * pw / pden;
+        }
+        // ---- critic (cal_value_loss, r_mappo.py:52-89)
+        const float v = p.values_new[i], vp = __ldg(p.value_preds + src);
+        const float dv = __fsub_rn(v, vp);
+        const bool vin = dv >= -p.clip && dv <= p.clip;
+        const float vpc = __fadd_rn(vp, fminf(fmaxf(dv, -p.clip), p.clip));
+        float ret = __ldg(p.returns + src);
+        if (p.valuenorm) ret = __fsub_rn(ret, vmean) / vstd;
+        float de_c, de_o;
+        const float l_c = value_err_loss(__fsub_rn(ret, vpc), p.delta, p.huber, de_c);
+        const float l_o = value_err_loss(__fsub_rn(ret, v), p.delta, p.huber, de_o);
+        float l = l_o, g = -de_o;  // d l / d v
+        if (p.clipped_vl) {
+            const float g_c = vin ? -de_c : 0.0f;
+            if (l_c > l_o) l = l_c, g = g_c;
+            else if (l_c == l_o) g = 0.5f * g + 0.5f * g_c;
+        }
+        const float vw = vmask ? act : 1.0f;
+        s_vl += (double)(l * vw);
+        if (p.dvalues) p.dvalues[i] = g * vw / vden;
+    }
+    s_pl = block_sum(s_pl, sh), s_vl = block_sum(s_vl, sh), s_ent = block_sum(s_ent, sh), s_ratio = block_sum(s_ratio, sh);
+    if (threadIdx.x == 0) {
+        atomicAdd(p.stats + S_PL, s_pl), atomicAdd(p.stats + S_VL, s_vl);
+        atomicAdd(p.stats + S_ENT, s_ent), atomicAdd(p.stats + S_RATIO, s_ratio);
+    }
+    if (last_block(p.stats + S_TICKET)) {
+        p.stats[0] = -atomicAdd(p.stats + S_PL, 0.0) / (pmask ? sum_act : nB);
+        p.stats[1] = atomicAdd(p.stats + S_VL, 0.0) / (vmask ? sum_act : nB);
+        p.stats[2] = atomicAdd(p.stats + S_ENT, 0.0) / (pmask ? sum_act : nB);
+        p.stats[3] = atomicAdd(p.stats + S_RATIO, 0.0) / nB;
+    }
+}
+
+int check_device(int device) {
+    const int ndev = ocb_device_count();
+    if (ndev <= 0) return fail(OCB_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(OCB_ERR_INVALID_ARG, "device %d not in 0..%d", device, ndev - 1);
+    return OCB_OK;
+}
+
+int grid_for(int device, long long threads_needed, int block, int per_sm) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    long long blocks = (threads_needed + block - 1) / block;
+    if (blocks > (long long)sms * per_sm) blocks = (long long)sms * per_sm;
+    return blocks < 1 ? 1 : (int)blocks;
+}
+
+}  // namespace
+
+extern "C" int ocb_minibatch_gather(int device, const int32_t* rows, int B, int obs_bytes_per_agent, const int8_t* obs,
+                                    void* obs_out, int obs_out_f32, int n_f32, const float* const* src_f32,
+                                    float* const* out_f32, int n_i32, const int32_t* const* src_i32,
+                                    int32_t* const* out_i32, void* stream) {
+    if (B < 1) return fail(OCB_ERR_INVALID_ARG, "B must be >= 1");
+    if (n_f32 < 0 || n_f32 > kMaxF32Fields || n_i32 < 0 || n_i32 > kMaxI32Fields)
+        return fail(OCB_ERR_INVALID_ARG, "at most %d float and %d int32 fields", kMaxF32Fields, kMaxI32Fields);
+    if ((n_f32 > 0 && (src_f32 == nullptr || out_f32 == nullptr)) || (n_i32 > 0 && (src_i32 == nullptr || out_i32 == nullptr)))
+        return fail(OCB_ERR_INVALID_ARG, "NULL field table");
+    if (obs_out != nullptr) {
+        if (obs == nullptr || obs_bytes_per_agent < 4 || (obs_bytes_per_agent & 3) != 0)
+            return fail(OCB_ERR_INVALID_ARG, "obs rows must be a positive multiple of 4 bytes");
+        if ((reinterpret_cast<uintptr_t>(obs) & 3u) != 0 || (reinterpret_cast<uintptr_t>(obs_out) & (obs_out_f32 ? 15u : 3u)) != 0)
+            return fail(OCB_ERR_INVALID_ARG, "obs must be 4-byte aligned (obs_out 16-byte aligned for fp32 output)");
+    }
+    int rc = check_device(device);
+    if (rc != OCB_OK) return rc;
+    DeviceGuard guard(device);
+    GatherParams p;
+    memset(&p, 0, sizeof(p));
+    p.rows = rows, p.B = B, p.words = obs_bytes_per_agent >> 2;
+    p.obs = reinterpret_cast<const uint32_t*>(obs), p.obs_out = obs_out, p.obs_out_f32 = obs_out_f32;
+    p.n_f32 = n_f32, p.n_i32 = n_i32;
+    for (int i = 0; i < n_f32; ++i) {
+        if (src_f32[i] == nullptr || out_f32[i] == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL float field %d", i);
+        p.src_f32[i] = src_f32[i], p.out_f32[i] = out_f32[i];
+    }
+    for (int i = 0; i < n_i32; ++i) {
+        if (src_i32[i] == nullptr || out_i32[i] == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL int32 field %d", i);
+        p.src_i32[i] = src_i32[i], p.out_i32[i] = out_i32[i];
+    }
+    const int grid = grid_for(device, (long long)B * p.words, 256, 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool vec16 = !obs_out_f32 && (obs_bytes_per_agent & 15) == 0 && obs_out != nullptr &&
+                       ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(obs_out)) & 15u) == 0;
+    if (obs_out_f32) minibatch_gather_kernel<uint32_t, 8, true><<<grid, 256, 0, s>>>(p);
+    else if (vec16) minibatch_gather_kernel<uint4, 4, false><<<grid, 256, 0, s>>>(p);
+    else minibatch_gather_kernel<uint32_t, 8, false><<<grid, 256, 0, s>>>(p);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "gather kernel launch failed: %s", cudaGetErrorString(err));
+    return OCB_OK;
+}
+
+extern "C" int ocb_ppo_loss(int device, const ocb_ppo_cfg* cfg, int B, const int32_t* rows, const float* logp_new,
+                            const float* entropy, const float* values_new, const float* old_logp_src, const float* adv_src,
+                            const float* value_preds_src, const float* returns_src, const float* active_src,
+                            float* vn_state, float* imp_weights, float* dlogp, float* dvalues, double* stats, void* stream) {
+    if (cfg == nullptr || logp_new == nullptr || values_new == nullptr || old_logp_src == nullptr || adv_src == nullptr ||
+        value_preds_src == nullptr || returns_src == nullptr || stats == nullptr)
+        return fail(OCB_ERR_INVALID_ARG, "NULL argument");
+    if (cfg->struct_size != sizeof(ocb_ppo_cfg)) return fail(OCB_ERR_INVALID_ARG, "ocb_ppo_cfg ABI mismatch");
+    if (B < 1) return fail(OCB_ERR_INVALID_ARG, "B must be >= 1");
+    if (cfg->use_valuenorm && vn_state == nullptr) return fail(OCB_ERR_INVALID_ARG, "use_valuenorm needs vn_state");
+    int rc = check_device(device);
+    if (rc != OCB_OK) return rc;
+    DeviceGuard guard(device);
+    LossParams p;
+    memset(&p, 0, sizeof(p));
+    p.rows = rows, p.B = B, p.logp_new = logp_new, p.entropy = entropy, p.values_new = values_new;
+    p.old_logp = old_logp_src, p.adv = adv_src, p.value_preds = value_preds_src, p.returns = returns_src, p.active = active_src;
+    p.vn_state = vn_state, p.imp_weights = imp_weights, p.dlogp = dlogp, p.dvalues = dvalues, p.stats = stats;
+    p.clip = cfg->clip_param, p.delta = cfg->huber_delta;
+    p.clipped_vl = cfg->use_clipped_value_loss, p.huber = cfg->use_huber_loss, p.valuenorm = cfg->use_valuenorm;
+    p.value_masks = cfg->use_value_active_masks, p.policy_masks = cfg->use_policy_active_masks;
+    p.vn_w = (float)cfg->vn_beta, p.vn_omw = (float)(1.0 - cfg->vn_beta), p.vn_eps = (float)cfg->vn_epsilon;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t err = cudaMemsetAsync(stats, 0, OCB_PPO_STATS * sizeof(double), s);
+    if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "ocb_ppo_loss: %s", cudaGetErrorString(err));
+    const int grid = grid_for(device, B, 256, 4);
+    ppo_stats_kernel<<<grid, 256, 0, s>>>(p);
+    ppo_loss_kernel<<<grid, 256, 0, s>>>(p);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "ppo loss launch failed: %s", cudaGetErrorString(err));
     return OCB_OK;
 }

@@ -209,3 +209,23 @@ class FusedPolicy:
             self._native.check(self._lib.ocb_policy_value(self._h, self._p(obs), M, self._p(tile_policy), self._p(out),
                                                           self._stream()))
         return out
+
+    def evaluate(self, obs, actions_src, rows=None, tile_policy=None, with_critic=True, want_logits=False, out=None):
+        """evaluate_actions (R_Actor.evaluate_actions r_actor_critic.py:73-109 + R_Critic.forward) over rows picked
+        out of ``obs`` in place (``ocb_policy_evaluate``): obs int8 ``[..., W, H, C]`` (e.g. the whole rollout
+        buffer), ``actions_src`` int32 indexed like obs rows, ``rows`` int32 ``[B]`` source-row indices (None =
+        every row in order) -> dict(logp [B], entropy [B], values [B]|None, logits [B,6]|None)."""
+        R = self._rows(obs)
+        if rows is not None:
+            assert rows.dtype == torch.int32 and rows.is_cuda and rows.is_contiguous()
+        B = R if rows is None else rows.numel()
+        assert actions_src.dtype == torch.int32 and actions_src.is_cuda and actions_src.is_contiguous()
+        if out is None:
+            f = lambda *s: torch.empty(s, dtype=torch.float32, device=self.device)
+            out = {"logp": f(B), "entropy": f(B), "values": f(B) if with_critic else None,
+                   "logits": f(B, NUM_ACTIONS) if want_logits else None}
+        with torch.cuda.device(self.device):
+            self._native.check(self._lib.ocb_policy_evaluate(
+                self._h, self._p(obs), self._p(rows), B, self._p(tile_policy), self._p(actions_src), self._p(out["logp"]),
+                self._p(out["entropy"]), self._p(out.get("logits")), self._p(out.get("values")), self._stream()))
+        return out

@@ -180,7 +180,7 @@ int ocb_set_world_offset(ocb_env* env, uint32_t world0);
 /* Fused tensor-core forward of the reference's CNN actor / critic (R_Actor / R_Critic,
  * train/MAPPO/r_actor_critic.py:12-71,142-197; CNNLayer train/MAPPO/utils/cnn.py:22-42;
  * Categorical head train/MAPPO/utils/distributions.py:55-68), 2 players, hidden_size 64 (every
- * train/*.sh; one fused kernel) or 512 (argparse default train/config.py:199; three GEMM-sized
+ * train script; one fused kernel) or 512 (argparse default train/config.py:199; three GEMM-sized
  * launches).  Shapes below are for hidden h: conv_w [h/2,20,3,3], fc1_w [h, (h/2)(W-2)(H-2)],
  * fc2_w [h,h], head_w [6|1, h].
  * A handle holds n_policies (actor, critic) weight sets for one layout. */
@@ -285,6 +285,65 @@ int ocb_compute_returns(int device, const ocb_returns_cfg* cfg, int T, int P, in
                         double* adv_stats, void* stream);
 /* advantages <- (advantages - mean) / (std + 1e-5), unbiased std, from adv_stats (r_mappo.py:180-182) */
 int ocb_normalize_advantages(int device, float* advantages, size_t n, const double* adv_stats, void* stream);
+
+/* ------------------------------------------------------- PPO minibatch: gather, evaluate_actions, loss */
+/* The data side of R_MAPPO.ppo_update (train/MAPPO/r_mappo.py:91-164) over the seat-major rollout
+ * buffer, consuming the int8 observations in place.  A minibatch is a list of agent-row indices
+ * `rows` (int32 [B], DEVICE): row = (t*P + seat)*N + world addresses obs_slab[:T], actions, logp,
+ * value_preds[:T], returns[:T] and advantages alike.  (The reference flattens [T,N,P] instead,
+ * shared_buffer.py:306-366; the host adapter converts its randperm indices.) */
+
+/* evaluate_actions (R_Actor.evaluate_actions r_actor_critic.py:73-109, ACTLayer.evaluate_actions
+ * utils/act.py:107-175 Discrete branch, R_Critic.forward 178-197): the tensor-core forward of
+ * ocb_policy_forward over obs rows picked by `rows` (NULL = rows 0..B-1), with the log-probability
+ * of the STORED action actions_src[row] and the entropy of the distribution per row instead of
+ * sampling.  obs [R,W,H,C] int8, actions_src int32 [R] (both indexed by source row); outputs are
+ * indexed by minibatch position: logp [B], entropy [B], logits [B,6] (may be NULL), values [B]
+ * (NULL = actor only).  hidden 64 and 512. */
+int ocb_policy_evaluate(ocb_policy* pol, const int8_t* obs, const int32_t* rows, int B, const int32_t* tile_policy,
+                        const int32_t* actions_src, float* logp, float* entropy, float* logits, float* values,
+                        void* stream);
+
+/* feed_forward_generator's fancy-indexing (shared_buffer.py:339-361) as one launch: copies the B
+ * picked rows of every non-NULL source into dense minibatch tensors (for callers that want
+ * materialised batches, e.g. the reference's own ppo_update).  obs rows are obs_bytes_per_agent
+ * bytes; obs_out is int8 [B,W,H,C] when obs_out_f32 == 0, else float [B,W,H,C] (the reference's
+ * dtype).  f32 sources/outputs: n_f32 <= 8 pairs (src_f32[i] [R] -> out_f32[i] [B], HOST arrays of
+ * DEVICE pointers); int32 likewise (n_i32 <= 4, e.g. actions).  rows == NULL copies rows 0..B-1.  HBM-bound: 2*S*C (or 5*S*C with fp32 output) + 8 bytes per scalar field per row. */
+int ocb_minibatch_gather(int device, const int32_t* rows, int B, int obs_bytes_per_agent, const int8_t* obs,
+                         void* obs_out, int obs_out_f32, int n_f32, const float* const* src_f32, float* const* out_f32,
+                         int n_i32, const int32_t* const* src_i32, int32_t* const* out_i32, void* stream);
+
+typedef struct ocb_ppo_cfg {
+    uint32_t struct_size;            /* sizeof(ocb_ppo_cfg) */
+    int32_t use_clipped_value_loss;  /* config.py use_clipped_value_loss, default 1 */
+    int32_t use_huber_loss;          /* default 1 */
+    int32_t use_valuenorm;           /* default 1: ValueNorm.update(return_batch) then normalize (r_mappo.py:61-64) */
+    int32_t use_value_active_masks;  /* default 1 (only matters with active_src) */
+    int32_t use_policy_active_masks; /* default 1 (only matters with active_src) */
+    float clip_param;                /* default 0.2 */
+    float huber_delta;               /* default 10.0 */
+    double vn_beta;                  /* ValueNorm beta, 0.99999 (valuenorm.py:11); double: the reference forms 1 - beta in Python */
+    double vn_epsilon;               /* ValueNorm epsilon, 1e-5 */
+} ocb_ppo_cfg;
+#define OCB_PPO_STATS 16
+/* cal_value_loss + the surrogate of ppo_update (r_mappo.py:52-89, 110-127): the forward losses and
+ * the analytic gradients a backward pass starts from.  Inputs by minibatch position: logp_new,
+ * entropy, values_new [B] (ocb_policy_evaluate's outputs).  Inputs by source row through `rows`
+ * (NULL = identity): old_logp_src, adv_src, value_preds_src, returns_src, active_src (NULL = all
+ * active; the *_active_masks options then reduce to plain means).  vn_state: DEVICE float[3] =
+ * ValueNorm (running_mean, running_mean_sq, debiasing_term), UPDATED in place with this batch's
+ * returns before normalising, as the reference does (ignored when use_valuenorm == 0).
+ * Outputs (DEVICE; the first three may be NULL): imp_weights [B]; dlogp [B] = d policy_loss /
+ * d logp_new; dvalues [B] = d value_loss / d values_new (torch.autograd's tie conventions);
+ * stats double[OCB_PPO_STATS]: [0] policy_loss, [1] value_loss, [2] dist_entropy, [3] mean
+ * imp_weight, [4] sum of active masks, [5] batch return mean, [6] batch return sq-mean, [7] B;
+ * [8..15] scratch.  Per-element arithmetic in fp32 like torch, reductions in fp64.  One memset
+ * and two launches, no host synchronisation. */
+int ocb_ppo_loss(int device, const ocb_ppo_cfg* cfg, int B, const int32_t* rows, const float* logp_new,
+                 const float* entropy, const float* values_new, const float* old_logp_src, const float* adv_src,
+                 const float* value_preds_src, const float* returns_src, const float* active_src, float* vn_state,
+                 float* imp_weights, float* dlogp, float* dvalues, double* stats, void* stream);
 
 /* ------------------------------------------------------- Balance-Beam */
 /* replaces BalanceBeamSimulator (src/balance_beam_env/mgr.cpp:191-233) behind

@@ -275,3 +275,25 @@ def test_actor_only_rollout_and_argument_checks():
     other = FusedPolicy(layouts.load_layout("random1", 400), 64, 1)
     with pytest.raises(ValueError):
         PolicyRollout(env, other, 5)
+
+
+def test_destroying_handles_during_a_capture_keeps_the_graph_valid():
+    """handles may be garbage-collected while another rollout is being captured (cudaFree is not capturable in
+    global mode): the destroy entry points switch the thread to relaxed capture mode for their frees"""
+    lp = layouts.load_layout("simple", 400)
+    pol, _, _ = make_policies(lp, 1)
+    env = B200Overcooked("simple", 256, 0, horizon=400, seed=4)
+    ro = PolicyRollout(env, pol, 6, seed=1)
+    ro.prime()
+    victims = [B200Overcooked("simple", 64, 0, horizon=400, seed=1), make_policies(lp, 1)[0]]
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ro._issue(False)
+        for v in victims:
+            v.close()
+    g.replay()
+    torch.cuda.synchronize()
+    orc = COracle(lp, 256)
+    o, r, d = orc.rollout(ro.buf.actions.cpu().numpy().astype(np.uint8))
+    assert np.array_equal(ro.buf.obs[1:].cpu().numpy(), o) and np.array_equal(ro.buf.rewards.cpu().numpy(), r)
