@@ -13,6 +13,7 @@
 #include "oc_kernels.h"
 #include "oc_tables.h"
 #include "policy_internal.h"
+#include "mixed_internal.h"
 #include "ocb.h"
 
 using namespace ocb;
@@ -485,4 +486,116 @@ extern "C" int ocb_rollout_policy_fused(ocb_env* e, ocb_policy* pol, int T, int 
     if (rc != OCB_OK) return rc;
     e->step_count += (uint64_t)T;
     return OCB_OK;
+}
+
+// ------------------------------------------------------------------ mixed-play collection
+// scratch layout: two ping-pong observations [P,N,SC] | a_main, a_partner, act [P,N] i32 | logp, v [P,N] f32 |
+// reward [P,N] i32 | done [N] i32 | two constant tile tables
+namespace {
+struct MixScratch {
+    int8_t* obs[2];
+    int32_t *a_main, *a_partner, *act, *rew, *done, *tiles_main, *tiles_partner;
+    float *logp, *v;
+    size_t bytes;
+    int n_tiles;
+};
+MixScratch mix_scratch(const ocb_env* e, void* base) {
+    MixScratch m;
+    const size_t PN = (size_t)e->P * e->N;
+    char* b = static_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* r = b ? b + off : nullptr;
+        off += (bytes + 255) & ~(size_t)255;
+        return r;
+    };
+    m.obs[0] = reinterpret_cast<int8_t*>(take(PN * e->SC));
+    m.obs[1] = reinterpret_cast<int8_t*>(take(PN * e->SC));
+    m.a_main = reinterpret_cast<int32_t*>(take(PN * 4));
+    m.a_partner = reinterpret_cast<int32_t*>(take(PN * 4));
+    m.act = reinterpret_cast<int32_t*>(take(PN * 4));
+    m.logp = reinterpret_cast<float*>(take(PN * 4));
+    m.v = reinterpret_cast<float*>(take(PN * 4));
+    m.rew = reinterpret_cast<int32_t*>(take(PN * 4));
+    m.done = reinterpret_cast<int32_t*>(take((size_t)e->N * 4));
+    m.n_tiles = (int)((PN + 127) / 128);
+    m.tiles_main = reinterpret_cast<int32_t*>(take((size_t)m.n_tiles * 4));
+    m.tiles_partner = reinterpret_cast<int32_t*>(take((size_t)m.n_tiles * 4));
+    m.bytes = off;
+    return m;
+}
+}  // namespace
+
+extern "C" size_t ocb_rollout_mixed_scratch_bytes(const ocb_env* e) { return e ? mix_scratch(e, nullptr).bytes : 0; }
+
+// 2L x { main actor+critic forward, partner actor forward, per-row select, env step, record of the forced
+// worlds } + the value of the never-written slot L; every launch on `stream`, nothing synchronises,
+// graph-capturable (the mask stream and the sampling offsets read the device-side step counter).
+extern "C" int ocb_rollout_mixed(ocb_env* e, ocb_policy* pol, int L, int main_policy, int partner_policy, int8_t* obs_buf,
+                                 int32_t* actions, float* logp, float* values, int32_t* reward, int32_t* done,
+                                 int deterministic, uint64_t seed, uint64_t mix_seed, void* scratch, size_t scratch_bytes,
+                                 void* stream) {
+    if (e == nullptr || pol == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL handle");
+    if (obs_buf == nullptr || actions == nullptr) return fail(OCB_ERR_INVALID_ARG, "obs_buf and actions are required");
+    if (e->P != 2) return fail(OCB_ERR_UNSUPPORTED, "the policy rollout supports 2 players");
+    if (L < 2) return fail(OCB_ERR_INVALID_ARG, "L must be >= 2");
+    if (e->N % (L - 1) != 0)
+        return fail(OCB_ERR_INVALID_ARG, "the env must hold a multiple of L - 1 = %d worlds (got %d)", L - 1, e->N);
+    const int sets = ocb_policy_num_sets(pol);
+    if (main_policy < 0 || main_policy >= sets || partner_policy < 0 || partner_policy >= sets)
+        return fail(OCB_ERR_INVALID_ARG, "policy index out of range (the handle holds %d sets)", sets);
+    const MixScratch m = mix_scratch(e, scratch);
+    if (scratch == nullptr || scratch_bytes < m.bytes)
+        return fail(OCB_ERR_INVALID_ARG, "scratch must hold ocb_rollout_mixed_scratch_bytes() = %zu bytes", m.bytes);
+    if ((reinterpret_cast<uintptr_t>(scratch) & 255u) != 0) return fail(OCB_ERR_INVALID_ARG, "scratch must be 256-byte aligned");
+    DeviceGuard guard(e->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t PN = (size_t)e->P * e->N, obs_step = PN * (size_t)e->SC;
+    const int M = (int)PN;
+    const uint64_t* ctr = reinterpret_cast<const uint64_t*>(e->d_step_counter);
+#define OCB_CU(call)                                                             \
+    do {                                                                         \
+        cudaError_t err__ = (call);                                              \
+        if (err__ != cudaSuccess) {                                              \
+            cudaGetLastError();                                                  \
+            return fail(OCB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(err__)); \
+        }                                                                        \
+    } while (0)
+    OCB_CU(launch_fill2_i32(m.tiles_main, m.n_tiles, main_policy, m.tiles_partner, m.n_tiles, partner_policy, st));
+    int rc = ocb_observe(e, m.obs[0], stream);
+    if (rc != OCB_OK) return rc;
+    // the partner samples from its own stream (same counters, different key)
+    const uint64_t partner_seed = seed ^ 0x9E3779B97F4A7C15ull;
+    for (int s = 0; s < 2 * L; ++s) {
+        const int8_t* cur = m.obs[s & 1];
+        rc = values ? ocb_policy_forward(pol, cur, M, m.tiles_main, m.a_main, m.logp, nullptr, m.v, deterministic, seed, 0,
+                                         ctr, stream)
+                    : ocb_policy_act_ex(pol, cur, M, m.tiles_main, m.a_main, m.logp, nullptr, deterministic, seed, 0, ctr,
+                                        stream);
+        if (rc != OCB_OK) return rc;
+        rc = ocb_policy_act_ex(pol, cur, M, m.tiles_partner, m.a_partner, nullptr, nullptr, deterministic, partner_seed, 0,
+                               ctr, stream);
+        if (rc != OCB_OK) return rc;
+        MixSelectParams sp;
+        sp.a_main = m.a_main, sp.a_partner = m.a_partner, sp.act = m.act;
+        sp.step_counter = e->d_step_counter, sp.mix_seed = mix_seed;
+        sp.P = e->P, sp.N = e->N, sp.L = L, sp.s = s;
+        OCB_CU(launch_mix_select(sp, st));
+        rc = ocb_step(e, m.act, m.obs[(s + 1) & 1], m.rew, m.done, stream);
+        if (rc != OCB_OK) return rc;
+        MixRecordParams rp;
+        rp.obs_cur = cur, rp.a_main = m.a_main, rp.logp_main = m.logp, rp.v_main = m.v, rp.rew_cur = m.rew,
+        rp.done_cur = m.done;
+        rp.obs_buf = obs_buf, rp.actions = actions, rp.logp = logp, rp.values = values, rp.reward = reward, rp.done = done;
+        rp.P = e->P, rp.N = e->N, rp.SC = e->SC, rp.L = L, rp.s = s;
+        OCB_CU(launch_mix_record(rp, st));
+    }
+    // slot L is never written by the collection (diaginsert / partinsert stop at L-1): the reference bootstraps from
+    // the all-zero observation the buffer was created with (MainPlayer.compute_one on mp_buf.share_obs[-1]); the
+    // critic's value of it is a constant of the weights (the tensor-core forward folds the terrain planes of real
+    // observations into its bias, so it is evaluated on the host when the weights are set)
+    OCB_CU(cudaMemsetAsync(obs_buf + (size_t)L * obs_step, 0, obs_step, st));
+    if (values != nullptr) OCB_CU(launch_fill_f32(values + (size_t)L * PN, PN, ocb_policy_zero_obs_value(pol, main_policy), st));
+    return OCB_OK;
+#undef OCB_CU
 }

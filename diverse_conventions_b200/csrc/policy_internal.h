@@ -12,3 +12,8 @@ int ocb_policy_rollout_fused_launch(ocb_policy* pol, int policy_index, const ocb
                                     int8_t* obs_slab, int32_t* actions, float* logp, float* values, int32_t* reward,
                                     int32_t* done, int deterministic, uint64_t seed, const uint64_t* d_offset,
                                     uint64_t* d_counter, void* stream);
+
+// number of (actor, critic) weight sets the handle holds
+int ocb_policy_num_sets(const ocb_policy* pol);
+// R_Critic value of the all-zero observation under weight set `policy` (computed on the host at set_weights)
+float ocb_policy_zero_obs_value(const ocb_policy* pol, int policy);

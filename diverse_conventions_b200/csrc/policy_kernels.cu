@@ -1178,6 +1178,9 @@ struct ocb_policy {
     Blob5 L5;
     uint8_t* d_scratch;
     size_t scratch_tiles;
+    // critic value of the all-zero observation per weight set (a constant of the weights; the mixed-play buffer
+    // bootstraps from the never-written slot L, which holds zeros in the reference)
+    std::vector<float> zero_value;
 };
 
 extern "C" int ocb_policy_destroy(ocb_policy* p) {
@@ -1188,6 +1191,32 @@ extern "C" int ocb_policy_destroy(ocb_policy* p) {
     cudaFree(p->d_blobs);
     delete p;
     return OCB_OK;
+}
+
+int ocb_policy_num_sets(const ocb_policy* p) { return p ? p->n_policies : 0; }
+float ocb_policy_zero_obs_value(const ocb_policy* p, int policy) {
+    return (p && policy >= 0 && policy < (int)p->zero_value.size()) ? p->zero_value[policy] : 0.0f;
+}
+
+// R_Critic.forward on an all-zero observation, fp32 on the host: the conv output is its bias at every position
+// (flatten index co*npos + pos, cnn.py:41), then FC -> ReLU -> FC -> ReLU -> v_out
+static float zero_obs_value(int hidden, int npos, const float* conv_b, const float* fc1_w, const float* fc1_b,
+                            const float* fc2_w, const float* fc2_b, const float* head_w, const float* head_b) {
+    const int co_n = hidden / 2, k1 = co_n * npos;
+    std::vector<float> x1((size_t)hidden), x2((size_t)hidden);
+    for (int o = 0; o < hidden; ++o) {
+        float acc = fc1_b[o];
+        for (int k = 0; k < k1; ++k) acc += fc1_w[(size_t)o * k1 + k] * fmaxf(conv_b[k / npos], 0.0f);
+        x1[o] = fmaxf(acc, 0.0f);
+    }
+    for (int o = 0; o < hidden; ++o) {
+        float acc = fc2_b[o];
+        for (int k = 0; k < hidden; ++k) acc += fc2_w[(size_t)o * hidden + k] * x1[k];
+        x2[o] = fmaxf(acc, 0.0f);
+    }
+    float v = head_b[0];
+    for (int k = 0; k < hidden; ++k) v += head_w[k] * x2[k];
+    return v;
 }
 
 extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, int n_policies, ocb_policy** out) {
@@ -1386,6 +1415,10 @@ extern "C" int ocb_policy_set_weights(ocb_policy* p, int policy, int net, const 
     if (p == nullptr || !conv_w || !conv_b || !fc1_w || !fc1_b || !fc2_w || !fc2_b || !head_w || !head_b)
         return fail(OCB_ERR_INVALID_ARG, "NULL argument");
     if (policy < 0 || policy >= p->n_policies || net < 0 || net > 1) return fail(OCB_ERR_INVALID_ARG, "bad policy / net index");
+    if (net == 1) {
+        p->zero_value.resize((size_t)p->n_policies, 0.0f);
+        p->zero_value[policy] = zero_obs_value(p->hidden, p->npos, conv_b, fc1_w, fc1_b, fc2_w, fc2_b, head_w, head_b);
+    }
     if (p->hidden == kH5) return set_weights512(p, policy, net, conv_w, conv_b, fc1_w, fc1_b, fc2_w, fc2_b, head_w, head_b);
     const BlobLayout& L = p->L;
     std::vector<uint8_t> blob((size_t)L.total, 0);

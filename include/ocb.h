@@ -260,6 +260,31 @@ int ocb_rollout_policy_fused(ocb_env* env, ocb_policy* pol, int T, int policy_in
                              float* logp, float* values, int32_t* reward, int32_t* done, int deterministic,
                              uint64_t seed, void* stream);
 
+/* ------------------------------------------------------- mixed-play ("MP") collection */
+/* XDPlayer.collect_mp_episode / next_mp_step (train/XD/xd_player.py:232-356) with the partner seat of
+ * MixedAgent (train/partner_agents.py:151-244) and the buffer placement of SharedReplayBuffer.diaginsert /
+ * partinsert (train/MAPPO/utils/shared_buffer.py:150-220), L = the trainer's episode_length:
+ * the env holds R replicas of G = L - 1 worlds (N = R*G; the reference runs R = 1, train/XD/serial.py:29) and is
+ * stepped 2L times from its current state.  At step s every agent row draws use_partner = (Philox4x32-10(counter =
+ * (row, step_lo, step_hi, "MIXE"), key = mix_seed).x < 2^31), row = seat*N + world, step = the env's global
+ * step count, unless world j = world mod G is FORCED to the main policy: s < L: j >= G - s (s > 0);
+ * s >= L: j < s - L.  The row plays the partner_policy actor's action when use_partner, else the
+ * main_policy actor's.  Exactly the forced worlds are recorded, all fields at the same slot t
+ * (s < L: t = j - G + s, the diagonal of diaginsert; s >= L: t = s - L, the row prefix of partinsert):
+ * obs_buf [L+1,P,N,W,H,C] int8 <- the observation acted on, actions [L,P,N] int32, logp [L,P,N] f32 and
+ * values [L+1,P,N] f32 of the main policy (actor, critic = the handle's weight set main_policy; the reference
+ * pairs the trained actor with mp_critic, train/XD/MCPolicy.py:21,60), reward [L,P,N] int32 and done [L,N] int32
+ * of that step (the reference stores masks = 1 - done at slot t here, not t + 1).  Every (t < L, seat, world)
+ * cell is written exactly once.  Slot L is what the reference leaves it: obs_buf[L] = 0 and values[L] = the
+ * critic's value of the all-zero observation (MainPlayer.compute_one on the never-written share_obs[-1]).
+ * logp, values, reward, done may be NULL.  `scratch` (DEVICE, 256-byte aligned, at least
+ * ocb_rollout_mixed_scratch_bytes(env) bytes) holds the per-step turn data.  10L + 4 launches on `stream`, no
+ * synchronisation, CUDA-graph capturable (masks and sampling offsets read the device-side step counter). */
+size_t ocb_rollout_mixed_scratch_bytes(const ocb_env* env);
+int ocb_rollout_mixed(ocb_env* env, ocb_policy* pol, int L, int main_policy, int partner_policy, int8_t* obs_buf,
+                      int32_t* actions, float* logp, float* values, int32_t* reward, int32_t* done, int deterministic,
+                      uint64_t seed, uint64_t mix_seed, void* scratch, size_t scratch_bytes, void* stream);
+
 /* ------------------------------------------------------- returns / GAE over the rollout buffer */
 /* SharedReplayBuffer.compute_returns (train/MAPPO/utils/shared_buffer.py:248-304) with the
  * ValueNorm de-normalisation (train/MAPPO/utils/valuenorm.py:76-87) and the advantage

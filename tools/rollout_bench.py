@@ -7,6 +7,8 @@ or one rank per GPU under torchrun.
 
 selfplay : MAPPO self-play rollout (actor + critic forward of both seats, sampling, env step,
            PPO buffer write), random-init networks, hidden 64.
+mixed    : CoMeDi mixed-play collection (ocb_rollout_mixed): 2L env steps of replicas * (L-1) worlds, main policy
+           actor + critic and partner actor forward per step, per-row switch, diagonal / prefix buffer placement.
 crossplay: n x n pair matrix on coordination_ring, pairs sharded over the ranks, actors only,
            one 400-step episode per world, matrix gathered with one collective.
 Prints one JSON line per configuration (rank 0)."""
@@ -44,7 +46,7 @@ def timed(fn, iters, world, dev):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--mode", default="selfplay", choices=["selfplay", "crossplay"])
+    ap.add_argument("--mode", default="selfplay", choices=["selfplay", "crossplay", "mixed"])
     ap.add_argument("--layouts", default="simple,unident_s,random1,random0,random3")
     ap.add_argument("--worlds", type=int, default=8192)
     ap.add_argument("--T", type=int, default=100)
@@ -53,6 +55,8 @@ def main():
     ap.add_argument("--policies", type=int, default=16)
     ap.add_argument("--worlds-per-pair", type=int, default=1024)
     ap.add_argument("--hidden", type=int, default=64, choices=[64, 512])
+    ap.add_argument("--L", type=int, default=400, help="mixed: episode_length of the trainer")
+    ap.add_argument("--replicas", type=int, default=20, help="mixed: copies of the (L-1)-world scheme per GPU")
     ap.add_argument("--fused", type=int, default=-1, help="1: one persistent launch per rollout, 0: 2T+1 launches, -1: auto")
     args = ap.parse_args()
 
@@ -85,6 +89,30 @@ def main():
                                   "buffer_mb": round(ro.buf.nbytes() / 2**20, 1),
                                   "episodes": int(ep), "mean_return": (float(rs) / int(ep)) if int(ep) else None}),
                       flush=True)
+            env.close()
+            pol.close()
+    elif args.mode == "mixed":
+        from diverse_conventions_b200.mixed import MixedPlayCollector  # noqa: E402
+        for layout in args.layouts.split(","):
+            lp = layouts.load_layout(layout, 400)
+            pol = FusedPolicy(lp, args.hidden, 2, gpu_id=local)
+            for i in range(2):
+                pol.set_weights(i, PolicyNet("actor", lp.width, lp.height, lp.channels, args.hidden).init_like_reference(1 + 100 * i),
+                                PolicyNet("critic", lp.width, lp.height, lp.channels, args.hidden).init_like_reference(2 + 100 * i))
+            N = args.replicas * (args.L - 1)
+            env = B200Overcooked(layout, N, local, horizon=400, seed=1, world_offset=rank * N)
+            col = MixedPlayCollector(env, pol, args.L, 0, 1, seed=1, mix_seed=7 + rank, use_graph=bool(args.graph))
+            col.collect()
+            col.collect()
+            ms = timed(col.collect, args.iters, world, dev)
+            if rank == 0:
+                env_agent_steps = 2 * N * world * 2 * args.L
+                print(json.dumps({"mode": "mixed", "layout": layout, "hidden": args.hidden, "n_gpus": world, "L": args.L,
+                                  "replicas_per_gpu": args.replicas, "worlds_per_gpu": N, "graph": bool(args.graph),
+                                  "ms_per_collection": round(ms, 4), "us_per_env_step": round(1e3 * ms / (2 * args.L), 3),
+                                  "agent_steps_per_s": round(env_agent_steps / (ms * 1e-3)),
+                                  "recorded_agent_steps_per_s": round(env_agent_steps / 2 / (ms * 1e-3)),
+                                  "launches_per_collection": 10 * args.L + 4}), flush=True)
             env.close()
             pol.close()
     else:
