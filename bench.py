@@ -128,6 +128,26 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def bind_to_gpu_local_cores(gpu_index):
+    """Pin this rank to the host cores NVML reports as local to its GPU, so that the pinned e2e buffers (first-touch
+    placement) and the copy-issuing thread sit on the GPU's NUMA node.  Best effort: returns the core count used or
+    None when NVML / the cpuset give nothing usable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        allowed = os.sched_getaffinity(0)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(allowed | {os.cpu_count() or 1}) + 64) // 64)
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus = local & allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -280,6 +300,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    numa_cores = bind_to_gpu_local_cores(local) if world > 1 else None
 
     N, K, W, spl = args.worlds, args.steps, args.warmup, args.env_steps_per_pass
     lp = layouts.load_layout(args.layout, HORIZON)
@@ -385,7 +406,7 @@ def run_ours(args):
                              "launch_ms": launch_ms, "peak_source": peak_src},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "call": "ocb_step_host (1 launch / step, obs+reward+done to pinned host memory)",
-                        "calls": E, "value_without_obs_d2h_rank0": e2e_noobs},
+                        "calls": E, "value_without_obs_d2h_rank0": e2e_noobs, "gpu_local_cores_rank0": numa_cores},
                 "policy_rollout": policy_leg,
                 "gpu_launches": launches, "clocks": clocks,
                 "env_steps": K * spl, "us_per_env_step": 1e3 * ms_total / (K * spl)}

@@ -99,9 +99,9 @@ def gather_minibatch(buf: RolloutBuffer, rows: torch.Tensor, advantages: torch.T
             FA(*[t.data_ptr() for t in f32_src]), FA(*[t.data_ptr() for t in f32_out]), 1, IA(buf.actions.data_ptr()),
             IA(actions_out.data_ptr()), _stream(dev)))
     batch = dict(zip(names, f32_out))
+    one = torch.ones((1, 1), dtype=torch.float32, device=dev)  # all agents active, all actions available: broadcast views
     batch.update(obs_batch=obs_out, share_obs_batch=obs_out, actions_batch=actions_out,
-                 masks_batch=None, active_masks_batch=torch.ones((B, 1), dtype=torch.float32, device=dev),
-                 available_actions_batch=torch.ones((B, 6), dtype=torch.float32, device=dev))
+                 masks_batch=None, active_masks_batch=one.expand(B, 1), available_actions_batch=one.expand(B, 6))
     return batch
 
 

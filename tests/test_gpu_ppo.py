@@ -63,10 +63,14 @@ def test_gather_matches_the_generators_minibatch(obs_dtype):
         assert np.array_equal(mb[k].cpu().numpy(), G["mb0_" + k]), k
 
 
-def test_gather_large_ragged_against_torch_indexing():
+@pytest.mark.parametrize("W,H,R,B", [(5, 5, 50_000, 33_333),   # 500-byte rows: 4-byte but not 16-byte multiples
+                                     (9, 5, 30_001, 20_002),   # 900 bytes (asymmetric_advantages), B % 4 == 2
+                                     (5, 4, 40_000, 10_003),   # 400 bytes: 16-byte multiples
+                                     (16, 16, 3_001, 2_047),   # 5,120 bytes: the largest grid the env accepts
+                                     (3, 3, 1_000, 3)])        # 180 bytes, fewer rows than one group
+def test_gather_large_ragged_against_torch_indexing(W, H, R, B):
     g = torch.Generator(device="cuda").manual_seed(0)
-    R, SC, B = 50_000, 500, 33_333  # 5x5x20 rows: 4-byte but not 16-byte aligned
-    obs = torch.randint(-3, 21, (R, 5, 5, 20), dtype=torch.int8, device="cuda", generator=g)
+    obs = torch.randint(-3, 21, (R, W, H, 20), dtype=torch.int8, device="cuda", generator=g)
 
     class Buf:
         pass
@@ -75,6 +79,7 @@ def test_gather_large_ragged_against_torch_indexing():
     b.value_preds, b.action_log_probs = torch.randn(R, device="cuda", generator=g), torch.randn(R, device="cuda", generator=g)
     ret, adv = torch.randn(R, device="cuda", generator=g), torch.randn(R, device="cuda", generator=g)
     rows = torch.randint(0, R, (B,), dtype=torch.int32, device="cuda", generator=g)
+    rows[0], rows[-1] = R - 1, 0   # first and last row of the source buffer
     for dt in (torch.int8, torch.float32):
         mb = ppo.gather_minibatch(b, rows, adv, ret, dt)
         torch.cuda.synchronize()
