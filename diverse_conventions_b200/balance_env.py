@@ -100,18 +100,23 @@ class B200BalanceBeam(VectorMultiAgentEnv):
             _native.check(self._lib.bb_reset(self._h, _ptr(self.static_observations), self._stream()))
         return self.get_obs()
 
-    def rollout_random(self, K, obs=True, actions=True):
+    def rollout_random(self, K, obs=True, actions=True, out=None):
         N, dev = self.num_envs, self.sim_device
-        out = {
+        if out is None:
+            out = self.alloc_rollout(K, obs, actions)
+        with torch.cuda.device(self.sim_device):
+            _native.check(self._lib.bb_rollout_random(self._h, K, _ptr(out["obs"]), _ptr(out["rewards"]), _ptr(out["dones"]),
+                                                      _ptr(out["actions"]), self._stream()))
+        return out
+
+    def alloc_rollout(self, K, obs=True, actions=True):
+        N, dev = self.num_envs, self.sim_device
+        return {
             "obs": torch.empty((K, 2, N, 7), dtype=torch.int32, device=dev) if obs else None,
             "rewards": torch.empty((K, 2, N), dtype=torch.float32, device=dev),
             "dones": torch.empty((K, N), dtype=torch.int32, device=dev),
             "actions": torch.empty((K, 2, N), dtype=torch.uint8, device=dev) if actions else None,
         }
-        with torch.cuda.device(self.sim_device):
-            _native.check(self._lib.bb_rollout_random(self._h, K, _ptr(out["obs"]), _ptr(out["rewards"]), _ptr(out["dones"]),
-                                                      _ptr(out["actions"]), self._stream()))
-        return out
 
     def get_state(self):
         st = np.empty((self.num_envs, 8), dtype=np.int32)
