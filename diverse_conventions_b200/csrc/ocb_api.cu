@@ -65,8 +65,15 @@ static int build_tables_or_fail(const ocb_config* cfg, Tables* tb, uint8_t* tmpl
 
 // lanes per world: few worlds -> more (redundant) lanes so that every SM scheduler still has
 // several warps to hide the latency of the sequential transition; many worlds -> fewer lanes,
-// less redundant issue.  Thresholds from tools/sweep.py on B200 (profiles/README.md).
-static int default_lanes(int N) { return N >= 8192 ? 1 : (N >= 2048 ? 2 : 4); }
+// less redundant issue.  From tools/sweep.py on B200 over world counts 1,024..32,768 and the 400 / 500 / 900-byte
+// layouts (profiles/r1_sweep_layouts.jsonl): below 8,192 worlds G=4 wins everywhere; from 16,384 worlds G=1 for the
+// small planes (0.99-1.03 of the HBM peak, 128 CTAs) and G=2 for planes >= 800 bytes (0.94); in between 4 resp. 2.
+static int default_lanes(int N, int SC) {
+    const bool big = SC >= 800;
+    if (N < 8192) return 4;
+    if (N < 16384) return big ? 2 : 4;
+    return big ? 2 : 1;
+}
 
 static int pick_launch_shape(const ocb_env* e, int G, int* warps, size_t* smem) {
     // 4 warps per CTA measured best on B200 even when that leaves some SMs without a CTA
@@ -145,7 +152,7 @@ extern "C" int ocb_create(const ocb_config* cfg, int device, uint32_t num_worlds
     e->P = e->h_tables.P, e->S = e->h_tables.S, e->C = e->h_tables.C, e->SC = e->h_tables.SC;
     e->L = 1 + 6 * e->P + 4 * e->S;
     e->seed = seed;
-    e->lanes_per_world = default_lanes(e->N);
+    e->lanes_per_world = default_lanes(e->N, e->SC);
     e->step_lanes = 8;
     e->use_tma = 1;
 
@@ -200,7 +207,7 @@ extern "C" uint64_t ocb_step_count(const ocb_env* e) { return e ? e->step_count 
 extern "C" int ocb_set_tuning(ocb_env* e, int lanes_per_world, int use_tma) {
     if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "env is NULL");
     const bool explicit_lanes = lanes_per_world != 0;
-    if (lanes_per_world == 0) lanes_per_world = default_lanes(e->N);
+    if (lanes_per_world == 0) lanes_per_world = default_lanes(e->N, e->SC);
     if (lanes_per_world != 1 && lanes_per_world != 2 && lanes_per_world != 4 && lanes_per_world != 8)
         return fail(OCB_ERR_INVALID_ARG, "lanes_per_world must be 1, 2, 4 or 8");
     int warps;
