@@ -266,7 +266,8 @@ __global__ void __launch_bounds__(256) minibatch_gather_kernel(const GatherParam
 // Rows whose byte size is not a multiple of 16 (500, 900, ... bytes: every layout but the 4-wide-multiple ones)
 // start at arbitrary 4-byte offsets, so neither side of a straight copy can be 16-byte vectorised.  Here a warp
 // assembles kGroup = 4 consecutive OUTPUT rows (4 * S*C bytes: starts and ends on a 16-byte boundary) in shared
-// memory: every source row is fetched with aligned 16-byte loads covering it (<= 24 bytes over-read per row), the
+// memory: every source row is fetched with aligned 16-byte loads covering it (<= 12 bytes over-read in front of a
+// row, inside the buffer; the partial vector at its end is read word by word), the
 // words are dropped into place with 4-byte shared stores (the realignment), and the group leaves as aligned
 // 16-byte streaming stores — int8 as is, or widened to fp32 (one float4 per word).  All loads of a pass (up to
 // kGroup * kVec vectors per lane) are issued before the first shared store.
@@ -301,7 +302,18 @@ __global__ void __launch_bounds__(kRealignWarps * 32) minibatch_gather_realign_k
 #pragma unroll
                     for (int k = 0; k < kVec; ++k) {
                         const int v = v0 + k * 32 + lane;
-                        if (r < nr && v < nvec) x[r][k] = __ldcs(in16 + (a0 >> 2) + v);
+                        if (r < nr && v < nvec) {
+                            const int rem = words - (4 * v - (int)(wstart[r] - a0));  // row words from this vector's start
+                            if (rem >= 4) {
+                                x[r][k] = __ldcs(in16 + (a0 >> 2) + v);
+                            } else {  // last, partial vector of the row: never read past the row (it may end the buffer)
+                                const uint32_t* w = p.obs + a0 + 4 * (long long)v;
+                                x[r][k].x = __ldcs(w);
+                                x[r][k].y = rem > 1 ? __ldcs(w + 1) : 0u;
+                                x[r][k].z = rem > 2 ? __ldcs(w + 2) : 0u;
+                                x[r][k].w = 0u;
+                            }
+                        }
                     }
                 }
 #pragma unroll
