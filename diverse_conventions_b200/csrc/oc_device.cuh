@@ -59,7 +59,6 @@ __device__ __forceinline__ void warp_copy_out(int8_t* __restrict__ dst, const ui
 template <int P, int G>
 __device__ __forceinline__ void load_world(const Tables& tb, const Consts& c, const RolloutParams& prm, int nl, int g,
                                            uint16_t* myobjs, World<P>& w) {
-    constexpr int WPW = 32 / G;
     const int N = prm.N;
 #pragma unroll
     for (int i = 0; i < P; ++i) {
@@ -70,12 +69,20 @@ __device__ __forceinline__ void load_world(const Tables& tb, const Consts& c, co
         w.held[i] = pw >> 16;
     }
     w.timestep = prm.timestep[nl];
-    for (int cell = g; cell < tb.S; cell += G) myobjs[cell * WPW] = prm.objs[(size_t)cell * N + nl];
+    // `myobjs` is this LANE's private column of the warp's [S][32] object array: the G lanes of a world split the
+    // global loads and write each value into all G sibling columns (disjoint cells per writer), after which every
+    // lane only ever touches its own column
+    uint16_t* col0 = myobjs - g;  // column of the world's lane 0
+    for (int cell = g; cell < tb.S; cell += G) {
+        const uint16_t v = prm.objs[(size_t)cell * N + nl];
+#pragma unroll
+        for (int h = 0; h < G; ++h) col0[cell * 32 + h] = v;
+    }
     __syncwarp();
     int cd = 0, np = 0;
     for (int idx = g; idx < c.n_objcells; idx += G) {
         const uint32_t ci = tb.cell_info[tb.objcells[idx]];
-        const uint32_t o = myobjs[info_cell(ci) * WPW];
+        const uint32_t o = myobjs[info_cell(ci) * 32];
         cd += (info_terrain(ci) == T_COUNTER && obj_name(o) == O_DISH);
         np += (info_terrain(ci) == T_POT) ? pot_counts(o) : 0;
     }

@@ -3,7 +3,10 @@
 // oc_rollout_kernel<P,G>: K fused environment steps per launch.
 //   * a warp owns a tile of WPW = 32/G consecutive worlds for the whole launch;
 //     every world is served by G lanes that execute the (sequential, branchy)
-//     transition redundantly in registers and split the observation byte pokes;
+//     transition redundantly — each lane on its own registers and its own private
+//     column of the cell objects in shared memory, so the lanes of a world never
+//     read-modify-write a shared word (no reliance on warp lock-step; racecheck
+//     clean) — and split the observation byte pokes (disjoint bytes);
 //   * world state lives in registers (players) and shared memory (cell objects)
 //     for all K steps; HBM is touched only for the mandatory I/O:
 //     actions in, observation planes / reward / done out;
@@ -24,7 +27,7 @@
 namespace ocb {
 
 // shared-memory carve-up of one CTA (all offsets 16-byte aligned):
-//   Tables | template[SC] | per warp: planes[P][view_stride] , objs[S][WPW] u16
+//   Tables | template[SC] | per warp: planes[P][view_stride] , objs[S][32] u16 (one column per LANE)
 template <int P, int G>
 struct Carve {
     static constexpr int WPW = 32 / G;
@@ -32,7 +35,7 @@ struct Carve {
     size_t warp_bytes, warp0;
     __device__ Carve(int S, int SC) {
         view_stride = (int)align16((size_t)WPW * SC);
-        warp_bytes = (size_t)P * view_stride + align16((size_t)S * WPW * 2);
+        warp_bytes = (size_t)P * view_stride + align16((size_t)S * 32 * 2);
         warp0 = align16(sizeof(Tables)) + align16((size_t)SC);
     }
 };
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, (G == 8 ? 6 : 4)) oc_rollout_k
     const Carve<P, G> cv(S, SC);
     const int view_stride = cv.view_stride;
     uint8_t* planes = smem + cv.warp0 + warp * cv.warp_bytes;                                 // [P][WPW][SC]
-    uint16_t* myobjs = reinterpret_cast<uint16_t*>(planes + (size_t)P * view_stride) + wi;  // [S][WPW]
+    uint16_t* myobjs = reinterpret_cast<uint16_t*>(planes + (size_t)P * view_stride) + lane;  // [S][32], private column
     uint8_t* myplanes = planes + wi * SC;                                                     // + v*view_stride
 
     const int N = prm.N;
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, (G == 8 ? 6 : 4)) oc_rollout_k
         uint32_t dirty[P];
 #pragma unroll
         for (int i = 0; i < P; ++i) oldslot[i] = w.slot[i];
-        const int r = step_world<P>(tb, c, w, myobjs, WPW, act, dirty);
+        const int r = step_world<P>(tb, c, w, myobjs, 32, act, dirty);
         const bool done = w.timestep >= c.horizon;  // envs/overcooked2_env.py:334
         cur_return += r;
         if (done) {  // auto-reset, pantheonrl_extension/vectorenv.py:369-370
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, (G == 8 ? 6 : 4)) oc_rollout_k
             ep_add += 1;
             cur_return = 0;
             reset_world<P>(tb, w);
-            for (int idx = g; idx < c.n_objcells; idx += G) myobjs[(int)tb.objcells[idx] * WPW] = 0;
+            for (int idx = 0; idx < c.n_objcells; ++idx) myobjs[(int)tb.objcells[idx] * 32] = 0;  // own column
         }
         if (rew_ptr != nullptr) {
             if (valid) {
@@ -157,10 +160,10 @@ __global__ void __launch_bounds__(kThreadsPerCta, (G == 8 ? 6 : 4)) oc_rollout_k
                 if (lane == 0) bulk_wait_read_all();
                 tma_pending = false;
             }
-            __syncwarp();  // also orders the cleared cells of a reset before the sibling lanes' reads
+            __syncwarp();
             obs_phase1<P, G>(tb, myplanes, view_stride, tmpl, full, g, oldslot);
             __syncwarp();
-            obs_phase2<P, G>(tb, c, myplanes, view_stride, myobjs, WPW, full, g, w, dirty);
+            obs_phase2<P, G>(tb, c, myplanes, view_stride, myobjs, 32, full, g, w, dirty);
             if (tma_ok) {
                 fence_proxy_async_smem();  // generic-proxy pokes -> visible to the async proxy
                 __syncwarp();
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, (G == 8 ? 6 : 4)) oc_rollout_k
             }
             obs_ptr += obs_step_stride;
         } else {
-            __syncwarp();  // cleared cells of a reset are read by the sibling lanes of the world
+            __syncwarp();
         }
     }
     if (tma_pending && lane == 0) bulk_wait_read_all();
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, (G == 8 ? 6 : 4)) oc_rollout_k
 #pragma unroll
         for (int i = 0; i < P; ++i)
             if (i % G == g) prm.players[(size_t)i * N + n] = player_pack(w.pos[i], w.orient[i], w.held[i]);
-        for (int cell = g; cell < S; cell += G) prm.objs[(size_t)cell * N + n] = myobjs[cell * WPW];
+        for (int cell = g; cell < S; cell += G) prm.objs[(size_t)cell * N + n] = myobjs[cell * 32];
         if (g == 0) {
             prm.timestep[n] = w.timestep;
             prm.cur_return[n] = cur_return;
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(kThreadsPerCta) oc_observe_kernel(const Rollou
     const Carve<P, G> cv(S, SC);
     const int view_stride = cv.view_stride;
     uint8_t* planes = smem + cv.warp0 + warp * cv.warp_bytes;
-    uint16_t* myobjs = reinterpret_cast<uint16_t*>(planes + (size_t)P * view_stride) + wi;
+    uint16_t* myobjs = reinterpret_cast<uint16_t*>(planes + (size_t)P * view_stride) + lane;
     uint8_t* myplanes = planes + wi * SC;
 
     const int N = prm.N;
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(kThreadsPerCta) oc_observe_kernel(const Rollou
     for (int i = 0; i < P; ++i) noslot[i] = 0, nodirty[i] = 0xFFFFFFFFu;
     obs_phase1<P, G>(tb, myplanes, view_stride, tmpl, true, g, noslot);
     __syncwarp();
-    obs_phase2<P, G>(tb, c, myplanes, view_stride, myobjs, WPW, true, g, w, nodirty);
+    obs_phase2<P, G>(tb, c, myplanes, view_stride, myobjs, 32, true, g, w, nodirty);
     __syncwarp();
     const int nbytes = nvalid * SC;
 #pragma unroll
@@ -350,7 +353,7 @@ static cudaError_t launch_pg(const RolloutParams& prm, int warps_per_cta, size_t
 size_t rollout_smem_bytes(int P, int S, int C, int G, int warps_per_cta) {
     const int WPW = 32 / G;
     const size_t SC = (size_t)S * C;
-    const size_t per_warp = (size_t)P * align16(WPW * SC) + align16((size_t)S * WPW * 2);
+    const size_t per_warp = (size_t)P * align16(WPW * SC) + align16((size_t)S * 32 * 2);
     return align16(sizeof(Tables)) + align16(SC) + warps_per_cta * per_warp;
 }
 
