@@ -794,8 +794,7 @@ enum : int {
     PB_HEAD_EMPTY = 21,         // [2] by tile parity: MMA commit + 256 epilogue arrivals -> producer
     PB_W_FULL = 24,             // [24] bulk copy complete_tx -> MMA
     PB_W_EMPTY = 48,            // [24] MMA commit -> producer
-    PB_D1_EMPTY = 72,           // [2] both epilogue groups (256 arrivals) -> MMA: conv stage s has been read into registers
-    PB_COUNT = 74,
+    PB_COUNT = 72,
     PB_TMEM_SLOT = 120          // 8-byte slot index that holds the TMEM base address
 };
 
@@ -873,7 +872,6 @@ __device__ __forceinline__ void pair_mma_role(long long* pw, const PolicyParams&
     uint32_t item_par = 0;       // phase parity bit of the A stage per network (items issued so far, mod 2)
     int slot = 0;
     uint32_t wround = 0, head_gen = 0, w_gen = 0, u = 0;
-    uint32_t d1_uses[2] = {0u, 0u};  // convs issued into each accumulator stage so far
 
     for (int t = t0; t < t1; ++t, ++u, gcb += W) {
         const bool chg = blob_changed(prm, t, t0);
@@ -891,13 +889,6 @@ __device__ __forceinline__ void pair_mma_role(long long* pw, const PolicyParams&
                     const uint32_t g = gcb + ox + d;
                     mbar_wait_p<kProf>(bars + 8 * (PB_COL_FULL + g % kColRing), (g / kColRing) & 1, pw[PW_COL_FULL]);
                 }
-            }
-            // the stage's previous conv result must have been read into registers by both epilogue groups (one release
-            // per conv, consumed in order: the k-th conv of a stage waits for release k-1)
-            {
-                const int st = cp & 1;
-                if (d1_uses[st] > 0) mbar_wait_p<kProf>(bars + 8 * (PB_D1_EMPTY + st), (d1_uses[st] - 1) & 1, pw[PW_D3_FULL]);
-                ++d1_uses[st];
             }
             // stage cp (< 2) still holds D3 of network cp of the previous tile until its head epilogue has read it
             if (u > 0 && cp < 2) mbar_wait_p<kProf>(bars + 8 * (PB_D3_EMPTY + cp), (u - 1) & 1, pw[PW_D3_FULL]);
@@ -958,14 +949,14 @@ __device__ __forceinline__ void pair_mma_role(long long* pw, const PolicyParams&
         };
 
         // static issue order: the conv runs two positions ahead of the FC1 partial sums (two accumulator stages);
-        // conv(p + 2) reuses the stage of position p and is issued as soon as both groups have LOADED position p
-        // (PB_D1_EMPTY), i.e. while they still compute / publish it, so its result is waiting when they come back
+        // conv(p + 2) reuses the stage of position p, which both groups have drained once both FC1 items of
+        // position p could be issued
         conv();
         conv();
         for (int p = 0; p < npos; ++p) {
-            if (p + 2 < npos) conv();
             fc(0, p);
             fc(1, p);
+            if (p + 2 < npos) conv();
         }
         fc(0, npos), fc(1, npos);
         fc(0, npos + 1), fc(1, npos + 1);
@@ -1019,8 +1010,6 @@ __device__ __forceinline__ void pair_epilogue_role(long long* pw, const PolicyPa
             tc_fence_after();
             float v[32];
             tmem_ld32(trow + kPColD1 + st * kHid + g * kCo, v);
-            tc_fence_before();
-            mbar_arrive(bars + 8 * (PB_D1_EMPTY + st));  // the accumulator stage may be overwritten by conv j + 2
             publish(v, s_bias1 + j * kCo);
         }
         mbar_wait_p<kProf>(bars + 8 * (PB_D2_FULL + g), u & 1, pw[PW_D2_FULL]);
@@ -1106,7 +1095,6 @@ __global__ void __launch_bounds__(kThreads, 1) policy_pair_kernel(const PolicyPa
             if ((i >= PB_COL_FULL && i < PB_COL_FULL + 4) || (i >= PB_A2_FULL && i < PB_A2_FULL + 2) ||
                 (i >= PB_D3_EMPTY && i < PB_D3_EMPTY + 2))
                 count = 128;
-            if (i >= PB_D1_EMPTY && i < PB_D1_EMPTY + 2) count = 32 * kEpiWarps;
             if (i >= PB_HEAD_EMPTY && i < PB_HEAD_EMPTY + 2) count = 32 * kEpiWarps + 1;
             mbar_init(bars + 8 * i, count);
         }

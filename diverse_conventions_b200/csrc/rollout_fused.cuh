@@ -279,7 +279,6 @@ __global__ void __launch_bounds__(kFThreads, 1) rollout_fused_kernel(const Fused
             if ((i >= PB_COL_FULL && i < PB_COL_FULL + 4) || (i >= PB_A2_FULL && i < PB_A2_FULL + 2) ||
                 (i >= PB_D3_EMPTY && i < PB_D3_EMPTY + 2))
                 count = 128;
-            if (i >= PB_D1_EMPTY && i < PB_D1_EMPTY + 2) count = 32 * kEpiWarps;
             if (i >= PB_HEAD_EMPTY && i < PB_HEAD_EMPTY + 2) count = 32 * kEpiWarps + 1;
             if (i == FB_OBS_FULL) count = 32 * kFEnvWarps;
             if (i == FB_OBS_EMPTY) count = 32 * kLoadWarps;
