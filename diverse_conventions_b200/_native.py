@@ -59,6 +59,7 @@ PROTOTYPES = {
     "ocb_policy_act_ex": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _u64, _u64, _vp, _vp]),
     "ocb_policy_value": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "ocb_policy_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _u64, _u64, _vp, _vp]),
+    "ocb_policy_set_sampling_rows": (_i, [_vp, _u32, _u32, _u32]),
     "ocb_policy_info": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "ocb_policy_reserve": (_i, [_vp, _i]),
     "ocb_policy_debug_profile": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i]),

@@ -120,6 +120,9 @@ struct PolicyParams {
     int deterministic;
     unsigned long long seed, offset;
     const unsigned long long* d_offset;  // optional device-resident addend of `offset`
+    // sampling rows of a sharded env (ocb_policy_set_sampling_rows): launch row r draws from counter row
+    // r + (r < rng_rows_per_seat ? rng_add0 : rng_add1); all zero = the launch row itself
+    unsigned int rng_rows_per_seat, rng_add0, rng_add1;
     int net_mask;             // 1 actor, 2 critic, 3 both (even CTAs actor, odd critic)
     int ring;                 // weight-ring slots in shared memory
     int pair_ring;            // same for policy_pair_kernel (chunks of both networks)
@@ -576,7 +579,8 @@ __device__ __forceinline__ int emit_actor_row(const PolicyParams& prm, long long
 #pragma unroll
             for (int a = 1; a < 6; ++a) act = (head[a] > head[act]) ? a : act;
         } else {
-            uint32_t r[4] = {rng_row, (uint32_t)offset, (uint32_t)(offset >> 32), 0x5A17u};
+            const uint32_t grow = rng_row + (rng_row < prm.rng_rows_per_seat ? prm.rng_add0 : prm.rng_add1);
+            uint32_t r[4] = {grow, (uint32_t)offset, (uint32_t)(offset >> 32), 0x5A17u};
             philox4x32_10(r, (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
             const float uu = (float)(r[0] >> 8) * (1.0f / 16777216.0f) * sum;
             float cum = 0.0f;
@@ -1181,6 +1185,7 @@ struct ocb_policy {
     // critic value of the all-zero observation per weight set (a constant of the weights; the mixed-play buffer
     // bootstraps from the never-written slot L, which holds zeros in the reference)
     std::vector<float> zero_value;
+    uint32_t rng_rows_per_seat = 0, rng_add0 = 0, rng_add1 = 0;  // ocb_policy_set_sampling_rows
 };
 
 extern "C" int ocb_policy_destroy(ocb_policy* p) {
@@ -1496,6 +1501,7 @@ static int policy_launch(ocb_policy* p, int net_mask, const int8_t* obs, int M, 
     prm.obs = obs, prm.M = M, prm.tiles = (M + kRows - 1) / kRows, prm.tile_policy = tile_policy;
     prm.logits = logits, prm.actions = actions, prm.logp = logp, prm.values = values;
     prm.deterministic = deterministic, prm.seed = seed, prm.offset = offset;
+    prm.rng_rows_per_seat = p->rng_rows_per_seat, prm.rng_add0 = p->rng_add0, prm.rng_add1 = p->rng_add1;
     prm.d_offset = reinterpret_cast<const unsigned long long*>(d_offset);
     prm.net_mask = net_mask, prm.ring = p->ring, prm.stage_stride = p->stage_stride;
     prm.pair_ring = p->pair_ring;
@@ -1571,6 +1577,12 @@ extern "C" int ocb_policy_evaluate(ocb_policy* p, const int8_t* obs, const int32
                          nullptr, nullptr, &ev);
 }
 
+extern "C" int ocb_policy_set_sampling_rows(ocb_policy* p, uint32_t rows_per_seat, uint32_t add_seat0, uint32_t add_seat1) {
+    if (p == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL handle");
+    p->rng_rows_per_seat = rows_per_seat, p->rng_add0 = add_seat0, p->rng_add1 = add_seat1;
+    return OCB_OK;
+}
+
 extern "C" int ocb_policy_info(const ocb_policy* p, int* ring_slots, int* chunks_per_unit, int* smem_bytes) {
     if (p == nullptr) return fail(OCB_ERR_INVALID_ARG, "policy is NULL");
     if (ring_slots) *ring_slots = p->ring;
@@ -1628,6 +1640,7 @@ int ocb_policy_rollout_fused_launch(ocb_policy* p, int policy_index, const Rollo
     fp.pol.W = p->W, fp.pol.H = p->H, fp.pol.S = p->S, fp.pol.SC = p->SC, fp.pol.npos = p->npos;
     fp.pol.M = kRows, fp.pol.tiles = 1;
     fp.pol.deterministic = deterministic, fp.pol.seed = seed, fp.pol.offset = 0;
+    fp.pol.rng_rows_per_seat = p->rng_rows_per_seat, fp.pol.rng_add0 = p->rng_add0, fp.pol.rng_add1 = p->rng_add1;
     fp.pol.d_offset = reinterpret_cast<const unsigned long long*>(d_offset);
     fp.pol.net_mask = 3, fp.pol.pair_ring = ring, fp.pol.stage_stride = p->stage_stride;
     fp.env = envp;

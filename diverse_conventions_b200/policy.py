@@ -195,6 +195,11 @@ class FusedPolicy:
                 self._ct.c_void_p(d_offset) if d_offset else None, self._stream()))
         return out
 
+    def set_sampling_rows(self, rows_per_seat: int = 0, add_seat0: int = 0, add_seat1: int = 0):
+        """shard-invariant sampling streams (``ocb_policy_set_sampling_rows``): for a shard of N worlds starting at
+        global world ``world0`` out of ``N_total`` pass ``(N, world0, N_total - N + world0)``; ``()`` = default"""
+        self._native.check(self._lib.ocb_policy_set_sampling_rows(self._h, rows_per_seat, add_seat0, add_seat1))
+
     def info(self) -> dict:
         r, c, b = self._ct.c_int(), self._ct.c_int(), self._ct.c_int()
         self._native.check(self._lib.ocb_policy_info(self._h, self._ct.byref(r), self._ct.byref(c), self._ct.byref(b)))

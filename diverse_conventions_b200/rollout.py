@@ -88,8 +88,13 @@ class PolicyRollout:
 
     def __init__(self, env: B200Overcooked, policy: FusedPolicy, T: int, tile_policy: Optional[torch.Tensor] = None,
                  with_critic: bool = True, with_logp: bool = True, seed: int = 0, use_graph: bool = False,
-                 fused: Optional[bool] = None, policy_index: int = 0):
-        """``fused``: run the rollout as ONE persistent launch (``ocb_rollout_policy_fused``: self-play of weight
+                 fused: Optional[bool] = None, policy_index: int = 0, world_offset: int = 0,
+                 total_worlds: Optional[int] = None):
+        """``total_worlds`` (with ``world_offset`` = global index of this env's world 0): key the action sampling by
+        the GLOBAL (seat, world) so that a sharded run draws exactly the streams of the unsharded one
+        (``ocb_policy_set_sampling_rows``); ``None`` keeps the launch-local rows.
+
+        ``fused``: run the rollout as ONE persistent launch (``ocb_rollout_policy_fused``: self-play of weight
         set ``policy_index``, hidden 64, critic on); ``None`` = use it whenever it applies, ``False`` = always the
         2T+1-launch path.  Both paths fill bit-identical buffers."""
         if env.num_players != 2:
@@ -120,11 +125,17 @@ class PolicyRollout:
         self._graphs = {}
         self.use_graph = use_graph
         self.rollouts = 0
+        N = env.num_envs
+        if total_worlds is not None and not (0 <= world_offset and world_offset + N <= total_worlds):
+            raise ValueError("world_offset + num_envs must lie inside total_worlds")
+        self._sampling_rows = (0, 0, 0) if total_worlds is None else (N, world_offset, total_worlds - N + world_offset)
 
     # ------------------------------------------------------------------ launches
     def _issue(self, deterministic: bool):
         b, env = self.buf, self.env
         stream = ctypes.c_void_p(torch.cuda.current_stream(env.sim_device).cuda_stream)
+        # handle-level state, set per issue: several rollouts may share one policy handle
+        _native.check(self._lib.ocb_policy_set_sampling_rows(self.policy._h, *self._sampling_rows))
         if self.fused:
             rc = self._lib.ocb_rollout_policy_fused(
                 env._h, self.policy._h, self.T, self.policy_index, _ptr(b.obs), _ptr(b.actions), _ptr(b.action_log_probs),
@@ -209,7 +220,7 @@ class CrossPlayEvaluator:
 
     def __init__(self, layout: str, policy: FusedPolicy, pairs, worlds_per_pair: int = 1024, horizon: int = 400,
                  gpu_id: int = 0, seed: int = 0, world_offset: int = 0, chunk_steps: int = 50, use_graph: bool = True,
-                 deterministic: bool = False):
+                 deterministic: bool = False, total_worlds: Optional[int] = None):
         self.pairs = [tuple(int(v) for v in p) for p in pairs]
         if not self.pairs:
             raise ValueError("no pairs on this rank")
@@ -223,8 +234,9 @@ class CrossPlayEvaluator:
         self.env = B200Overcooked(layout, N, gpu_id, horizon=horizon, seed=seed, world_offset=world_offset)
         table = pair_tile_policy(self.pairs, worlds_per_pair, self.env.sim_device)
         # the slab holds chunk_steps observations, not the whole episode: evaluation keeps no trajectory
+        # total_worlds = worlds of the whole pair list over all ranks: the matrix then does not depend on the sharding
         self.rollout = PolicyRollout(self.env, policy, chunk_steps, table, with_critic=False, with_logp=False, seed=seed,
-                                     use_graph=use_graph)
+                                     use_graph=use_graph, world_offset=world_offset, total_worlds=total_worlds)
 
     def run(self):
         """one full episode per world -> (return_sum int64 [pairs], episodes int64 [pairs]) on the device"""

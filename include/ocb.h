@@ -215,6 +215,13 @@ int ocb_policy_value(ocb_policy* pol, const int8_t* obs, int M, const int32_t* t
 int ocb_policy_forward(ocb_policy* pol, const int8_t* obs, int M, const int32_t* tile_policy, int32_t* actions,
                        float* logp, float* logits, float* values, int deterministic, uint64_t seed, uint64_t offset,
                        const uint64_t* d_offset, void* stream);
+/* Sampling streams that do not depend on how an env is sharded.  By default launch row r (r = seat * N + world for
+ * the rollouts) draws from counter row r.  For a shard holding worlds world0 .. world0 + N - 1 of N_total, call this
+ * with (N, world0, N_total - N + world0): seat-0 rows map to world0 + world, seat-1 rows to N_total + world0 + world,
+ * i.e. every (seat, global world) keeps its stream on any number of GPUs — the cross-play matrix gathered from 8 ranks
+ * is bit-identical to the single-GPU one.  Applies to every later sampling launch of this handle; (0, 0, 0) restores
+ * the default.  Not in the reference (its sampling is torch's global generator, train/MAPPO/utils/distributions.py:14-20). */
+int ocb_policy_set_sampling_rows(ocb_policy* pol, uint32_t rows_per_seat, uint32_t add_seat0, uint32_t add_seat1);
 /* launch shape in effect: weight-ring slots in shared memory, FC weight chunks per (tile, network)
  * unit (ring >= chunks means the weights stay resident), dynamic shared memory per CTA */
 int ocb_policy_info(const ocb_policy* pol, int* ring_slots, int* chunks_per_unit, int* smem_bytes);

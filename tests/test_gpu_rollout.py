@@ -297,3 +297,36 @@ def test_destroying_handles_during_a_capture_keeps_the_graph_valid():
     orc = COracle(lp, 256)
     o, r, d = orc.rollout(ro.buf.actions.cpu().numpy().astype(np.uint8))
     assert np.array_equal(ro.buf.obs[1:].cpu().numpy(), o) and np.array_equal(ro.buf.rewards.cpu().numpy(), r)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_crossplay_matrix_does_not_depend_on_the_sharding(use_graph):
+    """with the sampling keyed by the GLOBAL (seat, world) (ocb_policy_set_sampling_rows) the
+    per-pair returns of a sharded evaluation are bit-identical to the unsharded one — here 9 pairs in one env against
+    three "ranks" of 3 pairs each on the same GPU."""
+    layout, horizon, wpp, n_pol = "random1", 40, 128, 3
+    lp = layouts.load_layout(layout, horizon)
+    pol, _, _ = make_policies(lp, n_pol, gain=3.0)
+    pairs = sharding.all_pairs(n_pol)
+    total = len(pairs) * wpp
+
+    def run(my_pairs, offset, with_total=True):
+        ev = CrossPlayEvaluator(layout, pol, my_pairs, worlds_per_pair=wpp, horizon=horizon, seed=3, chunk_steps=20,
+                                use_graph=use_graph, world_offset=offset, total_worlds=total if with_total else None)
+        rs, ep = ev.run()
+        torch.cuda.synchronize()
+        out = (rs.clone(), ep.clone())
+        ev.close()
+        return out
+
+    whole_rs, whole_ep = run(pairs, 0)
+    parts = [run(sharding.pair_shard(pairs, r, 3), r * 3 * wpp) for r in range(3)]
+    assert torch.equal(torch.cat([p[0] for p in parts]), whole_rs)
+    assert torch.equal(torch.cat([p[1] for p in parts]), whole_ep)
+    assert int(whole_rs.sum()) > 0
+    # without the global rows the shards re-use the launch-local rows: same statistics, different streams
+    local = [run(sharding.pair_shard(pairs, r, 3), r * 3 * wpp, with_total=False) for r in range(3)]
+    assert not torch.equal(torch.cat([p[0] for p in local]), whole_rs)
+    # and the unsharded run is the default stream when the env is the whole job (offset 0, N == total)
+    plain_rs, _ = run(pairs, 0, with_total=False)
+    assert torch.equal(plain_rs, whole_rs)

@@ -126,7 +126,7 @@ def main():
         pairs = sharding.pair_shard(sharding.all_pairs(n), rank, world)
         ev = CrossPlayEvaluator(layout, pol, pairs, worlds_per_pair=args.worlds_per_pair, horizon=400, gpu_id=local,
                                 seed=1, world_offset=rank * len(pairs) * args.worlds_per_pair, chunk_steps=50,
-                                use_graph=bool(args.graph))
+                                use_graph=bool(args.graph), total_worlds=n * n * args.worlds_per_pair)
         ev.run()
         out = {}
 
@@ -142,6 +142,7 @@ def main():
                               "ms_per_matrix": round(ms, 3), "agent_steps_per_s": round(2 * worlds_total * 400 / (ms * 1e-3)),
                               "episodes": int(eps.sum()), "matrix_mean": float(mean.nanmean()),
                               "matrix_diag_mean": float(mean.diagonal().mean()),
+                              "matrix_sha256": __import__("hashlib").sha256(mean.cpu().numpy().tobytes()).hexdigest()[:16],
                               "matrix_row0": [round(float(x), 3) for x in mean[0].tolist()]}), flush=True)
         ev.close()
     if world > 1:
