@@ -106,6 +106,8 @@ class MixedPlayCollector:
     def _issue(self, deterministic: bool):
         b, env = self.buf, self.env
         stream = ctypes.c_void_p(torch.cuda.current_stream(env.sim_device).cuda_stream)
+        # launch-local sampling rows (a sharded PolicyRollout may have left global rows on a shared policy handle)
+        _native.check(self._lib.ocb_policy_set_sampling_rows(self.policy._h, 0, 0, 0))
         _native.check(self._lib.ocb_rollout_mixed(
             env._h, self.policy._h, self.L, self.main_policy, self.partner_policy, _ptr(b.obs), _ptr(b.actions),
             _ptr(b.action_log_probs), _ptr(b.value_preds), _ptr(b.rewards), _ptr(b.dones), int(deterministic), self.seed,
