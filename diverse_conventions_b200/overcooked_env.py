@@ -76,6 +76,8 @@ class B200Overcooked(VectorMultiAgentEnv):
         self.static_active_agents = torch.ones((P, N), dtype=torch.bool, device=dev)
         self.static_action_mask = torch.ones((N, NUM_ACTIONS), dtype=torch.bool, device=dev)
         self._actions_i32 = torch.empty((P, N), dtype=torch.int32, device=dev)
+        self._p_obs, self._p_rew, self._p_done = (_ptr(self.static_observations), _ptr(self.static_rewards),
+                                                  _ptr(self.static_dones))
 
         self.obs_size = self.size * self.channels
         self.state_size = self.obs_size
@@ -115,6 +117,13 @@ class B200Overcooked(VectorMultiAgentEnv):
 
     # ------------------------------------------------------------------ reference API
     def get_obs(self) -> List[VectorObservation]:
+        if self.device == self.sim_device:  # views of the static buffers, sliced once (tensor indexing costs microseconds)
+            views = self.__dict__.get("_static_views")
+            if views is None:
+                views = self._static_views = [(self.static_active_agents[i], self.static_observations[i])
+                                              for i in range(self.n_players)]
+            mask = self.static_action_mask
+            return [VectorObservation(a, o, action_mask=mask) for a, o in views]
         mask = self.to_torch(self.static_action_mask)
         return [VectorObservation(self.to_torch(self.static_active_agents[i]), self.to_torch(self.static_observations[i]),
                                   action_mask=mask) for i in range(self.n_players)]
@@ -137,9 +146,12 @@ class B200Overcooked(VectorMultiAgentEnv):
 
     def n_step(self, actions: torch.Tensor):
         a, code = self._prepare_actions(actions, 0)
-        with torch.cuda.device(self.sim_device):
-            _native.check(self._lib.ocb_step_ex(self._h, _ptr(a), code, _ptr(self.static_observations),
-                                                _ptr(self.static_rewards), _ptr(self.static_dones), self._stream()))
+        # the library switches to the env's device itself (DeviceGuard); torch only has to name the right stream
+        rc = self._lib.ocb_step_ex(self._h, _ptr(a), code, self._p_obs, self._p_rew, self._p_done, self._stream())
+        if rc < 0:
+            _native.check(rc)
+        if self.device == self.sim_device:
+            return self.get_obs(), self.static_rewards, self.static_dones, self.infos
         return self.get_obs(), self.to_torch(self.static_rewards), self.to_torch(self.static_dones), self.infos
 
     def n_reset(self):
