@@ -233,6 +233,16 @@ def ncu_traffic_bytes(kernel_name):
             with open(path) as f:
                 rows = json.load(f)
             vals = []
+            if isinstance(rows, dict):  # tools/ncu_summary.py: {"launches": [{"kernel": ..., "metric [unit]": value}]}
+                for r in rows.get("launches", []):
+                    if kernel_name.replace(" ", "") not in r.get("kernel", "").replace(" ", ""):
+                        continue
+                    tot = 0.0
+                    for k, v in r.items():
+                        if k.startswith("dram__bytes_read.sum [") or k.startswith("dram__bytes_write.sum ["):
+                            tot += float(v) * unit[k[k.index("[") + 1:-1]]
+                    vals.append(tot)
+                rows = []
             for r in rows:
                 if kernel_name.replace(" ", "") not in r.get("Kernel Name", "").replace(" ", ""):
                     continue
