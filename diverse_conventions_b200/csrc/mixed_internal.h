@@ -5,8 +5,6 @@
 
 namespace ocb {
 
-constexpr uint32_t kMixTag = 0x4D495845u;  // "MIXE": 4th Philox counter word of the mask stream
-
 struct MixSelectParams {
     const int32_t* a_main;     // [P][N] actions of the policy being trained
     const int32_t* a_partner;  // [P][N] actions of the partner convention

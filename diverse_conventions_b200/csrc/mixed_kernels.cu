@@ -16,7 +16,7 @@
 #include <stdint.h>
 
 #include "mixed_internal.h"
-#include "oc_core.cuh"
+#include "mixed_schedule.h"
 
 namespace ocb {
 
@@ -25,47 +25,21 @@ namespace {
 constexpr int kSelThreads = 256;
 constexpr int kRecWarps = 8;
 
-// forced-to-main schedule and buffer slot of (step s, world j of its replica); xd_player.py:298-305,
-// partner_agents.py:167-173 (forcing), xd_player.py:244-281 + shared_buffer.py:166,206 (slot)
-__device__ __forceinline__ bool forced_main(int L, int s, int j) {
-    const int G = L - 1;
-    return s < L ? (s > 0 && j >= G - s) : (j < s - L);
-}
-
 __global__ void __launch_bounds__(kSelThreads) mix_select_kernel(const MixSelectParams p) {
     const int row = blockIdx.x * kSelThreads + threadIdx.x;
     if (row >= p.P * p.N) return;
     const int n = row % p.N;
     int act = p.a_main[row];
-    if (!forced_main(p.L, p.s, n % (p.L - 1))) {
-        const unsigned long long step = *p.step_counter;
-        uint32_t r[4] = {(uint32_t)row, (uint32_t)step, (uint32_t)(step >> 32), kMixTag};
-        philox4x32_10(r, (uint32_t)p.mix_seed, (uint32_t)(p.mix_seed >> 32));
-        if (r[0] < 0x80000000u) act = p.a_partner[row];
-    }
+    if (!mix_forced_main(p.L, p.s, n % (p.L - 1)) && mix_draw_partner(p.mix_seed, (uint32_t)row, *p.step_counter))
+        act = p.a_partner[row];
     p.act[row] = act;
-}
-
-// first recorded world of a replica and how many are recorded at step s
-__device__ __forceinline__ void recorded_range(int L, int s, int* j0, int* cnt) {
-    const int G = L - 1;
-    if (s < L) *j0 = G - s, *cnt = s;  // s <= G
-    else *j0 = 0, *cnt = s - L;
 }
 
 __global__ void __launch_bounds__(kRecWarps * 32) mix_record_kernel(const MixRecordParams p) {
     const int lane = threadIdx.x & 31;
     const long long item = (long long)blockIdx.x * kRecWarps + (threadIdx.x >> 5);
-    int j0, cnt;
-    recorded_range(p.L, p.s, &j0, &cnt);
-    const int G = p.L - 1, R = p.N / G;
-    const long long per_seat = (long long)R * cnt;
-    if (item >= per_seat * p.P) return;
-    const int seat = (int)(item / per_seat);
-    const long long k = item - (long long)seat * per_seat;
-    const int rep = (int)(k / cnt), j = j0 + (int)(k - (long long)rep * cnt);
-    const int n = rep * G + j;
-    const int t = p.s < p.L ? j - G + p.s : p.s - p.L;
+    int seat, n, t;
+    if (!mix_record_item(p.L, p.s, p.N, p.P, item, &seat, &n, &t)) return;
     const size_t src = (size_t)seat * p.N + n, dst = ((size_t)t * p.P + seat) * p.N + n;
 
     // observation the action was computed on (SC is a multiple of 4: C = 20)

@@ -180,3 +180,29 @@ extern "C" int ocemu_rollout(const ocb_config* cfg, int G, int32_t* state, int N
     }
     return -1;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// mixed-play schedule / mask stream (csrc/mixed_schedule.h): the exact functions mix_select_kernel and
+// mix_record_kernel call, exported for the CPU test against oracle/mixed_oracle.py
+#include "mixed_schedule.h"
+
+extern "C" int ocemu_mix_forced(int L, int s, int j) { return ocb::mix_forced_main(L, s, j) ? 1 : 0; }
+
+// enumerates the record items of step s exactly as launch_mix_record / mix_record_kernel do; out = [items][3] (seat, world, slot)
+extern "C" int ocemu_mix_items(int L, int s, int N, int P, int* out, int max_items) {
+    const int G = L - 1, R = N / G;
+    const int cnt = s < L ? s : s - L;
+    const long long items = (long long)R * cnt * P;
+    int n = 0;
+    for (long long item = 0; item < items + 8; ++item) {  // a few past the end: the kernel's tail warps must bail out
+        int seat, world, slot;
+        if (!ocb::mix_record_item(L, s, N, P, item, &seat, &world, &slot)) continue;
+        if (n < max_items) out[3 * n] = seat, out[3 * n + 1] = world, out[3 * n + 2] = slot;
+        ++n;
+    }
+    return n;
+}
+
+extern "C" int ocemu_mix_draw(unsigned long long seed, unsigned int row, unsigned long long step) {
+    return ocb::mix_draw_partner(seed, row, step) ? 1 : 0;
+}

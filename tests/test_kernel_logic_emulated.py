@@ -66,3 +66,31 @@ def test_emulated_rng_stream_matches_oracle_stream():
     assert np.array_equal(ao, random_actions(77, 100, N, 5, K, 2))
     o, _, _ = orc.rollout(ao)
     assert np.array_equal(o, obs)
+
+
+def test_mixed_play_schedule_and_mask_stream_of_the_kernels_match_the_oracle():
+    """csrc/mixed_schedule.h (what mix_select_kernel / mix_record_kernel execute) against oracle/mixed_oracle.py, which is
+    pinned to the reference's collect_mp_episode / MixedAgent / diaginsert / partinsert goldens"""
+    import ctypes
+
+    import numpy as np
+
+    from emu import build_emu
+    from oracle import mixed_oracle as mo
+    L_ = build_emu.lib()
+    for L in (2, 3, 7, 10):
+        G = L - 1
+        forced, slot = mo.schedule(L)
+        for s in range(2 * L):
+            for j in range(G):
+                assert bool(L_.ocemu_mix_forced(L, s, j)) == bool(forced[s, j]), (L, s, j)
+            for replicas, P in ((1, 2), (3, 2)):
+                N = replicas * G
+                buf = np.full((2 * N * P + 16, 3), -1, dtype=np.int32)
+                n = L_.ocemu_mix_items(L, s, N, P, buf.ctypes.data_as(ctypes.c_void_p), buf.shape[0])
+                want = sorted((p, w, int(slot[s, w % G])) for p in range(P) for w in range(N) if forced[s, w % G])
+                assert n == len(want) and sorted(map(tuple, buf[:n].tolist())) == want, (L, s, replicas)
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        seed, row, step = int(rng.integers(0, 2**63)), int(rng.integers(0, 2**31)), int(rng.integers(0, 2**40))
+        assert bool(L_.ocemu_mix_draw(seed, row, step)) == mo.mix_draw(seed, row, step)
