@@ -11,8 +11,6 @@ on the same action streams (scripted cooks with noise phases, so pots fill, cook
 agree exactly: parsed parameters, observations, rewards, dones, packed states.
 """
 import ctypes
-import os
-
 import numpy as np
 import pytest
 import torch
@@ -22,63 +20,10 @@ from emu.build_emu import lib as emu_lib
 from oracle import ref_shim
 from oracle.c_oracle import COracle
 from oracle.overcooked_oracle import OvercookedOracle
+from random_layouts import random_layout, run_reference
 from scripted_agent import ScriptedTeam
 
 pytestmark = pytest.mark.reference
-
-NON_WALKABLE = "XXXXXXPODST"  # weights of the solid cell kinds
-
-
-def random_layout(rng) -> dict:
-    """a grid the CUDA path accepts (solid border, players on interior AIR) with at least one of every station"""
-    while True:
-        W, H = int(rng.integers(4, 10)), int(rng.integers(4, 7))
-        g = [[NON_WALKABLE[int(rng.integers(len(NON_WALKABLE)))] for _ in range(W)] for _ in range(H)]
-        air = []
-        for y in range(1, H - 1):
-            for x in range(1, W - 1):
-                if rng.random() < 0.7:
-                    g[y][x] = " "
-                    air.append((x, y))
-        n_players = int(rng.integers(1, 5))
-        flat = "".join("".join(r) for r in g)
-        if len(air) < n_players + 1 or not all(c in flat for c in "PODS"):
-            continue
-        for i, k in enumerate(rng.permutation(len(air))[:n_players]):
-            x, y = air[int(k)]
-            g[y][x] = str(i + 1)
-        d = {"grid": "\n".join("".join(r) for r in g), "start_order_list": None}
-        kind = int(rng.integers(3))
-        if kind == 0:
-            d["cook_time"], d["delivery_reward"] = int(rng.integers(1, 25)), int(rng.integers(1, 60))
-        elif kind == 1:
-            d["onion_time"], d["tomato_time"] = int(rng.integers(1, 9)), int(rng.integers(1, 9))
-            d["onion_value"], d["tomato_value"] = int(rng.integers(1, 12)), int(rng.integers(1, 12))
-        d["rew_shaping_params"] = None if rng.random() < 0.5 else {
-            "PLACEMENT_IN_POT_REW": int(rng.integers(0, 7)), "DISH_PICKUP_REWARD": int(rng.integers(0, 7)),
-            "SOUP_PICKUP_REWARD": int(rng.integers(0, 9)), "DISH_DISP_DISTANCE_REW": 0, "POT_DISTANCE_REW": 0,
-            "SOUP_DISTANCE_REW": 0}
-        return d
-
-
-def pack_ref_state(env) -> np.ndarray:
-    st = env.state
-    P, S = env.mdp.num_players, env.mdp.size
-    row = np.zeros(1 + 6 * P + 4 * S, dtype=np.int32)
-    row[0] = st.timestep
-
-    def put(at, obj):
-        if obj != 0:
-            row[at:at + 4] = (obj.name, obj.num_onions, obj.num_tomatoes, obj._cooking_tick)
-
-    for i, pl in enumerate(st.players):
-        row[1 + 6 * i] = pl.position
-        row[1 + 6 * i + 1] = pl.orientation
-        put(1 + 6 * i + 2, pl.held_object)
-    for c in range(S):
-        put(1 + 6 * P + 4 * c, st.objects[c])
-    return row
-
 
 @pytest.mark.parametrize("seed", range(24))  # placements, pickups and deliveries occur in most seeds; walled-in stations in the rest
 def test_random_layout_matches_the_live_reference(seed, tmp_path):
@@ -99,24 +44,10 @@ def test_random_layout_matches_the_live_reference(seed, tmp_path):
     P = lp.num_players
 
     # reference run, actions from scripted cooks on the reference's own state
-    venv = ns.SyncVectorEnv([lambda: ns.SimplifiedOvercooked(path, horizon=horizon)], device="cpu")
-    obs = venv.n_reset()
-    env = venv.envs[0]
-    team = ScriptedTeam(lp, rng, noise=0.2)
-    acts = np.zeros((steps, P, 1), np.uint8)
-    ref_obs = np.zeros((steps, P, 1, lp.width, lp.height, lp.channels), np.int8)
-    ref_rew = np.zeros((steps, P, 1), np.int32)
-    ref_done = np.zeros((steps, 1), np.int32)
-    ref_state = np.zeros((steps, 1 + 6 * P + 4 * lp.size), np.int32)
-    reset_obs = np.stack([o.obs[0].numpy() for o in obs]).astype(np.int8)
-    for t in range(steps):
-        team.noise = 1.0 if (t // 40) % 3 == 2 else 0.2
-        a = np.asarray(team.joint(pack_ref_state(env)), dtype=np.int64)
-        obs, r, dn, _ = venv.n_step(torch.from_numpy(a).reshape(P, 1, 1))
-        o = np.stack([x.obs[0].numpy() for x in obs])
-        assert np.array_equal(o, o.astype(np.int8))
-        acts[t, :, 0], ref_obs[t, :, 0], ref_rew[t, :, 0], ref_done[t, 0] = a, o, r.numpy()[:, 0], int(dn[0])
-        ref_state[t] = pack_ref_state(env)
+    ref = run_reference(ns, path, lp, horizon, steps, rng, ScriptedTeam)
+    acts = np.ascontiguousarray(ref["actions"][:, :, None])
+    ref_obs, ref_rew = ref["obs"][:, :, None], np.repeat(ref["rewards"][:, None, None], P, axis=1)
+    ref_done, ref_state, reset_obs = ref["dones"][:, None], ref["states"], ref["reset_obs"]
 
     # C oracle
     orc = COracle(lp, 1)
