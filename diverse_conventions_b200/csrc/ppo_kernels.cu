@@ -579,7 +579,7 @@ extern "C" int ocb_minibatch_gather(int device, const int32_t* rows, int B, int 
             kern<<<rgrid, kRealignWarps * 32, rl_smem, s>>>(p);
         }
     } else if (obs_out_f32) minibatch_gather_kernel<uint32_t, 8, true><<<grid, 256, 0, s>>>(p);
-    else if (vec16) minibatch_gather_kernel<uint4, 4, false><<<grid, 256, 0, s>>>(p);
+    else if (vec16) minibatch_gather_kernel<uint4, 8, false><<<grid, 256, 0, s>>>(p);  // 8 vectors in flight per thread: 0.70 of the HBM peak at 400-byte rows (4: 0.63, 16: 0.48)
     else minibatch_gather_kernel<uint32_t, 8, false><<<grid, 256, 0, s>>>(p);
     if (err == cudaSuccess) err = cudaGetLastError();
     if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "gather kernel launch failed: %s", cudaGetErrorString(err));
