@@ -61,22 +61,64 @@ class RolloutBuffer:
             getattr(self, "returns", None), getattr(self, "advantages", None))
         return self.returns, self.advantages
 
-    def shared_buffer_views(self) -> Dict[str, torch.Tensor]:
-        """Zero-copy views with the reference's SharedReplayBuffer names and axis order
-        (shared_buffer.py:45-76).  ``share_obs`` is ``obs`` (state == obs for Overcooked,
-        envs/overcooked2_env.py:110); ``masks[t+1] = 1 - done[t]`` is returned for t >= 0
-        (masks[0] belongs to the previous rollout, shared_buffer.py:222-232)."""
+    def shared_buffer_views(self, hidden_size: int = 64, recurrent_N: int = 1) -> Dict[str, torch.Tensor]:
+        """All 13 tensors of the reference's ``SharedReplayBuffer`` (train/MAPPO/utils/shared_buffer.py:45-76), with its
+        names, shapes and axis order ``[T(+1), N, P, ...]``, as views of this buffer — nothing is copied except the
+        [T+1, N] mask plane.  Field by field, as ``MainPlayer.collect_episode`` + ``chooseinsert`` leave them
+        (main_player.py:91-112,211-261, shared_buffer.py:115-148):
+
+        * ``obs`` / ``share_obs``  [T+1,N,P,W,H,C]  the int8 planes (the reference stores two fp32 copies; state == obs,
+          envs/overcooked2_env.py:110).  Slot T is the observation after the last step, which the reference only reads
+          for the bootstrap value (main_player.py:289-293).
+        * ``actions`` / ``action_log_probs`` / ``rewards``  [T,N,P,1]; ``value_preds`` [T+1,N,P,1] (slot T = bootstrap
+          value; the reference computes it in ``compute`` instead of storing it).
+        * ``masks`` [T+1,N,P,1]: ``masks[t+1] = 1 - done[t]``; ``masks[0] = 1`` as ``reset_after_update`` leaves it
+          (shared_buffer.py:240-245; MainPlayer.train calls it after every update).
+        * ``bad_masks`` / ``active_masks`` all ones (no time-limit bookkeeping; both seats act every step),
+          ``available_actions`` all ones [T+1,N,P,6] (overcooked2_env.py:64), ``rnn_states`` / ``rnn_states_critic``
+          zeros [T+1,N,P,recurrent_N,hidden] (feed-forward policies) — broadcast views of one scalar.
+        * ``returns`` [T+1,N,P,1]: filled by ``compute_returns`` (zeros before).
+        ``masks_next`` (= ``masks[1:]``) is kept for callers of the first version of this method."""
+        T, N, P, dev = self.T, self.N, self.P, self.obs.device
         sw = lambda t: None if t is None else t.transpose(1, 2)  # [*, P, N, ...] -> [*, N, P, ...]
+        col = lambda t: None if t is None else sw(t).unsqueeze(-1)
         obs = sw(self.obs)
-        not_done = (1 - self.dones).to(torch.float32)  # [T, N]
+        masks = torch.ones((T + 1, N), dtype=torch.float32, device=dev)
+        torch.sub(1.0, self.dones, out=masks[1:])
+        masks = masks[:, :, None, None].expand(T + 1, N, P, 1)
+        one = torch.ones((), dtype=torch.float32, device=dev)
+        zero = torch.zeros((), dtype=torch.float32, device=dev)
+        returns = getattr(self, "returns", None)
         return {
             "obs": obs, "share_obs": obs,
-            "actions": sw(self.actions).unsqueeze(-1),
-            "action_log_probs": None if self.action_log_probs is None else sw(self.action_log_probs).unsqueeze(-1),
-            "value_preds": None if self.value_preds is None else sw(self.value_preds).unsqueeze(-1),
-            "rewards": sw(self.rewards).unsqueeze(-1),
-            "masks_next": not_done[:, :, None, None].expand(self.T, self.N, self.P, 1),
+            "rnn_states": zero.expand(T + 1, N, P, recurrent_N, hidden_size),
+            "rnn_states_critic": zero.expand(T + 1, N, P, recurrent_N, hidden_size),
+            "value_preds": col(self.value_preds),
+            "returns": col(returns) if returns is not None else zero.expand(T + 1, N, P, 1),
+            "available_actions": one.expand(T + 1, N, P, 6),
+            "actions": col(self.actions),
+            "action_log_probs": col(self.action_log_probs),
+            "rewards": col(self.rewards),
+            "masks": masks, "bad_masks": one.expand(T + 1, N, P, 1), "active_masks": one.expand(T + 1, N, P, 1),
+            "masks_next": masks[1:],
         }
+
+    def fill_shared_replay_buffer(self, shared_buffer):
+        """Copy this rollout into an instance of the reference's ``SharedReplayBuffer`` (or anything with its 13 tensor
+        attributes), casting to its fp32 storage, so that the reference's ``compute_returns`` /
+        ``feed_forward_generator`` / ``R_MAPPO.train`` (shared_buffer.py:248-366, r_mappo.py:166-224) consume a
+        device-collected rollout unchanged.  One ``copy_`` per field; the buffer must be ``[T(+1), N, P, ...]``."""
+        views = self.shared_buffer_views(int(shared_buffer.rnn_states.shape[-1]), int(shared_buffer.rnn_states.shape[-2]))
+        for name in ("share_obs", "obs", "rnn_states", "rnn_states_critic", "value_preds", "returns", "available_actions",
+                     "actions", "action_log_probs", "rewards", "masks", "bad_masks", "active_masks"):
+            dst, src = getattr(shared_buffer, name, None), views[name]
+            if dst is None or src is None:
+                continue
+            if tuple(dst.shape) != tuple(src.shape):
+                raise ValueError("SharedReplayBuffer.%s is %s, this rollout gives %s" % (name, tuple(dst.shape), tuple(src.shape)))
+            dst.copy_(src)
+        shared_buffer.step = 0
+        return shared_buffer
 
 
 class PolicyRollout:
@@ -150,14 +192,14 @@ class PolicyRollout:
             self.seed, stream))
 
     def prime(self):
-        """slot 0 <- observation of the current state (first rollout) or the last slot of the
-        previous rollout (SharedReplayBuffer.after_update, shared_buffer.py:222-226)"""
+        """slot 0 <- observation of the env's CURRENT state.  Always re-observed (one cheap launch): the env may have
+        moved between two rollouts (``n_reset``, ``set_state``, another ``n_step`` / rollout on the same handle), and
+        copying the previous rollout's last slot (SharedReplayBuffer.after_update, shared_buffer.py:222-226) would then
+        pair a stale obs[0] with actions and values computed from the new state.  When nothing moved the result is the
+        same bytes as that copy."""
         with torch.cuda.device(self.env.sim_device):
-            if not self._primed:
-                _native.check(self._lib.ocb_observe(self.env._h, _ptr(self.buf.obs[0]), self.env._stream()))
-                self._primed = True
-            else:
-                self.buf.obs[0].copy_(self.buf.obs[self.T])
+            _native.check(self._lib.ocb_observe(self.env._h, _ptr(self.buf.obs[0]), self.env._stream()))
+            self._primed = True
 
     def collect(self, deterministic: bool = False) -> RolloutBuffer:
         """One T-step rollout, asynchronous on torch's current stream."""

@@ -1,10 +1,12 @@
 """Import shim for the UNMODIFIED Python reference (test infrastructure only).
 
-Only usable where ``/root/reference`` exists (the build container); the GPU box does
-not have it, so nothing under ``tests -m gpu``, ``smoke()`` or ``bench.py`` may call
-this.  It is used by ``tests/golden/make_golden.py`` to generate the committed golden
-vectors and by the optional ``-m "not gpu"`` tests that pin the oracle restatement
-against the live reference.
+The reference is looked up at ``/root/reference`` (the build container) and, failing
+that, at ``baseline/_ref`` — the verbatim, git-ignored install made by
+``tools/install_reference.py`` that travels to the GPU box with the tree.  Nothing reads
+``/root/reference`` at run time on the GPU box.  Users: ``tests/golden/make_*.py``
+(golden vectors), the ``reference``-marked tests (oracle restatement and the CUDA path
+against the live reference classes, trainers included) and the reference arm of
+``bench.py``.  The product package never imports this module.
 
 The reference imports ``gym`` (not installed) and the compiled Madrona modules
 (``build.madrona_*``, not buildable offline); neither is touched by the pure-Python
@@ -15,7 +17,21 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("OCB_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+INSTALLED_ROOT = os.path.abspath(os.path.join(_HERE, "..", "baseline", "_ref"))
+
+
+def _resolve_root() -> str:
+    env = os.environ.get("OCB_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", INSTALLED_ROOT):
+        if os.path.isfile(os.path.join(cand, "envs", "overcooked2_reimplement.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def available() -> bool:
@@ -53,6 +69,10 @@ def _install_stubs():
         gym.vector = vector
         sys.modules.update({"gym": gym, "gym.spaces": spaces, "gym.vector": vector,
                             "gym.vector.vector_env": vector_env})
+    if "shutup" not in sys.modules:  # train/testing.py:1 silences warnings with it; not installed here
+        sh = types.ModuleType("shutup")
+        sh.please = lambda: None
+        sys.modules["shutup"] = sh
     if "build" not in sys.modules:
         b = types.ModuleType("build")
         b.__path__ = []
@@ -104,3 +124,24 @@ def load_policy():
             sys.path.insert(0, p)
     from MAPPO.r_actor_critic import R_Actor, R_Critic  # noqa
     return R_Actor, R_Critic
+
+
+def load_trainers():
+    """The reference's rollout-side trainer classes, imported unmodified (train/ uses script-style absolute imports):
+    MainPlayer (train/MAPPO/main_player.py), CentralizedAgent / CentralizedMultiAgent / DecentralizedAgent
+    (train/partner_agents.py), run_sim (train/testing.py:39-59), XDPlayer (train/XD/xd_player.py),
+    SharedReplayBuffer (train/MAPPO/utils/shared_buffer.py), get_config (train/config.py)."""
+    ns = load()
+    from MAPPO.main_player import MainPlayer  # noqa
+    from MAPPO.utils.shared_buffer import SharedReplayBuffer  # noqa
+    from MAPPO.rMAPPOPolicy import R_MAPPOPolicy, rMAPPOWrapper  # noqa
+    from partner_agents import CentralizedAgent, CentralizedMultiAgent, DecentralizedAgent  # noqa
+    from XD.xd_player import XDPlayer  # noqa
+    from XD.MCPolicy import MCPolicy  # noqa
+    from config import get_config  # noqa
+    import testing  # noqa
+    ns.MainPlayer, ns.SharedReplayBuffer = MainPlayer, SharedReplayBuffer
+    ns.R_MAPPOPolicy, ns.rMAPPOWrapper = R_MAPPOPolicy, rMAPPOWrapper
+    ns.CentralizedAgent, ns.CentralizedMultiAgent, ns.DecentralizedAgent = CentralizedAgent, CentralizedMultiAgent, DecentralizedAgent
+    ns.XDPlayer, ns.MCPolicy, ns.get_config, ns.run_sim = XDPlayer, MCPolicy, get_config, testing.run_sim
+    return ns
