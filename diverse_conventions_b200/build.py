@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(HERE, "libocb.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "--threads", "0",
     "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
 ]
 

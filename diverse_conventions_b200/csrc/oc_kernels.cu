@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, (G == 8 ? 6 : 4)) oc_rollout_k
     const bool use_rng = prm.actions == nullptr;
     const bool want_obs = prm.obs != nullptr;
     ActionRng<P> rng;
-    unsigned long long t = prm.step0;
+    unsigned long long t = prm.step0_dev != nullptr ? *prm.step0_dev : prm.step0;
     const uint32_t gworld = prm.world0 + (uint32_t)nl;
     if (use_rng && (t % ActionRng<P>::kStepsPerBlock) != 0) rng.refill(prm.seed, gworld, t);
 
@@ -292,7 +292,7 @@ __global__ void oc_export_state_kernel(const Tables* __restrict__ tables, const 
 
 // counts (through *bad) the worlds holding a state the CUDA path does not represent:
 // out-of-range fields, objects on cells that cannot hold one, a pot holding anything but
-// a soup, a cooking soup outside a pot, a player off the AIR cells.
+// a soup, a cooking soup outside a pot, a player off the AIR cells, two players on one cell.
 __global__ void oc_import_state_kernel(const Tables* __restrict__ tables, const int32_t* in, uint32_t* players,
                                        uint16_t* objs, int32_t* timestep, int32_t* cur_return, int N, int* bad) {
     const int P = tables->P, S = tables->S, L = 1 + 6 * P + 4 * S;
@@ -315,6 +315,7 @@ __global__ void oc_import_state_kernel(const Tables* __restrict__ tables, const 
                 const uint32_t h = pl[2] ? obj_make(pl[2], pl[3], pl[4], pl[5]) : 0u;
                 players[(size_t)i * N + n] = player_pack(pl[0], pl[1], h);
             }
+            for (int j = 0; ok && j < i; ++j) ok = row[1 + 6 * j] != pl[0];  // unreachable in the MDP (collision rule)
         }
         for (int cell = 0; cell < S; ++cell) {
             const int32_t* oc = row + 1 + 6 * P + 4 * cell;
@@ -332,6 +333,15 @@ __global__ void oc_import_state_kernel(const Tables* __restrict__ tables, const 
         cur_return[n] = 0;
         if (!ok) atomicAdd(bad, 1);
     }
+}
+
+// device step counter += k as a launch of its own: used after launches that READ the counter at their start
+// (graph-captured rollouts), where an in-kernel increment by one CTA would race with late-starting CTAs
+__global__ void oc_counter_add_kernel(unsigned long long* ctr, unsigned long long k) { *ctr += k; }
+
+cudaError_t launch_counter_add(unsigned long long* counter, unsigned long long k, cudaStream_t stream) {
+    oc_counter_add_kernel<<<1, 1, 0, stream>>>(counter, k);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ launchers

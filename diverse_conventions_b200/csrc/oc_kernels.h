@@ -24,7 +24,9 @@ struct RolloutParams {
     int32_t* episodes;   // [N] completed episodes
     int N;
     int K;
-    unsigned long long step0;  // global step counter of the first step of this launch
+    unsigned long long step0;  // global step counter of the first step of this launch (host mirror)
+    const unsigned long long* step0_dev;  // when set, the launch reads its first step from the device counter instead
+                                          // (launches captured into a CUDA graph: replays must not reuse step0)
     unsigned long long seed;
     unsigned int world0;  // global index of world 0 (multi-GPU shards draw disjoint streams)
     const void* actions;  // [K][P][N] or nullptr -> on-device RNG
@@ -41,6 +43,7 @@ size_t rollout_smem_bytes(int P, int S, int C, int G, int warps_per_cta);
 
 cudaError_t launch_rollout(const RolloutParams& prm, int P, int G, int warps_per_cta, size_t smem_bytes,
                            bool observe_only, cudaStream_t stream);
+cudaError_t launch_counter_add(unsigned long long* counter, unsigned long long k, cudaStream_t stream);
 cudaError_t launch_reset(const Tables* tables, uint32_t* players, uint16_t* objs, int32_t* timestep, int32_t* cur_return,
                          int N, int rows, cudaStream_t stream);
 cudaError_t launch_export_state(const Tables* tables, const uint32_t* players, const uint16_t* objs,

@@ -67,6 +67,9 @@ inline int build_tables(const ocb_config* cfg, Tables* tb, uint8_t* tmpl, char* 
         if (x < 0 || x >= W || y < 0 || y >= H || cfg->terrain[y * W + x] != T_AIR)
             OCB_TABLE_FAIL(OCB_ERR_BAD_LAYOUT, "player %d start (%d,%d) is not a walkable cell", i, x, y);
         tb->start_pos[i] = y * W + x;
+        for (int j = 0; j < i; ++j)  // the MDP never puts two players on one cell (reimplement.py:356-366); the plane update assumes it
+            if (tb->start_pos[j] == tb->start_pos[i])
+                OCB_TABLE_FAIL(OCB_ERR_BAD_LAYOUT, "players %d and %d start on the same cell (%d,%d)", j, i, x, y);
     }
     // static part of the encoding (setup_base_observation, reimplement.py:165-171) in (W,H,C) order
     memset(tmpl, 0, (size_t)S * C);

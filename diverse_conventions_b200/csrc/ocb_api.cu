@@ -33,7 +33,8 @@ struct ocb_env {
     int device;
     int N, P, S, C, SC, L;
     uint64_t seed;
-    uint64_t step_count;
+    uint64_t step_count;   // host mirror of *d_step_counter
+    bool count_stale;      // launches were captured into a CUDA graph: replays advance only the device counter
     uint32_t world0;
     int lanes_per_world;  // G of the fused K-step launches
     int step_lanes;       // G of single-step / observe launches (load + full rebuild dominate there)
@@ -202,7 +203,35 @@ extern "C" int ocb_num_players(const ocb_env* e) { return e ? e->P : fail(OCB_ER
 extern "C" int ocb_obs_channels(const ocb_env* e) { return e ? e->C : fail(OCB_ERR_INVALID_ARG, "env is NULL"); }
 extern "C" int ocb_obs_bytes_per_agent(const ocb_env* e) { return e ? e->SC : fail(OCB_ERR_INVALID_ARG, "env is NULL"); }
 extern "C" int ocb_state_ints_per_world(const ocb_env* e) { return e ? e->L : fail(OCB_ERR_INVALID_ARG, "env is NULL"); }
-extern "C" uint64_t ocb_step_count(const ocb_env* e) { return e ? e->step_count : 0; }
+// host mirror <- device counter after graph replays (synchronises the device once; no-op otherwise)
+static int resync_step_count(ocb_env* e) {
+    if (!e->count_stale) return OCB_OK;
+    DeviceGuard guard(e->device);
+    unsigned long long v = 0;
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err == cudaSuccess) err = cudaMemcpy(&v, e->d_step_counter, sizeof(v), cudaMemcpyDeviceToHost);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OCB_ERR_CUDA, "step counter resync: %s", cudaGetErrorString(err));
+    }
+    e->step_count = v;
+    e->count_stale = false;
+    return OCB_OK;
+}
+static bool stream_capturing(void* stream) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing((cudaStream_t)stream, &cs) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return cs != cudaStreamCaptureStatusNone;
+}
+
+extern "C" uint64_t ocb_step_count(const ocb_env* e) {
+    if (e == nullptr) return 0;
+    if (e->count_stale) resync_step_count(const_cast<ocb_env*>(e));  // the device counter is the source of truth
+    return e->step_count;
+}
 
 extern "C" int ocb_set_tuning(ocb_env* e, int lanes_per_world, int use_tma) {
     if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "env is NULL");
@@ -259,7 +288,16 @@ static int run_rollout(ocb_env* e, int K, const void* actions, int act_dtype, in
     if (K < 0) return fail(OCB_ERR_INVALID_ARG, "K must be >= 0");
     if (act_dtype < OCB_ACT_I32 || act_dtype > OCB_ACT_U8) return fail(OCB_ERR_INVALID_ARG, "unknown action dtype %d", act_dtype);
     DeviceGuard guard(e->device);
+    // The first step of the launch keys the action RNG.  Normally it comes from the host mirror; a launch that is being
+    // captured into a CUDA graph reads it from the device counter instead (every replay continues the stream) and the
+    // counter is advanced by a launch of its own; the host mirror is resynchronised at the next uncaptured call.
+    const bool capturing = !observe_only && stream_capturing(stream);
+    if (!capturing && !observe_only && e->count_stale) {
+        const int src = resync_step_count(e);
+        if (src != OCB_OK) return src;
+    }
     RolloutParams p = base_params(e);
+    if (capturing) p.step0_dev = e->d_step_counter, p.step_counter = nullptr;
     p.K = K, p.actions = actions, p.act_dtype = act_dtype, p.actions_out = actions_out;
     p.obs = obs, p.rew = rew, p.done = done;
     int warps;
@@ -274,7 +312,16 @@ static int run_rollout(ocb_env* e, int K, const void* actions, int act_dtype, in
         cudaGetLastError();
         return fail(OCB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));
     }
-    if (!observe_only) e->step_count += (uint64_t)K;
+    if (capturing) {
+        err = launch_counter_add(e->d_step_counter, (unsigned long long)K, (cudaStream_t)stream);
+        if (err != cudaSuccess) {
+            cudaGetLastError();
+            return fail(OCB_ERR_CUDA, "counter launch failed: %s", cudaGetErrorString(err));
+        }
+        e->count_stale = true;  // the capture itself executes nothing
+    } else if (!observe_only) {
+        e->step_count += (uint64_t)K;
+    }
     return OCB_OK;
 }
 
@@ -491,7 +538,46 @@ extern "C" int ocb_rollout_policy_fused(ocb_env* e, ocb_policy* pol, int T, int 
                                                    reinterpret_cast<const uint64_t*>(e->d_step_counter),
                                                    reinterpret_cast<uint64_t*>(e->d_step_counter), stream);
     if (rc != OCB_OK) return rc;
-    e->step_count += (uint64_t)T;
+    if (stream_capturing(stream))
+        e->count_stale = true;
+    else
+        e->step_count += (uint64_t)T;
+    return OCB_OK;
+}
+
+// Diagnostic twin of ocb_rollout_policy_fused: the same launch with the instrumented build of the kernel.  h_trace
+// (HOST int64 [n_steps][64]) receives clock64 stamps of CTA 0 for steps u0 .. u0 + n_steps - 1 (event indices: see
+// trace_ev in policy_kernels.cu).  Synchronous.
+extern "C" int ocb_rollout_fused_debug_trace(ocb_env* e, ocb_policy* pol, int T, int policy_index, int8_t* obs_slab,
+                                             int32_t* actions, float* logp, float* values, int32_t* reward, int32_t* done,
+                                             uint64_t seed, int64_t* h_trace, int u0, int n_steps) {
+    if (e == nullptr || pol == nullptr || h_trace == nullptr || n_steps < 1) return fail(OCB_ERR_INVALID_ARG, "NULL handle / trace");
+    if (e->P != 2) return fail(OCB_ERR_UNSUPPORTED, "the policy rollout supports 2 players");
+    DeviceGuard guard(e->device);
+    long long* d_trace = nullptr;
+    const size_t bytes = (size_t)n_steps * 64 * sizeof(long long);
+    cudaError_t err = cudaMalloc(&d_trace, bytes);
+    if (err == cudaSuccess) err = cudaMemset(d_trace, 0, bytes);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OCB_ERR_CUDA, "ocb_rollout_fused_debug_trace: %s", cudaGetErrorString(err));
+    }
+    RolloutParams p = base_params(e);
+    const int rc = ocb_policy_rollout_fused_launch(pol, policy_index, p, e->h_tables.W, e->h_tables.H, T, obs_slab, actions, logp,
+                                                   values, reward, done, 0, seed,
+                                                   reinterpret_cast<const uint64_t*>(e->d_step_counter),
+                                                   reinterpret_cast<uint64_t*>(e->d_step_counter), nullptr, d_trace, u0, n_steps);
+    if (rc == OCB_OK) {
+        e->step_count += (uint64_t)T;
+        err = cudaDeviceSynchronize();
+        if (err == cudaSuccess) err = cudaMemcpy(h_trace, d_trace, bytes, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_trace);
+    if (rc != OCB_OK) return rc;
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OCB_ERR_CUDA, "ocb_rollout_fused_debug_trace: %s", cudaGetErrorString(err));
+    }
     return OCB_OK;
 }
 

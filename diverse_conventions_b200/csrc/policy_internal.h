@@ -11,7 +11,8 @@
 int ocb_policy_rollout_fused_launch(ocb_policy* pol, int policy_index, const ocb::RolloutParams& envp, int env_w, int env_h, int T,
                                     int8_t* obs_slab, int32_t* actions, float* logp, float* values, int32_t* reward,
                                     int32_t* done, int deterministic, uint64_t seed, const uint64_t* d_offset,
-                                    uint64_t* d_counter, void* stream);
+                                    uint64_t* d_counter, void* stream, long long* d_trace = nullptr, int trace_u0 = 0,
+                                    int trace_n = 0);
 
 // number of (actor, critic) weight sets the handle holds
 int ocb_policy_num_sets(const ocb_policy* pol);

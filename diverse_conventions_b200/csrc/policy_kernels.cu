@@ -81,7 +81,8 @@ struct BlobLayout {
     int wc_hi, wc_lo;    // [32 x 144] bf16 canonical, 9216 B each
     int bias1;           // [npos][32] fp32 (conv bias + static terrain contribution)
     int b1, b2;          // [64] fp32
-    int wh, bh;          // [8][64] fp32 (rows >= head_out are zero), [8] fp32
+    int wh, bh;          // head weights fp32, 2 KB: actor [64][8] (hidden-major: unit i -> 6 logit weights + 2 zeros, two
+                         // 16-byte loads per unit), critic [64] contiguous; bh [8] fp32
     int head_bytes;      // everything above (multiple of 128)
     int chunks;          // npos FC1 chunks + 2 FC2 chunks (K halves)
     int total;
@@ -128,6 +129,8 @@ struct PolicyParams {
     int pair_ring;            // same for policy_pair_kernel (chunks of both networks)
     int stage_stride;         // words per row of the loader staging buffer (odd)
     long long* prof;          // diagnostic build: [ctas][4 roles][PW_COUNT] stall cycles
+    long long* trace;         // diagnostic build of the fused rollout: [trace_n steps][kTraceEvents] clock64 stamps of CTA 0
+    int trace_u0, trace_n;    // first traced virtual tile (step) and number of traced steps
 };
 
 // shared-memory carve-up (byte offsets from a 128-byte aligned base)
@@ -239,6 +242,20 @@ __device__ __forceinline__ void mbar_wait_p(uint32_t mbar, uint32_t parity, long
 // stall accounts written by ocb_policy_debug_profile: per CTA, per role, [0] = total cycles of the role
 enum : int { PW_TOTAL = 0, PW_COL_EMPTY, PW_HEAD_FULL, PW_COL_FULL, PW_A2_FULL, PW_W_FULL, PW_D1_FULL, PW_D2_FULL,
              PW_A2_EMPTY, PW_D3_FULL, PW_HEAD_EMPTY, PW_W_EMPTY, PW_ISSUE_CONV, PW_ISSUE_FC, PW_LDG, PW_COUNT = 16 };
+
+// event trace of the fused rollout (ocb_rollout_fused_debug_trace): one clock64 stamp per (step, event) of CTA 0.
+// Events: 0 env got actions | 1 env stepped | 2 env planes free | 3 env planes published | 8 loader sees planes |
+// 9 loader first column done | 10 loader last column done | 16+p conv p issued | 24+j FC item j of the actor issued |
+// 32+p epilogue (actor group) sees conv p | 40+j epilogue published item j | 48 D2 seen | 49 D3 seen | 50 head done |
+// 51 actions handed to the env | 52 critic group sees D3 | 53 critic head done
+constexpr int kTraceEvents = 64;
+template <bool kProf>
+__device__ __forceinline__ void trace_ev(const PolicyParams& prm, int vt, int ev) {
+    if (kProf && prm.trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+        const int s = vt - prm.trace_u0;
+        if (s >= 0 && s < prm.trace_n && ev < kTraceEvents) prm.trace[s * kTraceEvents + ev] = clock64();
+    }
+}
 
 // global -> shared bulk copy that completes `bytes` of transaction count on `mbar`
 __device__ __forceinline__ void bulk_g2s(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
@@ -550,8 +567,16 @@ __device__ __forceinline__ void mma_role(long long* pw, const PolicyParams& prm,
 // FixedCategorical(logits): sample / mode and log-prob (train/MAPPO/utils/distributions.py:14-28)
 // `store` indexes the output arrays, `rng_row` keys the sampling counter (they differ in the fused
 // rollout, where a step's outputs land at step * rows + row); returns the action
+// the 32 random bits that sample the action of (row, step): Philox4x32-10, counter (row, offset lo, offset hi, tag)
+__device__ __forceinline__ uint32_t policy_draw(const PolicyParams& prm, uint32_t rng_row, unsigned long long offset) {
+    const uint32_t grow = rng_row + (rng_row < prm.rng_rows_per_seat ? prm.rng_add0 : prm.rng_add1);
+    uint32_t r[4] = {grow, (uint32_t)offset, (uint32_t)(offset >> 32), 0x5A17u};
+    philox4x32_10(r, (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
+    return r[0];
+}
+// `drawn` (optional): policy_draw of this row, computed by the caller while it was waiting for the accumulator
 __device__ __forceinline__ int emit_actor_row(const PolicyParams& prm, long long store, uint32_t rng_row, const float (&head)[6],
-                                              unsigned long long offset, bool force_sample = false) {
+                                              unsigned long long offset, bool force_sample = false, const uint32_t* drawn = nullptr) {
     if (prm.logits) {
 #pragma unroll
         for (int a = 0; a < 6; ++a) prm.logits[store * 6 + a] = head[a];
@@ -579,10 +604,8 @@ __device__ __forceinline__ int emit_actor_row(const PolicyParams& prm, long long
 #pragma unroll
             for (int a = 1; a < 6; ++a) act = (head[a] > head[act]) ? a : act;
         } else {
-            const uint32_t grow = rng_row + (rng_row < prm.rng_rows_per_seat ? prm.rng_add0 : prm.rng_add1);
-            uint32_t r[4] = {grow, (uint32_t)offset, (uint32_t)(offset >> 32), 0x5A17u};
-            philox4x32_10(r, (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
-            const float uu = (float)(r[0] >> 8) * (1.0f / 16777216.0f) * sum;
+            const uint32_t r0 = drawn != nullptr ? *drawn : policy_draw(prm, rng_row, offset);
+            const float uu = (float)(r0 >> 8) * (1.0f / 16777216.0f) * sum;
             float cum = 0.0f;
             act = 5;  // inverse CDF; falls through to the last action on round-off
             bool found = false;
@@ -601,6 +624,39 @@ __device__ __forceinline__ int emit_actor_row(const PolicyParams& prm, long long
         }
     }
     return act;
+}
+
+// head (64 -> 6 logits | 1 value) over 32 hidden units [i0, i0 + 32): h = relu(acc + b2), head += h * W.  The weights
+// are read as 16-byte broadcast loads (actor: [64][8] hidden-major, critic: [64]); fp32 FMAs on CUDA cores.
+__device__ __forceinline__ void head_accumulate(int net, const float (&v)[32], const float* b2, const float* s_wh, int i0,
+                                                float (&head)[6]) {
+    const float4* b4 = reinterpret_cast<const float4*>(b2);
+    if (net == 0) {
+        const float4* w4 = reinterpret_cast<const float4*>(s_wh) + 2 * i0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 b = b4[q];
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = 4 * q + k;
+                const float h = fmaxf(v[i] + bb[k], 0.0f);
+                const float4 wa = w4[2 * i], wb = w4[2 * i + 1];
+                head[0] = fmaf(h, wa.x, head[0]), head[1] = fmaf(h, wa.y, head[1]), head[2] = fmaf(h, wa.z, head[2]);
+                head[3] = fmaf(h, wa.w, head[3]), head[4] = fmaf(h, wb.x, head[4]), head[5] = fmaf(h, wb.y, head[5]);
+            }
+        }
+    } else {
+        const float4* w4 = reinterpret_cast<const float4*>(s_wh + i0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 b = b4[q], w = w4[q];
+            head[0] = fmaf(fmaxf(v[4 * q + 0] + b.x, 0.0f), w.x, head[0]);
+            head[0] = fmaf(fmaxf(v[4 * q + 1] + b.y, 0.0f), w.y, head[0]);
+            head[0] = fmaf(fmaxf(v[4 * q + 2] + b.z, 0.0f), w.z, head[0]);
+            head[0] = fmaf(fmaxf(v[4 * q + 3] + b.w, 0.0f), w.w, head[0]);
+        }
+    }
 }
 
 // epilogue: TMEM -> bias/ReLU -> bf16 hi/lo A operand; head, sampling and outputs.  Two groups of four
@@ -669,12 +725,7 @@ __device__ __forceinline__ void epilogue_role(long long* pw, const PolicyParams&
         {
             float v[32];
             tmem_ld32(trow + kColD2 + (u & 1) * kHid + eg * 32, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float h = fmaxf(v[i] + s_b2[eg * 32 + i], 0.0f);
-#pragma unroll
-                for (int a = 0; a < 6; ++a) head[a] = fmaf(h, s_wh[a * kHid + eg * 32 + i], head[a]);
-            }
+            head_accumulate(ur.net, v, s_b2 + eg * 32, s_wh, eg * 32, head);
         }
         tc_fence_before();
         mbar_arrive(bars + 8 * (B_HEAD_EMPTY + (u & 1)));  // done with the head block of this unit
@@ -783,6 +834,8 @@ constexpr int kPColD1 = 192;   // conv accumulators: stage s at + 64 s (actor 32
 constexpr int kPColA2 = 320;   // A operand of net g at + 32 g (hi 16 | lo 16)
 constexpr int kPColD2 = 384;   // FC1 accumulator of net g at + 64 g
 constexpr int kPMaxRing = 24;  // weight-ring slots (chunks of both networks)
+constexpr int kWarpFc = kWarpProd + 1;          // warps 18, 19: FC issuers of the actor / the critic
+constexpr int kPThreads = 32 * (kWarpFc + 2);   // 640: 8 epilogue + 8 loader + conv issuer + producer + 2 FC issuers
 constexpr int kPConvBytes = 9216;  // one network's conv weights, hi or lo
 constexpr int kPRestOff = 4 * kPConvBytes;  // per-network remainder of the head (bias1 .. bh) starts here
 enum : int {
@@ -798,7 +851,8 @@ enum : int {
     PB_HEAD_EMPTY = 21,         // [2] by tile parity: MMA commit + 256 epilogue arrivals -> producer
     PB_W_FULL = 24,             // [24] bulk copy complete_tx -> MMA
     PB_W_EMPTY = 48,            // [24] MMA commit -> producer
-    PB_COUNT = 72,
+    PB_D1_EMPTY = 72,           // [2] both epilogue groups (256 arrivals) -> conv issuer: stage has been read
+    PB_COUNT = 74,
     PB_TMEM_SLOT = 120          // 8-byte slot index that holds the TMEM base address
 };
 
@@ -822,11 +876,13 @@ __device__ __forceinline__ void pair_producer_role(long long* pw, const PolicyPa
                                                    uint32_t s_head, uint32_t s_wring, uint32_t bars) {
     const int R = prm.pair_ring, nch = 2 * L.chunks;
     const bool resident = R >= nch;
+    const bool static_w = resident && prm.tile_policy == nullptr;  // nothing to do after the first tile (pair_fc_role)
     const int Reff = resident ? nch : R;
     const uint32_t rest = (uint32_t)(L.head_bytes - L.bias1);
     uint32_t u = 0, round = 0;
     int slot = 0;
     for (int t = t0; t < t1; ++t, ++u) {
+        if (static_w && u > 0) break;
         const bool chg = blob_changed(prm, t, t0);
         const uint8_t* blob_a = prm.blobs + (size_t)tile_pol(prm, t) * 2 * prm.blob_stride;
         const uint8_t* blob_c = blob_a + prm.blob_stride;
@@ -847,7 +903,7 @@ __device__ __forceinline__ void pair_producer_role(long long* pw, const PolicyPa
         const bool load = !resident || chg;
         for (int j = 0; j < L.chunks; ++j) {
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {  // consumption order of pair_mma_role: (actor, j), (critic, j)
+            for (int g = 0; g < 2; ++g) {  // ring order: (actor, j), (critic, j) -> pair_fc_role g takes every other chunk
                 if (round > 0) mbar_wait_p<kProf>(bars + 8 * (PB_W_EMPTY + slot), (round - 1) & 1, pw[PW_W_EMPTY]);
                 if (load) {
                     if (elect_one()) {
@@ -863,42 +919,46 @@ __device__ __forceinline__ void pair_producer_role(long long* pw, const PolicyPa
     }
 }
 
+// MMA issue is split over THREE single-lane issuers (round 2; tools/fused_trace.py showed the one-warp issuer of round 1
+// spending ~2/3 of a conv position in its own serial code — waits, fences, commits — with the tensor pipe idle):
+//   * the conv warp streams the 18 MMAs of every conv position, gated only by the grid columns (loaders) and by the
+//     accumulator stage having been read by both epilogue groups (PB_D1_EMPTY), so it runs up to two positions ahead;
+//   * FC warp g issues the FC1 partial products and the two FC2 halves of network g as soon as epilogue group g has
+//     published their A operand; the two networks no longer wait for each other.
+// tcgen05.mma from different warps of a CTA execute in issue order; the three streams touch disjoint accumulators and
+// every cross-stream dependency is an mbarrier.
 template <bool kProf>
-__device__ __forceinline__ void pair_mma_role(long long* pw, const PolicyParams& prm, int t0, int t1, const BlobLayout L, uint32_t tmem,
-                                              uint32_t a_head, uint32_t a_wring, uint32_t bars) {
+__device__ __forceinline__ void pair_conv_role(long long* pw, const PolicyParams& prm, int t0, int t1, const BlobLayout L, uint32_t tmem,
+                                               uint32_t a_head, uint32_t bars) {
     const int W = prm.W, H = prm.H, PH = H - 2, npos = prm.npos;
-    const int R = prm.pair_ring, nch = 2 * L.chunks;
-    const bool resident = R >= nch;
-    const int Reff = resident ? nch : R;
-    const uint32_t idesc = make_idesc(kRows, kHid);  // N = 64 for the pair conv and for the FC layers
+    const uint32_t idesc = make_idesc(kRows, kHid);  // N = 64: actor channels 0-31 | critic channels 32-63
     const uint32_t a_wchi = a_head, a_wclo = a_head + 2 * kPConvBytes;
     uint32_t gcb = 0;            // running column index of grid column 0 of the tile
-    uint32_t item_par = 0;       // phase parity bit of the A stage per network (items issued so far, mod 2)
-    int slot = 0;
-    uint32_t wround = 0, head_gen = 0, w_gen = 0, u = 0;
+    uint32_t head_gen = 0, u = 0;
+    uint32_t uses[2] = {0, 0};   // conv positions issued into each accumulator stage so far
 
     for (int t = t0; t < t1; ++t, ++u, gcb += W) {
-        const bool chg = blob_changed(prm, t, t0);
-        if (chg) {
+        if (blob_changed(prm, t, t0)) {
             mbar_wait_p<kProf>(bars + 8 * PB_HEAD_FULL, head_gen & 1, pw[PW_HEAD_FULL]);
             ++head_gen;
         }
-        const bool w_loaded = !resident || chg;
-        if (resident && w_loaded) ++w_gen;
-        int cp = 0, ox = 0, oy = 0;  // next conv position of this tile
-
-        auto conv = [&]() {
+        int ox = 0, oy = 0;
+        for (int cp = 0; cp < npos; ++cp) {
+            const int st = cp & 1;
             if (oy == 0) {  // new window column(s)
                 for (int d = (ox == 0 ? 0 : 2); d < 3; ++d) {
                     const uint32_t g = gcb + ox + d;
                     mbar_wait_p<kProf>(bars + 8 * (PB_COL_FULL + g % kColRing), (g / kColRing) & 1, pw[PW_COL_FULL]);
                 }
             }
-            // stage cp (< 2) still holds D3 of network cp of the previous tile until its head epilogue has read it
+            // both epilogue groups have loaded the previous conv position of this stage ...
+            if (uses[st] > 0) mbar_wait_p<kProf>(bars + 8 * (PB_D1_EMPTY + st), (uses[st] - 1) & 1, pw[PW_D1_FULL]);
+            // ... and stage cp (< 2) was D3 of network cp of the previous tile until its head epilogue read it
             if (u > 0 && cp < 2) mbar_wait_p<kProf>(bars + 8 * (PB_D3_EMPTY + cp), (u - 1) & 1, pw[PW_D3_FULL]);
             tc_fence_after();
-            const uint32_t d1 = tmem + kPColD1 + (cp & 1) * kHid;
+            const uint32_t d1 = tmem + kPColD1 + st * kHid;
             const long long ti0 = kProf ? clock64() : 0;
+            if (cp == 3) trace_ev<kProf>(prm, t - t0, 54);  // waits of conv 3 done, issue starts
             if (elect_one()) {
 #pragma unroll
                 for (int j = 0; j < 9; ++j) {
@@ -907,7 +967,7 @@ __device__ __forceinline__ void pair_mma_role(long long* pw, const PolicyParams&
                     umma_bf16_ts(d1, ta, make_desc(a_wchi + j * 256, 128, 2304), idesc, j > 0);
                     umma_bf16_ts(d1, ta, make_desc(a_wclo + j * 256, 128, 2304), idesc, 1);
                 }
-                umma_commit(bars + 8 * (PB_D1_FULL + (cp & 1)));
+                umma_commit(bars + 8 * (PB_D1_FULL + st));
                 if (oy == PH - 1) {  // the window leaves column ox (and the last two columns with the last window)
                     umma_commit(bars + 8 * (PB_COL_EMPTY + (gcb + ox) % kColRing));
                     if (ox == W - 3) {
@@ -920,19 +980,45 @@ __device__ __forceinline__ void pair_mma_role(long long* pw, const PolicyParams&
             }
             __syncwarp();
             if (kProf) pw[PW_ISSUE_CONV] += clock64() - ti0;
-            ++cp;
+            if (cp < 8) trace_ev<kProf>(prm, t - t0, 16 + cp);
+            ++uses[st];
             if (++oy == PH) oy = 0, ++ox;
-        };
-        // one FC item of network g: D2[g] (+)= A[g] x W1_j (j < npos)   or   D3[g] (+)= A[g] x W2_half (j >= npos)
-        auto fc = [&](int g, int j) {
-            mbar_wait_p<kProf>(bars + 8 * (PB_A2_FULL + g), (item_par >> g) & 1, pw[PW_A2_FULL]);
+        }
+    }
+}
+
+// FC issuer of network g: D2[g] (+)= A[g] x W1_j (j < npos), then D3[g] (+)= A[g] x W2_half (j = npos, npos + 1)
+template <bool kProf>
+__device__ __forceinline__ void pair_fc_role(long long* pw, const PolicyParams& prm, const int g, int t0, int t1, const BlobLayout L,
+                                             uint32_t tmem, uint32_t a_wring, uint32_t bars) {
+    const int npos = prm.npos;
+    const int R = prm.pair_ring, nch = 2 * L.chunks;
+    const bool resident = R >= nch;
+    const bool static_w = resident && prm.tile_policy == nullptr;  // one weight set for the whole launch: loaded once
+    const int Reff = resident ? nch : R;
+    const uint32_t idesc = make_idesc(kRows, kHid);
+    const uint32_t a_hi = tmem + kPColA2 + g * kA2Cols, a_lo = a_hi + 16;
+    uint32_t item = 0, u = 0, w_gen = 0, wround = 0;
+    int slot = g;              // ring slot of this network's next chunk (the producer interleaves actor / critic chunks)
+    while (slot >= Reff) slot -= Reff, ++wround;
+    uint32_t d1_uses = 0;      // conv positions that went through accumulator stage g so far (PB_D1_EMPTY phase)
+
+    for (int t = t0; t < t1; ++t, ++u) {
+        const bool chg = blob_changed(prm, t, t0);
+        const bool w_loaded = !resident || chg;
+        if (resident && w_loaded) ++w_gen;
+        d1_uses += (uint32_t)(npos + 1 - g) / 2;
+        for (int j = 0; j < npos + 2; ++j, ++item) {
+            mbar_wait_p<kProf>(bars + 8 * (PB_A2_FULL + g), item & 1, pw[PW_A2_FULL]);
+            // the first FC2 product overwrites accumulator stage g: its last conv position must have been read by BOTH groups
+            if (j == npos) mbar_wait_p<kProf>(bars + 8 * (PB_D1_EMPTY + g), (d1_uses - 1) & 1, pw[PW_D1_FULL]);
             if (w_loaded) mbar_wait_p<kProf>(bars + 8 * (PB_W_FULL + slot), resident ? ((w_gen - 1) & 1) : (wround & 1), pw[PW_W_FULL]);
             tc_fence_after();
             const uint32_t dst = tmem + (j < npos ? kPColD2 : kPColD1) + g * kHid;
             const bool first = (j == 0 || j == npos);
-            const uint32_t a_hi = tmem + kPColA2 + g * kA2Cols, a_lo = a_hi + 16;
             const uint32_t b_hi = a_wring + slot * kChunk, b_lo = b_hi + 4096;
             const long long tf0 = kProf ? clock64() : 0;
+            if (j == 2) trace_ev<kProf>(prm, t - t0, g == 0 ? 55 : 57);  // waits of FC item 2 done, issue starts
             if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
@@ -942,28 +1028,17 @@ __device__ __forceinline__ void pair_mma_role(long long* pw, const PolicyParams&
                     umma_bf16_ts(dst, a_lo + ks * 8, bhi, idesc, 1);
                 }
                 umma_commit(bars + 8 * (PB_A2_EMPTY + g));
-                umma_commit(bars + 8 * (PB_W_EMPTY + slot));
+                if (!static_w) umma_commit(bars + 8 * (PB_W_EMPTY + slot));
                 if (j == npos - 1) umma_commit(bars + 8 * (PB_D2_FULL + g));
                 if (j == npos + 1) umma_commit(bars + 8 * (PB_D3_FULL + g));
             }
             __syncwarp();
             if (kProf) pw[PW_ISSUE_FC] += clock64() - tf0;
-            item_par ^= 1u << g;
-            if (++slot == Reff) slot = 0, ++wround;
-        };
-
-        // static issue order: the conv runs two positions ahead of the FC1 partial sums (two accumulator stages);
-        // conv(p + 2) reuses the stage of position p, which both groups have drained once both FC1 items of
-        // position p could be issued
-        conv();
-        conv();
-        for (int p = 0; p < npos; ++p) {
-            fc(0, p);
-            fc(1, p);
-            if (p + 2 < npos) conv();
+            if (g == 0 && j < 8) trace_ev<kProf>(prm, t - t0, 24 + j);
+            if (g == 1 && j == 2) trace_ev<kProf>(prm, t - t0, 58);
+            slot += 2;
+            if (slot >= Reff) slot -= Reff, ++wround;
         }
-        fc(0, npos), fc(1, npos);
-        fc(0, npos + 1), fc(1, npos + 1);
     }
 }
 
@@ -983,22 +1058,30 @@ __device__ __forceinline__ void pair_epilogue_role(long long* pw, const PolicyPa
     const uint32_t a2 = trow + kPColA2 + g * kA2Cols;
 
     uint32_t u = 0, head_gen = 0, item = 0, d1_par = 0;  // d1_par: phase parity bit per conv accumulator stage
+    int trace_vt = 0, trace_item = 0;
     // bias + ReLU + hi/lo split of 32 activations -> A operand stage of this network
     auto publish = [&](float (&v)[32], const float* bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias);
+        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[i], 0.0f);
+        for (int q = 0; q < 8; ++q) {  // the conversion runs before the wait: the stage is usually still being read
+            const float4 b = b4[q];
+            split2(fmaxf(v[4 * q] + b.x, 0.0f), fmaxf(v[4 * q + 1] + b.y, 0.0f), hi[2 * q], lo[2 * q]);
+            split2(fmaxf(v[4 * q + 2] + b.z, 0.0f), fmaxf(v[4 * q + 3] + b.w, 0.0f), hi[2 * q + 1], lo[2 * q + 1]);
+        }
         if (item >= 1) {
             mbar_wait_p<kProf>(bars + 8 * (PB_A2_EMPTY + g), (item - 1) & 1, pw[PW_A2_EMPTY]);
             tc_fence_after();
         }
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+        if (kProf && warp == 0 && trace_item == 2) trace_ev<kProf>(prm, trace_vt, 60);  // A2 stage free and split done
         tmem_st16(a2, hi);
         tmem_st16(a2 + 16, lo);
         tmem_st_wait();
+        if (kProf && warp == 0 && trace_item == 2) trace_ev<kProf>(prm, trace_vt, 61);  // stores landed
         tc_fence_before();
         mbar_arrive(bars + 8 * (PB_A2_FULL + g));
+        if (kProf && warp == 0 && trace_item < 8) trace_ev<kProf>(prm, trace_vt, 40 + trace_item);
+        ++trace_item;
         ++item;
     };
 
@@ -1007,16 +1090,22 @@ __device__ __forceinline__ void pair_epilogue_role(long long* pw, const PolicyPa
             mbar_wait_p<kProf>(bars + 8 * PB_HEAD_FULL, head_gen & 1, pw[PW_HEAD_FULL]);
             ++head_gen;
         }
+        trace_vt = t - t0, trace_item = 0;
         for (int j = 0; j < npos; ++j) {
             const int st = j & 1;
             mbar_wait_p<kProf>(bars + 8 * (PB_D1_FULL + st), (d1_par >> st) & 1, pw[PW_D1_FULL]);
+            if (kProf && warp == 0 && j < 8) trace_ev<kProf>(prm, trace_vt, 32 + j);
             d1_par ^= 1u << st;
             tc_fence_after();
             float v[32];
             tmem_ld32(trow + kPColD1 + st * kHid + g * kCo, v);
+            tc_fence_before();
+            mbar_arrive(bars + 8 * (PB_D1_EMPTY + st));  // the conv issuer may overwrite this stage (after the other group too)
+            if (kProf && warp == 0 && j == 2) trace_ev<kProf>(prm, trace_vt, 59);  // accumulator in registers
             publish(v, s_bias1 + j * kCo);
         }
         mbar_wait_p<kProf>(bars + 8 * (PB_D2_FULL + g), u & 1, pw[PW_D2_FULL]);
+        if (kProf && warp == 0) trace_ev<kProf>(prm, trace_vt, 48);
         tc_fence_after();
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
@@ -1026,7 +1115,9 @@ __device__ __forceinline__ void pair_epilogue_role(long long* pw, const PolicyPa
         }
 
         // ---- FC2 epilogue + head (fp32 on CUDA cores), all 64 hidden units of this network
+        const uint32_t drawn = g == 0 ? out.draw(t, trow_id) : 0u;  // off the critical path: while FC2 runs
         mbar_wait_p<kProf>(bars + 8 * (PB_D3_FULL + g), u & 1, pw[PW_D3_FULL]);
+        if (kProf && (warp & 3) == 0) trace_ev<kProf>(prm, trace_vt, g == 0 ? 49 : 52);
         tc_fence_after();
         float head[6];
 #pragma unroll
@@ -1039,19 +1130,12 @@ __device__ __forceinline__ void pair_epilogue_role(long long* pw, const PolicyPa
                 tc_fence_before();
                 mbar_arrive(bars + 8 * (PB_D3_EMPTY + g));
             }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float h = fmaxf(v[i] + s_b2[half * 32 + i], 0.0f);
-                if (g == 0) {
-#pragma unroll
-                    for (int a = 0; a < 6; ++a) head[a] = fmaf(h, s_wh[a * kHid + half * 32 + i], head[a]);
-                } else {
-                    head[0] = fmaf(h, s_wh[half * 32 + i], head[0]);
-                }
-            }
+            head_accumulate(g, v, s_b2 + half * 32, s_wh, half * 32, head);
         }
         mbar_arrive(bars + 8 * (PB_HEAD_EMPTY + (u & 1)));  // done with the head block of this tile
-        out(t, trow_id, g, head);
+        if (kProf && (warp & 3) == 0) trace_ev<kProf>(prm, trace_vt, g == 0 ? 50 : 53);
+        out(t, trow_id, g, head, drawn);
+        if (kProf && warp == 0) trace_ev<kProf>(prm, trace_vt, 51);
     }
 }
 // output stage of the plain forward: rows are tile-major
@@ -1061,20 +1145,24 @@ struct PairForwardOut {
     __device__ __forceinline__ PairForwardOut(const PolicyParams& p) : prm(p), offset(p.offset) {
         if (p.d_offset != nullptr) offset += *p.d_offset;
     }
-    __device__ __forceinline__ void operator()(int t, int trow_id, int g, const float (&head)[6]) const {
+    __device__ __forceinline__ uint32_t draw(int t, int trow_id) const {
+        if (prm.deterministic || prm.given_actions != nullptr || !(prm.actions || prm.logp)) return 0u;
+        return policy_draw(prm, (uint32_t)((long long)t * kRows + trow_id), offset);
+    }
+    __device__ __forceinline__ void operator()(int t, int trow_id, int g, const float (&head)[6], uint32_t drawn) const {
         const long long row = (long long)t * kRows + trow_id;
         if (row < prm.M) {
             if (g == 1) {
                 if (prm.values) prm.values[row] = head[0];
             } else {
-                emit_actor_row(prm, row, (uint32_t)row, head, offset);
+                emit_actor_row(prm, row, (uint32_t)row, head, offset, false, &drawn);
             }
         }
     }
 };
 
 template <bool kProf>
-__global__ void __launch_bounds__(kThreads, 1) policy_pair_kernel(const PolicyParams prm) {
+__global__ void __launch_bounds__(kPThreads, 1) policy_pair_kernel(const PolicyParams prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -1100,6 +1188,7 @@ __global__ void __launch_bounds__(kThreads, 1) policy_pair_kernel(const PolicyPa
                 (i >= PB_D3_EMPTY && i < PB_D3_EMPTY + 2))
                 count = 128;
             if (i >= PB_HEAD_EMPTY && i < PB_HEAD_EMPTY + 2) count = 32 * kEpiWarps + 1;
+            if (i >= PB_D1_EMPTY && i < PB_D1_EMPTY + 2) count = 32 * kEpiWarps;
             mbar_init(bars + 8 * i, count);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1121,9 +1210,11 @@ __global__ void __launch_bounds__(kThreads, 1) policy_pair_kernel(const PolicyPa
     } else if (warp < kWarpMma) {
         loader_role<kProf>(pw, prm, ur, tmem, s_stage, bars);
     } else if (warp == kWarpMma) {
-        pair_mma_role<kProf>(pw, prm, ur.t0, ur.t1, L, tmem, smem_addr(s_head), smem_addr(s_wring), bars);
-    } else {
+        pair_conv_role<kProf>(pw, prm, ur.t0, ur.t1, L, tmem, smem_addr(s_head), bars);
+    } else if (warp == kWarpProd) {
         pair_producer_role<kProf>(pw, prm, ur.t0, ur.t1, L, smem_addr(s_head), smem_addr(s_wring), bars);
+    } else {
+        pair_fc_role<kProf>(pw, prm, warp - kWarpFc, ur.t0, ur.t1, L, tmem, smem_addr(s_wring), bars);
     }
     if (kProf && prm.prof != nullptr &&
         (tid == 0 || tid == 32 * kEpiWarps || tid == 32 * kWarpMma || tid == 32 * kWarpProd)) {
@@ -1287,7 +1378,8 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
     if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(conv512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(gemm512_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(gemm512_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
@@ -1467,7 +1559,13 @@ extern "C" int ocb_policy_set_weights(ocb_policy* p, int policy, int net, const 
     memcpy(blob.data() + L.b1, fc1_b, kHid * 4);
     memcpy(blob.data() + L.b2, fc2_b, kHid * 4);
     const int head_out = net == 0 ? 6 : 1;
-    memcpy(blob.data() + L.wh, head_w, (size_t)head_out * kHid * 4);
+    float* whp = reinterpret_cast<float*>(blob.data() + L.wh);
+    if (net == 0) {  // actor: hidden-major [64][8] (head_accumulate)
+        for (int i = 0; i < kHid; ++i)
+            for (int a = 0; a < head_out; ++a) whp[i * 8 + a] = head_w[(size_t)a * kHid + i];
+    } else {
+        memcpy(whp, head_w, (size_t)kHid * 4);
+    }
     memcpy(blob.data() + L.bh, head_b, (size_t)head_out * 4);
     DeviceGuard guard(p->device);
     cudaError_t err = cudaMemcpy(p->d_blobs + ((size_t)policy * 2 + net) * L.total, blob.data(), (size_t)L.total,
@@ -1518,9 +1616,9 @@ static int policy_launch(ocb_policy* p, int net_mask, const int8_t* obs, int M, 
         ctas = prm.tiles < p->sm_count ? prm.tiles : p->sm_count;
         if (ctas_out) *ctas_out = ctas;
         if (prof != nullptr)
-            policy_pair_kernel<true><<<ctas, kThreads, p->pair_smem_bytes, (cudaStream_t)stream>>>(prm);
+            policy_pair_kernel<true><<<ctas, kPThreads, p->pair_smem_bytes, (cudaStream_t)stream>>>(prm);
         else
-            policy_pair_kernel<false><<<ctas, kThreads, p->pair_smem_bytes, (cudaStream_t)stream>>>(prm);
+            policy_pair_kernel<false><<<ctas, kPThreads, p->pair_smem_bytes, (cudaStream_t)stream>>>(prm);
     } else {
         if (net_mask == 3) {  // (tile, network) units: even CTAs run the actor, odd ones the critic
             const int per_net = prm.tiles < p->sm_count / 2 ? prm.tiles : p->sm_count / 2;
@@ -1620,7 +1718,7 @@ extern "C" int ocb_policy_debug_profile(ocb_policy* p, const int8_t* obs, int M,
 int ocb_policy_rollout_fused_launch(ocb_policy* p, int policy_index, const RolloutParams& envp, int env_w, int env_h, int T,
                                     int8_t* obs_slab, int32_t* actions, float* logp, float* values, int32_t* reward,
                                     int32_t* done, int deterministic, uint64_t seed, const uint64_t* d_offset,
-                                    uint64_t* d_counter, void* stream) {
+                                    uint64_t* d_counter, void* stream, long long* d_trace, int trace_u0, int trace_n) {
     if (p == nullptr) return fail(OCB_ERR_INVALID_ARG, "policy is NULL");
     if (p->hidden != kHid) return fail(OCB_ERR_UNSUPPORTED, "the fused rollout kernel exists for hidden_size 64 only");
     if (policy_index < 0 || policy_index >= p->n_policies) return fail(OCB_ERR_INVALID_ARG, "policy index out of range");
@@ -1648,7 +1746,11 @@ int ocb_policy_rollout_fused_launch(ocb_policy* p, int policy_index, const Rollo
     fp.obs_slab = obs_slab, fp.actions = actions, fp.logp = logp, fp.values = values, fp.reward = reward, fp.done = done;
     const int ctas = fp.wtiles < p->sm_count ? fp.wtiles : p->sm_count;
     const size_t smem = (size_t)fused_smem_layout(p->npos, ring, p->S, p->SC).total;
-    rollout_fused_kernel<<<ctas, kFThreads, smem, (cudaStream_t)stream>>>(fp);
+    fp.pol.trace = d_trace, fp.pol.trace_u0 = trace_u0, fp.pol.trace_n = trace_n;
+    if (d_trace != nullptr)
+        rollout_fused_kernel<true><<<ctas, kFThreads, smem, (cudaStream_t)stream>>>(fp);
+    else
+        rollout_fused_kernel<false><<<ctas, kFThreads, smem, (cudaStream_t)stream>>>(fp);
     if (d_counter != nullptr)
         counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(d_counter), (unsigned long long)T);
     cudaError_t err = cudaGetLastError();

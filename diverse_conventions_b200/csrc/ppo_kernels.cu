@@ -36,6 +36,7 @@ struct GaeParams {
     double* stats;             // [3] sum, sum of squares, count (or nullptr)
     int T, R, N;
     float gamma, gl, vn_mean, vn_std;
+    const float* vn_dev;       // optional DEVICE float[2] = (mean, std): overrides vn_mean / vn_std (no host round trip)
     int use_gae;
 };
 
@@ -74,7 +75,9 @@ __global__ void __launch_bounds__(kGaeThreads) gae_kernel(const GaeParams p) {
         float gae = 0.0f;
         float ret_next = v_next;  // discounted-sum branch: returns[T] = next_value (shared_buffer.py:297)
         if (!p.use_gae) ret[(size_t)p.T * R] = v_next;  // the GAE branch never writes returns[T] (shared_buffer.py:277-287)
-        float dn_next = denorm(v_next, p.vn_std, p.vn_mean);
+        const float vn_mean = p.vn_dev != nullptr ? __ldg(p.vn_dev) : p.vn_mean;
+        const float vn_std = p.vn_dev != nullptr ? __ldg(p.vn_dev + 1) : p.vn_std;
+        float dn_next = denorm(v_next, vn_std, vn_mean);
         for (int t1 = p.T; t1 > 0; t1 -= kGaeUnroll) {
             if (t1 > kGaeUnroll) gae_load(nxt, vp, rw, dn, t1 - kGaeUnroll, R, N);
 #pragma unroll
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(kGaeThreads) gae_kernel(const GaeParams p) {
                 if (t < 0) break;
                 const float r = (float)cur.r[k];
                 const float m = cur.d[k] ? 0.0f : 1.0f;  // masks[t+1] = 1 - done[t] (main_player.py:254-258)
-                const float dn0 = denorm(cur.v[k], p.vn_std, p.vn_mean);
+                const float dn0 = denorm(cur.v[k], vn_std, vn_mean);
                 float out;
                 if (p.use_gae) {
                     // delta = r + gamma * denorm(v[t+1]) * mask - denorm(v[t]);  gae = delta + gamma*lambda * mask * gae
@@ -146,9 +149,20 @@ __global__ void normalize_adv_kernel(float* adv, size_t n, const double* stats) 
 
 }  // namespace
 
+extern "C" int ocb_compute_returns_dev(int device, const ocb_returns_cfg* cfg, int T, int P, int N, const float* value_preds,
+                                       const int32_t* rewards, const int32_t* done, float* returns, float* advantages,
+                                       double* adv_stats, const float* vn_mean_std, void* stream);
+
 extern "C" int ocb_compute_returns(int device, const ocb_returns_cfg* cfg, int T, int P, int N, const float* value_preds,
                                    const int32_t* rewards, const int32_t* done, float* returns, float* advantages,
                                    double* adv_stats, void* stream) {
+    return ocb_compute_returns_dev(device, cfg, T, P, N, value_preds, rewards, done, returns, advantages, adv_stats, nullptr,
+                                   stream);
+}
+
+extern "C" int ocb_compute_returns_dev(int device, const ocb_returns_cfg* cfg, int T, int P, int N, const float* value_preds,
+                                       const int32_t* rewards, const int32_t* done, float* returns, float* advantages,
+                                       double* adv_stats, const float* vn_mean_std, void* stream) {
     if (cfg == nullptr || value_preds == nullptr || rewards == nullptr || done == nullptr || returns == nullptr)
         return fail(OCB_ERR_INVALID_ARG, "NULL argument");
     if (cfg->struct_size != sizeof(ocb_returns_cfg)) return fail(OCB_ERR_INVALID_ARG, "ocb_returns_cfg ABI mismatch");
@@ -161,7 +175,7 @@ extern "C" int ocb_compute_returns(int device, const ocb_returns_cfg* cfg, int T
     p.value_preds = value_preds, p.rewards = rewards, p.done = done, p.returns = returns, p.advantages = advantages;
     p.stats = adv_stats, p.T = T, p.R = P * N, p.N = N;
     p.gamma = (float)cfg->gamma, p.gl = (float)(cfg->gamma * cfg->gae_lambda);
-    p.vn_mean = cfg->vn_mean, p.vn_std = cfg->vn_std, p.use_gae = cfg->use_gae;
+    p.vn_mean = cfg->vn_mean, p.vn_std = cfg->vn_std, p.use_gae = cfg->use_gae, p.vn_dev = vn_mean_std;
     cudaStream_t s = (cudaStream_t)stream;
     if (adv_stats != nullptr) {
         cudaError_t err = cudaMemsetAsync(adv_stats, 0, 3 * sizeof(double), s);

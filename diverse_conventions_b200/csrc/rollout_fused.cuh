@@ -33,8 +33,8 @@ struct FusedParams {
 };
 
 constexpr int kFEnvWarps = 2;
-constexpr int kFWarpEnv = kWarpProd + 1;                    // warps 18, 19
-constexpr int kFThreads = kThreads + 32 * kFEnvWarps;       // 640
+constexpr int kFWarpEnv = kWarpFc + 2;                      // warps 20, 21
+constexpr int kFThreads = kPThreads + 32 * kFEnvWarps;      // 704
 constexpr int kFWorlds = 32 * kFEnvWarps;                   // worlds per CTA tile
 enum : int {
     FB_OBS_FULL = PB_COUNT,      // env warps (64 arrivals) -> loaders: planes of virtual tile vt are complete
@@ -69,6 +69,7 @@ __host__ __device__ inline FusedSmemLayout fused_smem_layout(int npos, int ring,
 
 // loaders: shared-memory planes -> bf16 cell blocks in TMEM.  Thread (lw, lane) owns row 32 lw + lane
 // = seat lw / 2, env warp lw % 2, world `lane`; the two groups take alternate columns of the stream.
+template <bool kProf>
 __device__ __forceinline__ void fused_loader_role(const FusedParams& fp, uint32_t nvt, uint32_t tmem, const uint8_t* s_env,
                                                   const FusedSmemLayout& sl, uint32_t bars) {
     const int lwarp = (threadIdx.x >> 5) - kEpiWarps, lg = lwarp >> 2, lw = lwarp & 3, lane = threadIdx.x & 31;
@@ -83,8 +84,10 @@ __device__ __forceinline__ void fused_loader_role(const FusedParams& fp, uint32_
     for (uint32_t gc = lg; gc < ncols; gc += 2) {
         if (fresh) {
             mbar_wait(bars + 8 * FB_OBS_FULL, lt & 1);
-            fresh = false;
+            if (kProf && lwarp == 0) trace_ev<kProf>(fp.pol, (int)lt, 8);
         }
+        const bool first_col = fresh;
+        fresh = false;
         const int slot = gc % kColRing;
         if (gc >= kColRing) {
             mbar_wait(bars + 8 * (PB_COL_EMPTY + slot), ((gc / kColRing) - 1) & 1);
@@ -104,15 +107,18 @@ __device__ __forceinline__ void fused_loader_role(const FusedParams& fp, uint32_
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bars + 8 * (PB_COL_FULL + slot));
+        if (kProf && lwarp == 0 && first_col) trace_ev<kProf>(fp.pol, (int)lt, 9);
         lx += 2;
         if (lx >= W) {  // this group's last column of the tile: its plane reads are done
             mbar_arrive(bars + 8 * FB_OBS_EMPTY);
+            if (kProf && lwarp == 0) trace_ev<kProf>(fp.pol, (int)lt, 10);
             lx -= W, ++lt, fresh = true;
         }
     }
 }
 
 // env warps: one world per lane, state in registers / shared memory across the T steps
+template <bool kProf>
 __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s_env, const FusedSmemLayout& sl, const Tables& tb,
                                                const uint8_t* tmpl, const uint8_t* s_act, uint32_t bars) {
     constexpr int P = 2;
@@ -152,6 +158,7 @@ __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s
             uint32_t dirty[P] = {0xFFFFFFFFu, 0xFFFFFFFFu};
             if (u > 0) {
                 mbar_wait(bars + 8 * FB_ACT_FULL, acts & 1);
+                if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)vt, 0);
                 ++acts;
                 int act[P];
                 act[0] = s_act[ew * 32 + lane], act[1] = s_act[kFWorlds + ew * 32 + lane];
@@ -176,6 +183,7 @@ __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s
                     done_ptr += N;
                 }
                 full = done;
+                if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)vt, 1);
             }
             // the planes still hold virtual tile vt - 1: its loaders and its bulk store must be done with them
             if (vt > 0) mbar_wait(bars + 8 * FB_OBS_EMPTY, (vt - 1) & 1);
@@ -184,9 +192,11 @@ __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s
                 tma_pending = false;
             }
             __syncwarp();
+            if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)vt, 2);
             obs_phase1<P, 1>(tb, myplanes, view_stride, tmpl, full, 0, oldslot);
             obs_phase2<P, 1>(tb, c, myplanes, view_stride, myobjs, 32, full, 0, w, dirty);
             mbar_arrive(bars + 8 * FB_OBS_FULL);  // release: the loaders may read this lane's planes
+            if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)vt, 3);
             int8_t* dst = obs_ptr + (size_t)u * obs_step_stride;
             if (tma_ok) {
                 fence_proxy_async_smem();
@@ -231,7 +241,13 @@ struct FusedOut {
         base = f.pol.offset;
         if (f.pol.d_offset != nullptr) base += *f.pol.d_offset;
     }
-    __device__ __forceinline__ void operator()(int, int trow_id, int g, const float (&head)[6]) {
+    __device__ __forceinline__ uint32_t draw(int, int trow_id) const {
+        if (fp.pol.deterministic || u >= fp.T) return 0u;
+        const int wl = trow_id & (kFWorlds - 1), seat = trow_id >> 6;
+        const long long row = (long long)seat * fp.env.N + (kt * kFWorlds + wl);
+        return policy_draw(fp.pol, (uint32_t)row, base + (unsigned long long)u);
+    }
+    __device__ __forceinline__ void operator()(int, int trow_id, int g, const float (&head)[6], uint32_t drawn) {
         const int N = fp.env.N, wl = trow_id & (kFWorlds - 1), seat = trow_id >> 6;
         const int n = kt * kFWorlds + wl;
         const long long row = (long long)seat * N + n;               // row of one step's [2][N] block
@@ -242,7 +258,7 @@ struct FusedOut {
             PolicyParams op = fp.pol;  // output pointers of this step; rows past N sample but store nothing
             const bool valid = n < N;
             op.actions = valid ? fp.actions : nullptr, op.logp = valid ? fp.logp : nullptr, op.logits = nullptr;
-            const int act = emit_actor_row(op, store, (uint32_t)row, head, base + (unsigned long long)u, true);
+            const int act = emit_actor_row(op, store, (uint32_t)row, head, base + (unsigned long long)u, true, &drawn);
             s_act[trow_id] = (uint8_t)act;
             mbar_arrive(bars + 8 * FB_ACT_FULL);
         }
@@ -250,6 +266,7 @@ struct FusedOut {
     }
 };
 
+template <bool kProf>
 __global__ void __launch_bounds__(kFThreads, 1) rollout_fused_kernel(const FusedParams fp) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
@@ -280,6 +297,7 @@ __global__ void __launch_bounds__(kFThreads, 1) rollout_fused_kernel(const Fused
                 (i >= PB_D3_EMPTY && i < PB_D3_EMPTY + 2))
                 count = 128;
             if (i >= PB_HEAD_EMPTY && i < PB_HEAD_EMPTY + 2) count = 32 * kEpiWarps + 1;
+            if (i >= PB_D1_EMPTY && i < PB_D1_EMPTY + 2) count = 32 * kEpiWarps;
             if (i == FB_OBS_FULL) count = 32 * kFEnvWarps;
             if (i == FB_OBS_EMPTY) count = 32 * kLoadWarps;
             if (i == FB_ACT_FULL) count = 128;
@@ -301,17 +319,19 @@ __global__ void __launch_bounds__(kFThreads, 1) rollout_fused_kernel(const Fused
     const int nk = ((int)blockIdx.x < fp.wtiles) ? (fp.wtiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int nvt = nk * (fp.T + 1);
 
-    long long pw[1] = {};
+    long long pw[kProf ? PW_COUNT : 1] = {};
     if (warp < kEpiWarps) {
-        pair_epilogue_role<false>(pw, prm, 0, nvt, L, tmem, s_head, bars, FusedOut(fp, s_act, bars));
+        pair_epilogue_role<kProf>(pw, prm, 0, nvt, L, tmem, s_head, bars, FusedOut(fp, s_act, bars));
     } else if (warp < kWarpMma) {
-        fused_loader_role(fp, (uint32_t)nvt, tmem, s_env, sl, bars);
+        fused_loader_role<kProf>(fp, (uint32_t)nvt, tmem, s_env, sl, bars);
     } else if (warp == kWarpMma) {
-        pair_mma_role<false>(pw, prm, 0, nvt, L, tmem, smem_addr(s_head), smem_addr(s_wring), bars);
+        pair_conv_role<kProf>(pw, prm, 0, nvt, L, tmem, smem_addr(s_head), bars);
     } else if (warp == kWarpProd) {
-        pair_producer_role<false>(pw, prm, 0, nvt, L, smem_addr(s_head), smem_addr(s_wring), bars);
+        pair_producer_role<kProf>(pw, prm, 0, nvt, L, smem_addr(s_head), smem_addr(s_wring), bars);
+    } else if (warp < kFWarpEnv) {
+        pair_fc_role<kProf>(pw, prm, warp - kWarpFc, 0, nvt, L, tmem, smem_addr(s_wring), bars);
     } else {
-        fused_env_role(fp, s_env, sl, *s_tables, s_tmpl, s_act, bars);
+        fused_env_role<kProf>(fp, s_env, sl, *s_tables, s_tmpl, s_act, bars);
     }
     __syncwarp();
     tc_fence_before();

@@ -152,6 +152,9 @@ class LayoutParams:
         for x, y in zip(self.start_player_x, self.start_player_y):
             if self.terrain[y * W + x] != 0:
                 raise ValueError("player start cell is not AIR")
+        starts = list(zip(self.start_player_x, self.start_player_y))[:self.num_players]
+        if len(set(starts)) != len(starts):
+            raise ValueError("two players start on the same cell")
 
     def to_config(self) -> ocb_config:
         self.validate()

@@ -23,11 +23,25 @@ class ocb_returns_cfg(ctypes.Structure):
 
 def valuenorm_mean_std(value_normalizer) -> Tuple[float, float]:
     """(debiased mean, sqrt of the clamped debiased variance) of a reference ``ValueNorm`` (or any
-    object with ``running_mean_var()``, valuenorm.py:34-41); ``None`` -> (0, 1)."""
+    object with ``running_mean_var()``, valuenorm.py:34-41) as Python floats; ``None`` -> (0, 1).
+    Synchronises when the statistics live on a CUDA device — ``compute_returns`` uses
+    ``valuenorm_mean_std_device`` for those instead."""
     if value_normalizer is None:
         return 0.0, 1.0
     mean, var = value_normalizer.running_mean_var()
     return float(mean.reshape(-1)[0]), float(torch.sqrt(var).reshape(-1)[0])
+
+
+def valuenorm_mean_std_device(value_normalizer, device) -> Optional[torch.Tensor]:
+    """float32 ``[mean, std]`` on ``device`` when the normaliser's statistics are CUDA tensors (the device-resident
+    ``ValueNormState`` or a reference ``ValueNorm`` moved to the GPU): two tiny torch launches, no host
+    synchronisation, so ``compute_returns`` stays asynchronous and graph-capturable.  ``None`` otherwise."""
+    if value_normalizer is None:
+        return None
+    mean, var = value_normalizer.running_mean_var()
+    if not (torch.is_tensor(mean) and mean.is_cuda):
+        return None
+    return torch.stack([mean.reshape(-1)[0], torch.sqrt(var).reshape(-1)[0]]).to(device=device, dtype=torch.float32)
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -36,11 +50,16 @@ def _p(t: Optional[torch.Tensor]):
 
 def compute_returns(value_preds: torch.Tensor, rewards: torch.Tensor, dones: torch.Tensor, gamma: float = 0.99,
                     gae_lambda: float = 0.95, use_gae: bool = True, value_normalizer=None, normalize: bool = True,
-                    out_returns: Optional[torch.Tensor] = None, out_advantages: Optional[torch.Tensor] = None):
+                    out_returns: Optional[torch.Tensor] = None, out_advantages: Optional[torch.Tensor] = None,
+                    group=None):
     """value_preds f32 ``[T+1,P,N]`` (slot T = bootstrap value), rewards int32 ``[T,P,N]``, dones int32
     ``[T,N]`` on one CUDA device -> ``(returns [T+1,P,N], advantages [T,P,N])``; the advantages are
     normalised in place ((a - mean) / (std + 1e-5)) when ``normalize``.  Asynchronous on torch's
-    current stream; no host synchronisation."""
+    current stream; no host synchronisation (ValueNorm statistics that live on the GPU are read there).
+    ``group``: a ``torch.distributed`` process group (or ``True`` for the default group) over which the
+    advantage statistics (sum, sum of squares, count — three doubles) are all-reduced before the
+    normalisation, so that world-sharded ranks normalise exactly like the unsharded run (r_mappo.py:174-182
+    takes mean / std over the whole [T, N, 2] batch)."""
     if not value_preds.is_cuda:
         raise RuntimeError("compute_returns needs CUDA tensors; there is no CPU fallback")
     T, P, N = rewards.shape
@@ -52,7 +71,8 @@ def compute_returns(value_preds: torch.Tensor, rewards: torch.Tensor, dones: tor
         if not t.is_contiguous():
             raise ValueError("buffers must be contiguous")
     dev = value_preds.device
-    mean, std = valuenorm_mean_std(value_normalizer)
+    vn_dev = valuenorm_mean_std_device(value_normalizer, dev)
+    mean, std = (0.0, 1.0) if vn_dev is not None else valuenorm_mean_std(value_normalizer)
     cfg = ocb_returns_cfg(ctypes.sizeof(ocb_returns_cfg), int(use_gae), gamma, gae_lambda, mean, std)
     returns = out_returns if out_returns is not None else torch.zeros((T + 1, P, N), dtype=torch.float32, device=dev)
     adv = out_advantages if out_advantages is not None else torch.empty((T, P, N), dtype=torch.float32, device=dev)
@@ -60,8 +80,11 @@ def compute_returns(value_preds: torch.Tensor, rewards: torch.Tensor, dones: tor
     lib = _native.lib()
     with torch.cuda.device(dev):
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        _native.check(lib.ocb_compute_returns(dev.index, ctypes.byref(cfg), T, P, N, _p(value_preds), _p(rewards), _p(dones),
-                                              _p(returns), _p(adv), _p(stats), stream))
+        _native.check(lib.ocb_compute_returns_dev(dev.index, ctypes.byref(cfg), T, P, N, _p(value_preds), _p(rewards),
+                                                  _p(dones), _p(returns), _p(adv), _p(stats), _p(vn_dev), stream))
+        if normalize and group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(stats, group=None if group is True else group)
         if normalize:
             _native.check(lib.ocb_normalize_advantages(dev.index, _p(adv), adv.numel(), _p(stats), stream))
     return returns, adv

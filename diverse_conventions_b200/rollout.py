@@ -50,7 +50,7 @@ class RolloutBuffer:
                    if t is not None)
 
     def compute_returns(self, gamma: float = 0.99, gae_lambda: float = 0.95, use_gae: bool = True, value_normalizer=None,
-                        normalize: bool = True):
+                        normalize: bool = True, group=None):
         """returns [T+1,P,N] and (normalised) advantages [T,P,N] of this rollout, on the device
         (SharedReplayBuffer.compute_returns + the advantage normalisation of R_MAPPO.train; see returns.py)"""
         from .returns import compute_returns
@@ -58,7 +58,7 @@ class RolloutBuffer:
             raise ValueError("this buffer was collected without the critic")
         self.returns, self.advantages = compute_returns(
             self.value_preds, self.rewards, self.dones, gamma, gae_lambda, use_gae, value_normalizer, normalize,
-            getattr(self, "returns", None), getattr(self, "advantages", None))
+            getattr(self, "returns", None), getattr(self, "advantages", None), group)
         return self.returns, self.advantages
 
     def shared_buffer_views(self, hidden_size: int = 64, recurrent_N: int = 1) -> Dict[str, torch.Tensor]:

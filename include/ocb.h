@@ -267,6 +267,14 @@ int ocb_rollout_policy_fused(ocb_env* env, ocb_policy* pol, int T, int policy_in
                              float* logp, float* values, int32_t* reward, int32_t* done, int deterministic,
                              uint64_t seed, void* stream);
 
+/* Diagnostic: ocb_rollout_policy_fused through the instrumented build of the kernel (synchronous, sampled
+ * actions).  h_trace (HOST int64 [n_steps][64]) receives clock64 stamps of CTA 0 for steps u0 .. u0+n_steps-1;
+ * event indices are listed at trace_ev in csrc/policy_kernels.cu (env / loader / MMA issue / epilogue hand-offs).
+ * Used by tools/fused_trace.py to attribute the per-step latency of the dependent chain. */
+int ocb_rollout_fused_debug_trace(ocb_env* env, ocb_policy* pol, int T, int policy_index, int8_t* obs_slab,
+                                  int32_t* actions, float* logp, float* values, int32_t* reward, int32_t* done,
+                                  uint64_t seed, int64_t* h_trace, int u0, int n_steps);
+
 /* ------------------------------------------------------- mixed-play ("MP") collection */
 /* XDPlayer.collect_mp_episode / next_mp_step (train/XD/xd_player.py:232-356) with the partner seat of
  * MixedAgent (train/partner_agents.py:151-244) and the buffer placement of SharedReplayBuffer.diaginsert /
@@ -315,7 +323,14 @@ typedef struct ocb_returns_cfg {
 int ocb_compute_returns(int device, const ocb_returns_cfg* cfg, int T, int P, int N, const float* value_preds,
                         const int32_t* rewards, const int32_t* done, float* returns, float* advantages,
                         double* adv_stats, void* stream);
-/* advantages <- (advantages - mean) / (std + 1e-5), unbiased std, from adv_stats (r_mappo.py:180-182) */
+/* Same, with the ValueNorm statistics read on the DEVICE: vn_mean_std = float[2] (debiased mean, sqrt of the clamped
+ * debiased variance), overriding cfg->vn_mean / vn_std when not NULL — no host round trip, graph-capturable. */
+int ocb_compute_returns_dev(int device, const ocb_returns_cfg* cfg, int T, int P, int N, const float* value_preds,
+                            const int32_t* rewards, const int32_t* done, float* returns, float* advantages,
+                            double* adv_stats, const float* vn_mean_std, void* stream);
+/* advantages <- (advantages - mean) / (std + 1e-5), unbiased std, from adv_stats (r_mappo.py:180-182).  Sharded runs
+ * all-reduce (sum) the three doubles across ranks between the two calls so that every rank normalises with the
+ * statistics of the whole batch (returns.py: compute_returns(group=...)). */
 int ocb_normalize_advantages(int device, float* advantages, size_t n, const double* adv_stats, void* stream);
 
 /* ------------------------------------------------------- PPO minibatch: gather, evaluate_actions, loss */

@@ -152,9 +152,37 @@ def test_set_state_rejects_unrepresentable_states():
     bad[2, cell0 + 4 * 6: cell0 + 4 * 6 + 4] = (3, 0, 0, -1)  # dish floating on an AIR cell
     with pytest.raises(_native.NativeError):
         env.set_state(bad)
+    bad = st.copy()
+    bad[3, 1 + 6] = bad[3, 1]  # both players on one cell: unreachable in the MDP, the plane update assumes it never happens
+    with pytest.raises(_native.NativeError):
+        env.set_state(bad)
     assert np.array_equal(env.get_state(), st)  # rejected states leave the env untouched
     with pytest.raises(_native.NativeError):
         env.set_state(st[:2])
+
+
+def test_graph_replays_of_random_rollouts_continue_the_action_stream():
+    """a captured ocb_rollout_random reads its first step from the device counter: replays draw fresh actions, the
+    host mirror (ocb_step_count) follows, and an uncaptured launch afterwards continues where the replays stopped"""
+    N, K, seed = 96, 8, 77
+    env = make_env("simple", N, seed=seed)
+    out = env.alloc_rollout(K)
+    env.rollout_random(K, out)  # uncaptured warm-up: steps 0..7
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        env.rollout_random(K, out)
+    acts = []
+    for _ in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        acts.append(out["actions"].cpu().numpy().copy())
+    assert env.step_count == 4 * K
+    assert np.array_equal(np.concatenate(acts), random_actions(seed, 0, N, K, 3 * K, 2))
+    tail = env.rollout_random(K)
+    torch.cuda.synchronize()
+    assert np.array_equal(tail["actions"].cpu().numpy(), random_actions(seed, 0, N, 4 * K, K, 2))
+    assert env.step_count == 5 * K
 
 
 # --------------------------------------------------------------------------- API conventions

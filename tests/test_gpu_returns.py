@@ -85,3 +85,31 @@ def test_full_size_buffer_properties():
                                  done[:, cols].cpu().numpy(), 0.99, 1.0, True)
     assert np.array_equal(ret[:T, :, cols].cpu().numpy(), oret[:T])
     assert torch.equal(ret[:T, 0], ret[:T, 1])
+
+
+def test_device_resident_valuenorm_statistics_give_the_same_bits_without_a_host_sync():
+    """a ValueNorm whose statistics are CUDA tensors is read on the device (ocb_compute_returns_dev): identical
+    returns / advantages to the host-float path, and capturable into a CUDA graph"""
+    T, P, N = 50, 2, 300
+    rng = np.random.default_rng(5)
+    v = _dev(rng.normal(0, 2.0, size=(T + 1, P, N)).astype(np.float32), torch.float32)
+    r = _dev(rng.choice([0, 0, 3, 20], size=(T, 1, N)).repeat(P, axis=1).astype(np.int32), torch.int32)
+    d = _dev((rng.random((T, N)) < 0.05).astype(np.int32), torch.int32)
+
+    class DevVN(_VN):
+        def running_mean_var(self):
+            m, var = super().running_mean_var()
+            return m.cuda(), var.cuda()
+
+    host = R.compute_returns(v, r, d, 0.99, 0.95, True, _VN(1.25, 2.5), normalize=False)
+    dev = R.compute_returns(v, r, d, 0.99, 0.95, True, DevVN(1.25, 2.5), normalize=False)
+    assert torch.equal(host[0][:T], dev[0][:T]) and torch.equal(host[1], dev[1])
+    vn = DevVN(1.25, 2.5)
+    out_r, out_a = torch.zeros_like(host[0]), torch.zeros_like(host[1])
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        R.compute_returns(v, r, d, 0.99, 0.95, True, vn, False, out_r, out_a)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out_r[:T], host[0][:T]) and torch.equal(out_a, host[1])

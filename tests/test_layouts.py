@@ -67,3 +67,10 @@ def test_validation_rejects_open_border_and_long_cook():
         layouts.parse_layout_dict(d, 400).to_config()
     with pytest.raises(FileNotFoundError):
         layouts.load_layout("no_such_layout", 400)
+
+
+def test_validation_rejects_two_players_on_one_start_cell():
+    lp = layouts.load_layout("simple", 400)
+    lp.start_player_x[1], lp.start_player_y[1] = lp.start_player_x[0], lp.start_player_y[0]
+    with pytest.raises(ValueError):
+        lp.to_config()
