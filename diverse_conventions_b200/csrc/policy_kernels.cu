@@ -1747,6 +1747,10 @@ int ocb_policy_rollout_fused_launch(ocb_policy* p, int policy_index, const Rollo
     const int ctas = fp.wtiles < p->sm_count ? fp.wtiles : p->sm_count;
     const size_t smem = (size_t)fused_smem_layout(p->npos, ring, p->S, p->SC).total;
     fp.pol.trace = d_trace, fp.pol.trace_u0 = trace_u0, fp.pol.trace_n = trace_n;
+    {   // 16-byte plane reads pay when the rows are 16-byte aligned (cramped_room, counter_circuit); OCB_FUSED_VEC_LOADER overrides
+        const char* e = getenv("OCB_FUSED_VEC_LOADER");
+        fp.vec_loader = e != nullptr ? (e[0] != '0') : (p->SC % 16 == 0);
+    }
     if (d_trace != nullptr)
         rollout_fused_kernel<true><<<ctas, kFThreads, smem, (cudaStream_t)stream>>>(fp);
     else

@@ -30,6 +30,7 @@ struct FusedParams {
     float* values;       // [T+1][2][N]
     int32_t* reward;     // [T][2][N] or nullptr
     int32_t* done;       // [T][N] or nullptr
+    int vec_loader;      // loaders read the planes as 16-byte vectors (conflict-free) instead of 4-byte words
 };
 
 constexpr int kFEnvWarps = 2;
@@ -93,16 +94,55 @@ __device__ __forceinline__ void fused_loader_role(const FusedParams& fp, uint32_
             mbar_wait(bars + 8 * (PB_COL_EMPTY + slot), ((gc / kColRing) - 1) & 1);
             tc_fence_after();
         }
-        const uint32_t* mine = myrow + lx * seg;
-        for (int y = 0; y < H; ++y) {
-            uint32_t w[5];
+        if (fp.vec_loader) {
+            // The 20 H bytes of this row's grid column, read as 16-byte vectors from the enclosing aligned range: rows are SC
+            // bytes apart (100 / 125 / 225 words), so 4-byte loads of a warp hit 4-way bank conflicts while 16-byte loads are
+            // conflict-free; eight loader warps on 4-byte loads alone kept the shared-memory pipe busy for ~650 cycles per
+            // column pair (tools/fused_trace.py).  `r` = words the column starts after the aligned address.
+            const uint32_t* colp = myrow + lx * seg;
+            const int r = (int)((reinterpret_cast<uintptr_t>(colp) >> 2) & 3);  // per lane when SC is not a multiple of 16
+            const uint4* src4 = reinterpret_cast<const uint4*>(colp - r);
+            constexpr int kMaxVec = (5 * kMaxH + 3 + 3) / 4;  // 9
+            const int nvec = (seg + r + 3) >> 2;
+            uint32_t c[4 * kMaxVec];
+    #pragma unroll
+            for (int i = 0; i < kMaxVec; ++i) {
+                if (i < nvec) {
+                    const uint4 q = src4[i];
+                    c[4 * i] = q.x, c[4 * i + 1] = q.y, c[4 * i + 2] = q.z, c[4 * i + 3] = q.w;
+                } else {
+                    c[4 * i] = c[4 * i + 1] = c[4 * i + 2] = c[4 * i + 3] = 0u;
+                }
+            }
+            auto word = [&](int k) -> uint32_t {  // word k of the column = c[k + r], r in 0..3 (static register indices)
+                const uint32_t a = (r & 1) ? c[k + 1] : c[k], b = (r & 1) ? c[k + 3] : c[k + 2];
+                return (r & 2) ? b : a;
+            };
+    #pragma unroll
+            for (int y = 0; y < kMaxH; ++y) {
+                if (y < H) {
+                    uint32_t w[5];
+    #pragma unroll
+                    for (int q = 0; q < 5; ++q) w[q] = word(y * 5 + q);
+                    const uint4 c0 = make_uint4(bytes_bf16x2(w[0], pair_sel(0, 1)), bytes_bf16x2(w[0], pair_sel(2, 3)),
+                                                bytes_bf16x2(w[1], pair_sel(0, 1)), bytes_bf16x2(w[1], pair_sel(2, 3)));
+                    const uint4 c1 = make_uint4(bytes_bf16x2(w[2], pair_sel(0, 1)), bytes_bf16x2(w[4], pair_sel(0, 1)),
+                                                bytes_bf16x2(w[4], pair_sel(2, 3)), bytes_bf16x2(w[3], pair_sel(3, 4)));
+                    tmem_st8(tcells + (slot * H + y) * kCellCols, c0, c1);
+                }
+            }
+        } else {
+            const uint32_t* mine = myrow + lx * seg;
+            for (int y = 0; y < H; ++y) {
+                uint32_t w[5];
 #pragma unroll
-            for (int q = 0; q < 5; ++q) w[q] = mine[y * 5 + q];
-            const uint4 c0 = make_uint4(bytes_bf16x2(w[0], pair_sel(0, 1)), bytes_bf16x2(w[0], pair_sel(2, 3)),
-                                        bytes_bf16x2(w[1], pair_sel(0, 1)), bytes_bf16x2(w[1], pair_sel(2, 3)));
-            const uint4 c1 = make_uint4(bytes_bf16x2(w[2], pair_sel(0, 1)), bytes_bf16x2(w[4], pair_sel(0, 1)),
-                                        bytes_bf16x2(w[4], pair_sel(2, 3)), bytes_bf16x2(w[3], pair_sel(3, 4)));
-            tmem_st8(tcells + (slot * H + y) * kCellCols, c0, c1);
+                for (int q = 0; q < 5; ++q) w[q] = mine[y * 5 + q];
+                const uint4 c0 = make_uint4(bytes_bf16x2(w[0], pair_sel(0, 1)), bytes_bf16x2(w[0], pair_sel(2, 3)),
+                                            bytes_bf16x2(w[1], pair_sel(0, 1)), bytes_bf16x2(w[1], pair_sel(2, 3)));
+                const uint4 c1 = make_uint4(bytes_bf16x2(w[2], pair_sel(0, 1)), bytes_bf16x2(w[4], pair_sel(0, 1)),
+                                            bytes_bf16x2(w[4], pair_sel(2, 3)), bytes_bf16x2(w[3], pair_sel(3, 4)));
+                tmem_st8(tcells + (slot * H + y) * kCellCols, c0, c1);
+            }
         }
         tmem_st_wait();
         tc_fence_before();
