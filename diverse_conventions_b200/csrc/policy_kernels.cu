@@ -574,9 +574,12 @@ __device__ __forceinline__ uint32_t policy_draw(const PolicyParams& prm, uint32_
     philox4x32_10(r, (uint32_t)prm.seed, (uint32_t)(prm.seed >> 32));
     return r[0];
 }
-// `drawn` (optional): policy_draw of this row, computed by the caller while it was waiting for the accumulator
+// `drawn` (optional): policy_draw of this row, computed by the caller while it was waiting for the accumulator.
+// `early_slot` / `early_bar` (fused rollout): the action byte is published there and the mbarrier arrived on as soon as
+// the action is known — the env warps start the transition while this thread still computes the log-prob and stores.
 __device__ __forceinline__ int emit_actor_row(const PolicyParams& prm, long long store, uint32_t rng_row, const float (&head)[6],
-                                              unsigned long long offset, bool force_sample = false, const uint32_t* drawn = nullptr) {
+                                              unsigned long long offset, bool force_sample = false, const uint32_t* drawn = nullptr,
+                                              uint8_t* early_slot = nullptr, uint32_t early_bar = 0) {
     if (prm.logits) {
 #pragma unroll
         for (int a = 0; a < 6; ++a) prm.logits[store * 6 + a] = head[a];
@@ -614,6 +617,10 @@ __device__ __forceinline__ int emit_actor_row(const PolicyParams& prm, long long
                 cum += e[a];
                 if (!found && uu < cum) act = a, found = true;
             }
+        }
+        if (early_slot != nullptr) {
+            *early_slot = (uint8_t)act;
+            mbar_arrive(early_bar);
         }
         if (prm.actions) prm.actions[store] = act;
         if (prm.logp) {
@@ -852,7 +859,10 @@ enum : int {
     PB_W_FULL = 24,             // [24] bulk copy complete_tx -> MMA
     PB_W_EMPTY = 48,            // [24] MMA commit -> producer
     PB_D1_EMPTY = 72,           // [2] both epilogue groups (256 arrivals) -> conv issuer: stage has been read
-    PB_COUNT = 74,
+    // split mode (fused rollout): one conv stream per network, accumulator stages [net][2] of 32 columns
+    PBS_D1_FULL = 74,           // [2][2] conv issuer of net g -> epilogue group g
+    PBS_D1_EMPTY = 78,          // [2][2] epilogue group g (128 arrivals) -> conv issuer of net g
+    PB_COUNT = 82,
     PB_TMEM_SLOT = 120          // 8-byte slot index that holds the TMEM base address
 };
 
@@ -927,12 +937,22 @@ __device__ __forceinline__ void pair_producer_role(long long* pw, const PolicyPa
 //     published their A operand; the two networks no longer wait for each other.
 // tcgen05.mma from different warps of a CTA execute in issue order; the three streams touch disjoint accumulators and
 // every cross-stream dependency is an mbarrier.
-template <bool kProf>
+// kNet = -1: one stream for both networks (N = 64, pair kernel).  kNet = 0 / 1 (fused rollout): the stream of ONE network
+// (N = 32, its own two 32-column accumulator stages inside the same 128 columns).  The critic's stream of a tile starts
+// only when the actor's FC2 of that tile has been issued: the tensor pipe then carries nothing but the actor — the only
+// network the next env step waits for — until the actions are out, and the critic's forward fills the pipe's idle time
+// under the head / sampling / env step / plane loading of the next step.  Same products per output element, same order.
+// `ring` grid columns are resident in the cell region (barriers col_full + slot / col_empty + slot): 4 in the pair kernel;
+// the split mode needs the WHOLE grid resident (ring >= W), because the critic's stream starts after the actor's finished.
+template <bool kProf, int kNet>
 __device__ __forceinline__ void pair_conv_role(long long* pw, const PolicyParams& prm, int t0, int t1, const BlobLayout L, uint32_t tmem,
-                                               uint32_t a_head, uint32_t bars) {
+                                               uint32_t a_head, uint32_t bars, const uint32_t ring = kColRing,
+                                               const int col_full = PB_COL_FULL, const int col_empty = PB_COL_EMPTY) {
     const int W = prm.W, H = prm.H, PH = H - 2, npos = prm.npos;
-    const uint32_t idesc = make_idesc(kRows, kHid);  // N = 64: actor channels 0-31 | critic channels 32-63
-    const uint32_t a_wchi = a_head, a_wclo = a_head + 2 * kPConvBytes;
+    constexpr int kN = kNet < 0 ? kHid : kCo;
+    const uint32_t idesc = make_idesc(kRows, kN);  // N = 64: actor channels 0-31 | critic channels 32-63
+    const uint32_t a_wchi = a_head + (kNet == 1 ? kPConvBytes : 0), a_wclo = a_wchi + 2 * kPConvBytes;
+    const int b_full = kNet < 0 ? PB_D1_FULL : PBS_D1_FULL + 2 * kNet, b_empty = kNet < 0 ? PB_D1_EMPTY : PBS_D1_EMPTY + 2 * kNet;
     uint32_t gcb = 0;            // running column index of grid column 0 of the tile
     uint32_t head_gen = 0, u = 0;
     uint32_t uses[2] = {0, 0};   // conv positions issued into each accumulator stage so far
@@ -942,37 +962,38 @@ __device__ __forceinline__ void pair_conv_role(long long* pw, const PolicyParams
             mbar_wait_p<kProf>(bars + 8 * PB_HEAD_FULL, head_gen & 1, pw[PW_HEAD_FULL]);
             ++head_gen;
         }
+        if (kNet == 1) mbar_wait_p<kProf>(bars + 8 * PB_D3_FULL, u & 1, pw[PW_D3_FULL]);  // the actor's FC2 of this tile is on its way
         int ox = 0, oy = 0;
         for (int cp = 0; cp < npos; ++cp) {
             const int st = cp & 1;
             if (oy == 0) {  // new window column(s)
                 for (int d = (ox == 0 ? 0 : 2); d < 3; ++d) {
                     const uint32_t g = gcb + ox + d;
-                    mbar_wait_p<kProf>(bars + 8 * (PB_COL_FULL + g % kColRing), (g / kColRing) & 1, pw[PW_COL_FULL]);
+                    mbar_wait_p<kProf>(bars + 8 * (col_full + g % ring), (g / ring) & 1, pw[PW_COL_FULL]);
                 }
             }
             // both epilogue groups have loaded the previous conv position of this stage ...
-            if (uses[st] > 0) mbar_wait_p<kProf>(bars + 8 * (PB_D1_EMPTY + st), (uses[st] - 1) & 1, pw[PW_D1_FULL]);
-            // ... and stage cp (< 2) was D3 of network cp of the previous tile until its head epilogue read it
-            if (u > 0 && cp < 2) mbar_wait_p<kProf>(bars + 8 * (PB_D3_EMPTY + cp), (u - 1) & 1, pw[PW_D3_FULL]);
+            if (uses[st] > 0) mbar_wait_p<kProf>(bars + 8 * (b_empty + st), (uses[st] - 1) & 1, pw[PW_D1_FULL]);
+            // ... and stage cp (< 2) was (part of) D3 of a network of the previous tile until its head epilogue read it
+            if (u > 0 && cp < 2) mbar_wait_p<kProf>(bars + 8 * (PB_D3_EMPTY + (kNet < 0 ? cp : kNet)), (u - 1) & 1, pw[PW_D3_FULL]);
             tc_fence_after();
-            const uint32_t d1 = tmem + kPColD1 + st * kHid;
+            const uint32_t d1 = tmem + kPColD1 + (kNet < 0 ? st * kHid : kNet * kHid + st * kCo);
             const long long ti0 = kProf ? clock64() : 0;
-            if (cp == 3) trace_ev<kProf>(prm, t - t0, 54);  // waits of conv 3 done, issue starts
+            if (cp == 3 && kNet <= 0) trace_ev<kProf>(prm, t - t0, 54);  // waits of conv 3 done, issue starts
             if (elect_one()) {
 #pragma unroll
                 for (int j = 0; j < 9; ++j) {
                     const int dx = j / 3, dy = j - dx * 3;
-                    const uint32_t ta = tmem + kColCells + (((gcb + ox + dx) % kColRing) * H + oy + dy) * kCellCols;
+                    const uint32_t ta = tmem + kColCells + (((gcb + ox + dx) % ring) * H + oy + dy) * kCellCols;
                     umma_bf16_ts(d1, ta, make_desc(a_wchi + j * 256, 128, 2304), idesc, j > 0);
                     umma_bf16_ts(d1, ta, make_desc(a_wclo + j * 256, 128, 2304), idesc, 1);
                 }
-                umma_commit(bars + 8 * (PB_D1_FULL + st));
+                umma_commit(bars + 8 * (b_full + st));
                 if (oy == PH - 1) {  // the window leaves column ox (and the last two columns with the last window)
-                    umma_commit(bars + 8 * (PB_COL_EMPTY + (gcb + ox) % kColRing));
+                    umma_commit(bars + 8 * (col_empty + (gcb + ox) % ring));
                     if (ox == W - 3) {
-                        umma_commit(bars + 8 * (PB_COL_EMPTY + (gcb + ox + 1) % kColRing));
-                        umma_commit(bars + 8 * (PB_COL_EMPTY + (gcb + ox + 2) % kColRing));
+                        umma_commit(bars + 8 * (col_empty + (gcb + ox + 1) % ring));
+                        umma_commit(bars + 8 * (col_empty + (gcb + ox + 2) % ring));
                     }
                 }
                 // last conv of the tile: the conv weights of the head are free once these MMAs complete
@@ -980,7 +1001,7 @@ __device__ __forceinline__ void pair_conv_role(long long* pw, const PolicyParams
             }
             __syncwarp();
             if (kProf) pw[PW_ISSUE_CONV] += clock64() - ti0;
-            if (cp < 8) trace_ev<kProf>(prm, t - t0, 16 + cp);
+            if (cp < 8 && kNet <= 0) trace_ev<kProf>(prm, t - t0, 16 + cp);
             ++uses[st];
             if (++oy == PH) oy = 0, ++ox;
         }
@@ -988,7 +1009,7 @@ __device__ __forceinline__ void pair_conv_role(long long* pw, const PolicyParams
 }
 
 // FC issuer of network g: D2[g] (+)= A[g] x W1_j (j < npos), then D3[g] (+)= A[g] x W2_half (j = npos, npos + 1)
-template <bool kProf>
+template <bool kProf, bool kSplit>
 __device__ __forceinline__ void pair_fc_role(long long* pw, const PolicyParams& prm, const int g, int t0, int t1, const BlobLayout L,
                                              uint32_t tmem, uint32_t a_wring, uint32_t bars) {
     const int npos = prm.npos;
@@ -1010,15 +1031,17 @@ __device__ __forceinline__ void pair_fc_role(long long* pw, const PolicyParams& 
         d1_uses += (uint32_t)(npos + 1 - g) / 2;
         for (int j = 0; j < npos + 2; ++j, ++item) {
             mbar_wait_p<kProf>(bars + 8 * (PB_A2_FULL + g), item & 1, pw[PW_A2_FULL]);
+            if (g == 0 && j == npos) trace_ev<kProf>(prm, t - t0, 62);  // FC2 first half: A operand seen
             // the first FC2 product overwrites accumulator stage g: its last conv position must have been read by BOTH groups
-            if (j == npos) mbar_wait_p<kProf>(bars + 8 * (PB_D1_EMPTY + g), (d1_uses - 1) & 1, pw[PW_D1_FULL]);
+            // (split mode: D3[g] covers the two stages of network g alone, which group g drained before it published this item)
+            if (!kSplit && j == npos) mbar_wait_p<kProf>(bars + 8 * (PB_D1_EMPTY + g), (d1_uses - 1) & 1, pw[PW_D1_FULL]);
             if (w_loaded) mbar_wait_p<kProf>(bars + 8 * (PB_W_FULL + slot), resident ? ((w_gen - 1) & 1) : (wround & 1), pw[PW_W_FULL]);
             tc_fence_after();
             const uint32_t dst = tmem + (j < npos ? kPColD2 : kPColD1) + g * kHid;
             const bool first = (j == 0 || j == npos);
             const uint32_t b_hi = a_wring + slot * kChunk, b_lo = b_hi + 4096;
             const long long tf0 = kProf ? clock64() : 0;
-            if (j == 2) trace_ev<kProf>(prm, t - t0, g == 0 ? 55 : 57);  // waits of FC item 2 done, issue starts
+            if (j == npos) trace_ev<kProf>(prm, t - t0, g == 0 ? 55 : 57);  // waits of the first FC2 item done, issue starts
             if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
@@ -1035,7 +1058,7 @@ __device__ __forceinline__ void pair_fc_role(long long* pw, const PolicyParams& 
             __syncwarp();
             if (kProf) pw[PW_ISSUE_FC] += clock64() - tf0;
             if (g == 0 && j < 8) trace_ev<kProf>(prm, t - t0, 24 + j);
-            if (g == 1 && j == 2) trace_ev<kProf>(prm, t - t0, 58);
+            if (g == 1 && j == npos) trace_ev<kProf>(prm, t - t0, 58);
             slot += 2;
             if (slot >= Reff) slot -= Reff, ++wround;
         }
@@ -1043,7 +1066,7 @@ __device__ __forceinline__ void pair_fc_role(long long* pw, const PolicyParams& 
 }
 
 // `out(t, trow_id, g, head)` consumes the head outputs of row trow_id of tile t (g = 0: six logits, g = 1: head[0] = value)
-template <bool kProf, class Out>
+template <bool kProf, bool kSplit, class Out>
 __device__ __forceinline__ void pair_epilogue_role(long long* pw, const PolicyParams& prm, int t0, int t1, const BlobLayout L, uint32_t tmem,
                                                    const uint8_t* s_head, uint32_t bars, Out&& out) {
     const int warp = threadIdx.x >> 5, g = warp >> 2, trow_id = (warp & 3) * 32 + (threadIdx.x & 31);
@@ -1093,14 +1116,15 @@ __device__ __forceinline__ void pair_epilogue_role(long long* pw, const PolicyPa
         trace_vt = t - t0, trace_item = 0;
         for (int j = 0; j < npos; ++j) {
             const int st = j & 1;
-            mbar_wait_p<kProf>(bars + 8 * (PB_D1_FULL + st), (d1_par >> st) & 1, pw[PW_D1_FULL]);
+            mbar_wait_p<kProf>(bars + 8 * ((kSplit ? PBS_D1_FULL + 2 * g : PB_D1_FULL) + st), (d1_par >> st) & 1, pw[PW_D1_FULL]);
             if (kProf && warp == 0 && j < 8) trace_ev<kProf>(prm, trace_vt, 32 + j);
             d1_par ^= 1u << st;
             tc_fence_after();
             float v[32];
-            tmem_ld32(trow + kPColD1 + st * kHid + g * kCo, v);
+            tmem_ld32(trow + kPColD1 + (kSplit ? g * kHid + st * kCo : st * kHid + g * kCo), v);
             tc_fence_before();
-            mbar_arrive(bars + 8 * (PB_D1_EMPTY + st));  // the conv issuer may overwrite this stage (after the other group too)
+            // the conv issuer may overwrite this stage (pair kernel: once the other group has read its half too)
+            mbar_arrive(bars + 8 * ((kSplit ? PBS_D1_EMPTY + 2 * g : PB_D1_EMPTY) + st));
             if (kProf && warp == 0 && j == 2) trace_ev<kProf>(prm, trace_vt, 59);  // accumulator in registers
             publish(v, s_bias1 + j * kCo);
         }
@@ -1206,15 +1230,15 @@ __global__ void __launch_bounds__(kPThreads, 1) policy_pair_kernel(const PolicyP
     long long pw[kProf ? PW_COUNT : 1] = {};
     const long long t_begin = kProf ? clock64() : 0;
     if (warp < kEpiWarps) {
-        pair_epilogue_role<kProf>(pw, prm, ur.t0, ur.t1, L, tmem, s_head, bars, PairForwardOut(prm));
+        pair_epilogue_role<kProf, false>(pw, prm, ur.t0, ur.t1, L, tmem, s_head, bars, PairForwardOut(prm));
     } else if (warp < kWarpMma) {
         loader_role<kProf>(pw, prm, ur, tmem, s_stage, bars);
     } else if (warp == kWarpMma) {
-        pair_conv_role<kProf>(pw, prm, ur.t0, ur.t1, L, tmem, smem_addr(s_head), bars);
+        pair_conv_role<kProf, -1>(pw, prm, ur.t0, ur.t1, L, tmem, smem_addr(s_head), bars);
     } else if (warp == kWarpProd) {
         pair_producer_role<kProf>(pw, prm, ur.t0, ur.t1, L, smem_addr(s_head), smem_addr(s_wring), bars);
     } else {
-        pair_fc_role<kProf>(pw, prm, warp - kWarpFc, ur.t0, ur.t1, L, tmem, smem_addr(s_wring), bars);
+        pair_fc_role<kProf, false>(pw, prm, warp - kWarpFc, ur.t0, ur.t1, L, tmem, smem_addr(s_wring), bars);
     }
     if (kProf && prm.prof != nullptr &&
         (tid == 0 || tid == 32 * kEpiWarps || tid == 32 * kWarpMma || tid == 32 * kWarpProd)) {
@@ -1378,8 +1402,10 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
     if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(conv512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(gemm512_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(gemm512_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
@@ -1751,10 +1777,25 @@ int ocb_policy_rollout_fused_launch(ocb_policy* p, int policy_index, const Rollo
         const char* e = getenv("OCB_FUSED_VEC_LOADER");
         fp.vec_loader = e != nullptr ? (e[0] != '0') : (p->SC % 16 == 0);
     }
-    if (d_trace != nullptr)
-        rollout_fused_kernel<true><<<ctas, kFThreads, smem, (cudaStream_t)stream>>>(fp);
-    else
-        rollout_fused_kernel<false><<<ctas, kFThreads, smem, (cudaStream_t)stream>>>(fp);
+    {   // split mode (the critic's conv stream deferred behind the actor's FC2): needs every grid column of a tile resident
+        const int slots = 192 / (kCellCols * p->H);
+        const char* e = getenv("OCB_FUSED_SPLIT");
+        const bool want = e != nullptr ? (e[0] != '0') : true;
+        fp.col_ring = (want && slots >= p->W) ? (p->W < kFMaxColRing ? p->W : kFMaxColRing) : 0;
+        if (fp.col_ring < p->W) fp.col_ring = 0;
+    }
+    if (fp.col_ring > 0) {
+        if (d_trace != nullptr)
+            rollout_fused_kernel<true, true><<<ctas, kFThreads, smem, (cudaStream_t)stream>>>(fp);
+        else
+            rollout_fused_kernel<false, true><<<ctas, kFThreads, smem, (cudaStream_t)stream>>>(fp);
+    } else {
+        fp.col_ring = kColRing;
+        if (d_trace != nullptr)
+            rollout_fused_kernel<true, false><<<ctas, kFThreads, smem, (cudaStream_t)stream>>>(fp);
+        else
+            rollout_fused_kernel<false, false><<<ctas, kFThreads, smem, (cudaStream_t)stream>>>(fp);
+    }
     if (d_counter != nullptr)
         counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(d_counter), (unsigned long long)T);
     cudaError_t err = cudaGetLastError();

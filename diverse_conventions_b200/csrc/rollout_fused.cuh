@@ -31,19 +31,24 @@ struct FusedParams {
     int32_t* reward;     // [T][2][N] or nullptr
     int32_t* done;       // [T][N] or nullptr
     int vec_loader;      // loaders read the planes as 16-byte vectors (conflict-free) instead of 4-byte words
+    int col_ring;        // grid columns resident in the cell region: W in split mode (whole grid), else kColRing
 };
 
 constexpr int kFEnvWarps = 2;
-constexpr int kFWarpEnv = kWarpFc + 2;                      // warps 20, 21
-constexpr int kFThreads = kPThreads + 32 * kFEnvWarps;      // 704
+constexpr int kFWarpConvC = kWarpFc + 2;                    // warp 20: conv issuer of the critic (warp kWarpMma issues the actor's)
+constexpr int kFWarpEnv = kFWarpConvC + 1;                  // warps 21, 22
+constexpr int kFThreads = 32 * (kFWarpEnv + kFEnvWarps);    // 736
 constexpr int kFWorlds = 32 * kFEnvWarps;                   // worlds per CTA tile
+constexpr int kFMaxColRing = 6;  // 192 cell columns / (8 columns x H = 4)
 enum : int {
     FB_OBS_FULL = PB_COUNT,      // env warps (64 arrivals) -> loaders: planes of virtual tile vt are complete
     FB_OBS_EMPTY = PB_COUNT + 1, // loaders (256 arrivals) -> env warps: planes of vt have been consumed
     FB_ACT_FULL = PB_COUNT + 2,  // actor epilogue group (128 arrivals) -> env warps
-    FB_COUNT = PB_COUNT + 3
+    FB_COL_FULL = PB_COUNT + 3,  // [6] split mode: loader -> both conv issuers (128 arrivals)
+    FB_COL_EMPTY = FB_COL_FULL + kFMaxColRing,  // [6] split mode: both conv issuers' commits (2) -> loader
+    FB_COUNT = FB_COL_EMPTY + kFMaxColRing
 };
-constexpr int kFActSlot = 80;  // 8-byte slots 80..95 of the barrier block hold the tile's 128 sampled actions (bytes)
+constexpr int kFActSlot = 100;  // 8-byte slots 100..115 of the barrier block hold the tile's 128 sampled actions (bytes)
 static_assert((int)FB_COUNT <= kFActSlot && kFActSlot + 16 <= (int)PB_TMEM_SLOT, "barrier block overflow");
 
 struct FusedSmemLayout {
@@ -70,7 +75,7 @@ __host__ __device__ inline FusedSmemLayout fused_smem_layout(int npos, int ring,
 
 // loaders: shared-memory planes -> bf16 cell blocks in TMEM.  Thread (lw, lane) owns row 32 lw + lane
 // = seat lw / 2, env warp lw % 2, world `lane`; the two groups take alternate columns of the stream.
-template <bool kProf>
+template <bool kProf, bool kSplit>
 __device__ __forceinline__ void fused_loader_role(const FusedParams& fp, uint32_t nvt, uint32_t tmem, const uint8_t* s_env,
                                                   const FusedSmemLayout& sl, uint32_t bars) {
     const int lwarp = (threadIdx.x >> 5) - kEpiWarps, lg = lwarp >> 2, lw = lwarp & 3, lane = threadIdx.x & 31;
@@ -89,9 +94,10 @@ __device__ __forceinline__ void fused_loader_role(const FusedParams& fp, uint32_
         }
         const bool first_col = fresh;
         fresh = false;
-        const int slot = gc % kColRing;
-        if (gc >= kColRing) {
-            mbar_wait(bars + 8 * (PB_COL_EMPTY + slot), ((gc / kColRing) - 1) & 1);
+        const uint32_t ring = kSplit ? (uint32_t)fp.col_ring : (uint32_t)kColRing;
+        const int slot = gc % ring;
+        if (gc >= ring) {
+            mbar_wait(bars + 8 * ((kSplit ? FB_COL_EMPTY : PB_COL_EMPTY) + slot), ((gc / ring) - 1) & 1);
             tc_fence_after();
         }
         if (fp.vec_loader) {
@@ -146,7 +152,7 @@ __device__ __forceinline__ void fused_loader_role(const FusedParams& fp, uint32_
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(bars + 8 * (PB_COL_FULL + slot));
+        mbar_arrive(bars + 8 * ((kSplit ? FB_COL_FULL : PB_COL_FULL) + slot));
         if (kProf && lwarp == 0 && first_col) trace_ev<kProf>(fp.pol, (int)lt, 9);
         lx += 2;
         if (lx >= W) {  // this group's last column of the tile: its plane reads are done
@@ -196,6 +202,13 @@ __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s
             bool full = true;
             int oldslot[P] = {0, 0};
             uint32_t dirty[P] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+            // the planes still hold virtual tile vt - 1: its loaders and its bulk store must be done with them (both finish
+            // long before the actions arrive, so these waits sit before the action wait, off the critical path)
+            if (vt > 0) mbar_wait(bars + 8 * FB_OBS_EMPTY, (vt - 1) & 1);
+            if (tma_pending) {
+                if (lane == 0) bulk_wait_read_all();
+                tma_pending = false;
+            }
             if (u > 0) {
                 mbar_wait(bars + 8 * FB_ACT_FULL, acts & 1);
                 if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)vt, 0);
@@ -224,12 +237,6 @@ __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s
                 }
                 full = done;
                 if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)vt, 1);
-            }
-            // the planes still hold virtual tile vt - 1: its loaders and its bulk store must be done with them
-            if (vt > 0) mbar_wait(bars + 8 * FB_OBS_EMPTY, (vt - 1) & 1);
-            if (tma_pending) {
-                if (lane == 0) bulk_wait_read_all();
-                tma_pending = false;
             }
             __syncwarp();
             if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)vt, 2);
@@ -298,15 +305,14 @@ struct FusedOut {
             PolicyParams op = fp.pol;  // output pointers of this step; rows past N sample but store nothing
             const bool valid = n < N;
             op.actions = valid ? fp.actions : nullptr, op.logp = valid ? fp.logp : nullptr, op.logits = nullptr;
-            const int act = emit_actor_row(op, store, (uint32_t)row, head, base + (unsigned long long)u, true, &drawn);
-            s_act[trow_id] = (uint8_t)act;
-            mbar_arrive(bars + 8 * FB_ACT_FULL);
+            emit_actor_row(op, store, (uint32_t)row, head, base + (unsigned long long)u, true, &drawn, s_act + trow_id,
+                           bars + 8 * FB_ACT_FULL);
         }
         if (++u > fp.T) u = 0, kt += gridDim.x;
     }
 };
 
-template <bool kProf>
+template <bool kProf, bool kSplit>
 __global__ void __launch_bounds__(kFThreads, 1) rollout_fused_kernel(const FusedParams fp) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
@@ -336,8 +342,11 @@ __global__ void __launch_bounds__(kFThreads, 1) rollout_fused_kernel(const Fused
             if ((i >= PB_COL_FULL && i < PB_COL_FULL + 4) || (i >= PB_A2_FULL && i < PB_A2_FULL + 2) ||
                 (i >= PB_D3_EMPTY && i < PB_D3_EMPTY + 2))
                 count = 128;
-            if (i >= PB_HEAD_EMPTY && i < PB_HEAD_EMPTY + 2) count = 32 * kEpiWarps + 1;
+            if (i >= PB_HEAD_EMPTY && i < PB_HEAD_EMPTY + 2) count = 32 * kEpiWarps + (kSplit ? 2 : 1);
             if (i >= PB_D1_EMPTY && i < PB_D1_EMPTY + 2) count = 32 * kEpiWarps;
+            if (i >= PBS_D1_EMPTY && i < PBS_D1_EMPTY + 4) count = 128;
+            if (i >= FB_COL_FULL && i < FB_COL_FULL + kFMaxColRing) count = 128;
+            if (i >= FB_COL_EMPTY && i < FB_COL_EMPTY + kFMaxColRing) count = 2;  // both conv streams have read the column
             if (i == FB_OBS_FULL) count = 32 * kFEnvWarps;
             if (i == FB_OBS_EMPTY) count = 32 * kLoadWarps;
             if (i == FB_ACT_FULL) count = 128;
@@ -361,15 +370,21 @@ __global__ void __launch_bounds__(kFThreads, 1) rollout_fused_kernel(const Fused
 
     long long pw[kProf ? PW_COUNT : 1] = {};
     if (warp < kEpiWarps) {
-        pair_epilogue_role<kProf>(pw, prm, 0, nvt, L, tmem, s_head, bars, FusedOut(fp, s_act, bars));
+        pair_epilogue_role<kProf, kSplit>(pw, prm, 0, nvt, L, tmem, s_head, bars, FusedOut(fp, s_act, bars));
     } else if (warp < kWarpMma) {
-        fused_loader_role<kProf>(fp, (uint32_t)nvt, tmem, s_env, sl, bars);
+        fused_loader_role<kProf, kSplit>(fp, (uint32_t)nvt, tmem, s_env, sl, bars);
     } else if (warp == kWarpMma) {
-        pair_conv_role<kProf>(pw, prm, 0, nvt, L, tmem, smem_addr(s_head), bars);
+        if (kSplit)
+            pair_conv_role<kProf, 0>(pw, prm, 0, nvt, L, tmem, smem_addr(s_head), bars, (uint32_t)fp.col_ring, FB_COL_FULL, FB_COL_EMPTY);
+        else
+            pair_conv_role<kProf, -1>(pw, prm, 0, nvt, L, tmem, smem_addr(s_head), bars);
     } else if (warp == kWarpProd) {
         pair_producer_role<kProf>(pw, prm, 0, nvt, L, smem_addr(s_head), smem_addr(s_wring), bars);
-    } else if (warp < kFWarpEnv) {
-        pair_fc_role<kProf>(pw, prm, warp - kWarpFc, 0, nvt, L, tmem, smem_addr(s_wring), bars);
+    } else if (warp < kFWarpConvC) {
+        pair_fc_role<kProf, kSplit>(pw, prm, warp - kWarpFc, 0, nvt, L, tmem, smem_addr(s_wring), bars);
+    } else if (warp == kFWarpConvC) {
+        if (kSplit)
+            pair_conv_role<kProf, 1>(pw, prm, 0, nvt, L, tmem, smem_addr(s_head), bars, (uint32_t)fp.col_ring, FB_COL_FULL, FB_COL_EMPTY);
     } else {
         fused_env_role<kProf>(fp, s_env, sl, *s_tables, s_tmpl, s_act, bars);
     }
