@@ -841,8 +841,12 @@ constexpr int kPColD1 = 192;   // conv accumulators: stage s at + 64 s (actor 32
 constexpr int kPColA2 = 320;   // A operand of net g at + 32 g (hi 16 | lo 16)
 constexpr int kPColD2 = 384;   // FC1 accumulator of net g at + 64 g
 constexpr int kPMaxRing = 24;  // weight-ring slots (chunks of both networks)
-constexpr int kWarpFc = kWarpProd + 1;          // warps 18, 19: FC issuers of the actor / the critic
-constexpr int kPThreads = 32 * (kWarpFc + 2);   // 640: 8 epilogue + 8 loader + conv issuer + producer + 2 FC issuers
+// The four MMA issuers sit on four different SM sub-partitions (warp % 4): each UTCHMMA needs its operands moved into
+// uniform registers, and two issuers on one sub-partition share that datapath (measured: no gain from the second one).
+constexpr int kWarpConv2 = kWarpMma + 1;        // warp 17: second conv issuer (odd positions; warp kWarpMma = 16 issues the even ones)
+constexpr int kWarpFc = kWarpConv2 + 1;         // warps 18, 19: FC issuers of the actor / the critic
+constexpr int kPWarpProd = kWarpFc + 2;         // warp 20: weight producer of the pair / fused kernels
+constexpr int kPThreads = 32 * (kPWarpProd + 1);  // 672: 8 epilogue + 8 loader + 2 conv issuers + 2 FC issuers + producer
 constexpr int kPConvBytes = 9216;  // one network's conv weights, hi or lo
 constexpr int kPRestOff = 4 * kPConvBytes;  // per-network remainder of the head (bias1 .. bh) starts here
 enum : int {
@@ -944,10 +948,15 @@ __device__ __forceinline__ void pair_producer_role(long long* pw, const PolicyPa
 // under the head / sampling / env step / plane loading of the next step.  Same products per output element, same order.
 // `ring` grid columns are resident in the cell region (barriers col_full + slot / col_empty + slot): 4 in the pair kernel;
 // the split mode needs the WHOLE grid resident (ring >= W), because the critic's stream starts after the actor's finished.
+// An issuer handles the conv positions cp0, cp0 + cpstep, ... of every tile: with cpstep = 2 two warps share a stream
+// (position parity == accumulator stage), because ONE thread issuing 18 MMAs + commits + its waits per position
+// (~1.15 k cycles, tools/fused_trace.py) is slower than the epilogue that consumes them.  Every issuer releases a grid
+// column (col_empty) once none of ITS later positions reads it; the barrier counts the issuers.
 template <bool kProf, int kNet>
 __device__ __forceinline__ void pair_conv_role(long long* pw, const PolicyParams& prm, int t0, int t1, const BlobLayout L, uint32_t tmem,
-                                               uint32_t a_head, uint32_t bars, const uint32_t ring = kColRing,
-                                               const int col_full = PB_COL_FULL, const int col_empty = PB_COL_EMPTY) {
+                                               uint32_t a_head, uint32_t bars, const int cp0 = 0, const int cpstep = 1,
+                                               const uint32_t ring = kColRing, const int col_full = PB_COL_FULL,
+                                               const int col_empty = PB_COL_EMPTY) {
     const int W = prm.W, H = prm.H, PH = H - 2, npos = prm.npos;
     constexpr int kN = kNet < 0 ? kHid : kCo;
     const uint32_t idesc = make_idesc(kRows, kN);  // N = 64: actor channels 0-31 | critic channels 32-63
@@ -955,31 +964,40 @@ __device__ __forceinline__ void pair_conv_role(long long* pw, const PolicyParams
     const int b_full = kNet < 0 ? PB_D1_FULL : PBS_D1_FULL + 2 * kNet, b_empty = kNet < 0 ? PB_D1_EMPTY : PBS_D1_EMPTY + 2 * kNet;
     uint32_t gcb = 0;            // running column index of grid column 0 of the tile
     uint32_t head_gen = 0, u = 0;
-    uint32_t uses[2] = {0, 0};   // conv positions issued into each accumulator stage so far
+    uint32_t uses[2] = {0, 0};   // conv positions THIS issuer put into each accumulator stage so far
+    const bool tracer = kNet <= 0;
 
     for (int t = t0; t < t1; ++t, ++u, gcb += W) {
         if (blob_changed(prm, t, t0)) {
             mbar_wait_p<kProf>(bars + 8 * PB_HEAD_FULL, head_gen & 1, pw[PW_HEAD_FULL]);
             ++head_gen;
         }
-        if (kNet == 1) mbar_wait_p<kProf>(bars + 8 * PB_D3_FULL, u & 1, pw[PW_D3_FULL]);  // the actor's FC2 of this tile is on its way
-        int ox = 0, oy = 0;
-        for (int cp = 0; cp < npos; ++cp) {
-            const int st = cp & 1;
-            if (oy == 0) {  // new window column(s)
-                for (int d = (ox == 0 ? 0 : 2); d < 3; ++d) {
-                    const uint32_t g = gcb + ox + d;
-                    mbar_wait_p<kProf>(bars + 8 * (col_full + g % ring), (g / ring) & 1, pw[PW_COL_FULL]);
-                }
+        if (kNet == 1) {
+            // the critic's stream starts when the actor's LAST conv position of this tile has completed: the pipe carried only
+            // the actor during its conv phase, and the critic's conv (one issuer, ~1.1 k cycles per position) still ends
+            // before the loaders of the next step want the cell columns back
+            const int s_last = (npos - 1) & 1;
+            const uint32_t cum = (u + 1) * (uint32_t)((npos + 1 - s_last) / 2);
+            mbar_wait_p<kProf>(bars + 8 * (PBS_D1_FULL + s_last), (cum - 1) & 1, pw[PW_D3_FULL]);
+        }
+        int cols_seen = 0, released = 0;  // grid columns of this tile waited for / released by this issuer
+        for (int cp = cp0; cp < npos; cp += cpstep) {
+            const int ox = cp / PH, oy = cp - ox * PH, st = cp & 1;
+            for (; cols_seen < ox + 3; ++cols_seen) {  // new window column(s)
+                const uint32_t g = gcb + cols_seen;
+                mbar_wait_p<kProf>(bars + 8 * (col_full + g % ring), (g / ring) & 1, pw[PW_COL_FULL]);
             }
-            // both epilogue groups have loaded the previous conv position of this stage ...
+            // the stage's previous conv position has been loaded by its reader(s): with cpstep = 2 the stage belongs to this
+            // issuer alone; with cpstep = 1 the issuer alternates stages and counts per stage
             if (uses[st] > 0) mbar_wait_p<kProf>(bars + 8 * (b_empty + st), (uses[st] - 1) & 1, pw[PW_D1_FULL]);
             // ... and stage cp (< 2) was (part of) D3 of a network of the previous tile until its head epilogue read it
             if (u > 0 && cp < 2) mbar_wait_p<kProf>(bars + 8 * (PB_D3_EMPTY + (kNet < 0 ? cp : kNet)), (u - 1) & 1, pw[PW_D3_FULL]);
             tc_fence_after();
             const uint32_t d1 = tmem + kPColD1 + (kNet < 0 ? st * kHid : kNet * kHid + st * kCo);
+            const int nxt = cp + cpstep;
+            const int keep = nxt < npos ? nxt / PH : W;  // first grid column a later position of this issuer still reads
             const long long ti0 = kProf ? clock64() : 0;
-            if (cp == 3 && kNet <= 0) trace_ev<kProf>(prm, t - t0, 54);  // waits of conv 3 done, issue starts
+            if (cp == 3 && tracer) trace_ev<kProf>(prm, t - t0, 54);  // waits of conv 3 done, issue starts
             if (elect_one()) {
 #pragma unroll
                 for (int j = 0; j < 9; ++j) {
@@ -989,21 +1007,15 @@ __device__ __forceinline__ void pair_conv_role(long long* pw, const PolicyParams
                     umma_bf16_ts(d1, ta, make_desc(a_wclo + j * 256, 128, 2304), idesc, 1);
                 }
                 umma_commit(bars + 8 * (b_full + st));
-                if (oy == PH - 1) {  // the window leaves column ox (and the last two columns with the last window)
-                    umma_commit(bars + 8 * (col_empty + (gcb + ox) % ring));
-                    if (ox == W - 3) {
-                        umma_commit(bars + 8 * (col_empty + (gcb + ox + 1) % ring));
-                        umma_commit(bars + 8 * (col_empty + (gcb + ox + 2) % ring));
-                    }
-                }
-                // last conv of the tile: the conv weights of the head are free once these MMAs complete
-                if (cp + 1 == npos) umma_commit(bars + 8 * (PB_HEAD_EMPTY + (u & 1)));
+                for (int c = released; c < keep; ++c) umma_commit(bars + 8 * (col_empty + (gcb + c) % ring));
+                // last conv of this issuer in the tile: its reads of the conv weights are done once these MMAs complete
+                if (nxt >= npos) umma_commit(bars + 8 * (PB_HEAD_EMPTY + (u & 1)));
             }
             __syncwarp();
+            released = keep > released ? keep : released;
             if (kProf) pw[PW_ISSUE_CONV] += clock64() - ti0;
-            if (cp < 8 && kNet <= 0) trace_ev<kProf>(prm, t - t0, 16 + cp);
+            if (cp < 8 && tracer) trace_ev<kProf>(prm, t - t0, 16 + cp);
             ++uses[st];
-            if (++oy == PH) oy = 0, ++ox;
         }
     }
 }
@@ -1211,7 +1223,8 @@ __global__ void __launch_bounds__(kPThreads, 1) policy_pair_kernel(const PolicyP
             if ((i >= PB_COL_FULL && i < PB_COL_FULL + 4) || (i >= PB_A2_FULL && i < PB_A2_FULL + 2) ||
                 (i >= PB_D3_EMPTY && i < PB_D3_EMPTY + 2))
                 count = 128;
-            if (i >= PB_HEAD_EMPTY && i < PB_HEAD_EMPTY + 2) count = 32 * kEpiWarps + 1;
+            if (i >= PB_COL_EMPTY && i < PB_COL_EMPTY + 4) count = 2;  // both conv issuers are done with the column
+            if (i >= PB_HEAD_EMPTY && i < PB_HEAD_EMPTY + 2) count = 32 * kEpiWarps + 2;
             if (i >= PB_D1_EMPTY && i < PB_D1_EMPTY + 2) count = 32 * kEpiWarps;
             mbar_init(bars + 8 * i, count);
         }
@@ -1233,15 +1246,15 @@ __global__ void __launch_bounds__(kPThreads, 1) policy_pair_kernel(const PolicyP
         pair_epilogue_role<kProf, false>(pw, prm, ur.t0, ur.t1, L, tmem, s_head, bars, PairForwardOut(prm));
     } else if (warp < kWarpMma) {
         loader_role<kProf>(pw, prm, ur, tmem, s_stage, bars);
-    } else if (warp == kWarpMma) {
-        pair_conv_role<kProf, -1>(pw, prm, ur.t0, ur.t1, L, tmem, smem_addr(s_head), bars);
-    } else if (warp == kWarpProd) {
+    } else if (warp == kWarpMma || warp == kWarpConv2) {
+        pair_conv_role<kProf, -1>(pw, prm, ur.t0, ur.t1, L, tmem, smem_addr(s_head), bars, warp == kWarpMma ? 0 : 1, 2);
+    } else if (warp == kPWarpProd) {
         pair_producer_role<kProf>(pw, prm, ur.t0, ur.t1, L, smem_addr(s_head), smem_addr(s_wring), bars);
     } else {
         pair_fc_role<kProf, false>(pw, prm, warp - kWarpFc, ur.t0, ur.t1, L, tmem, smem_addr(s_wring), bars);
     }
     if (kProf && prm.prof != nullptr &&
-        (tid == 0 || tid == 32 * kEpiWarps || tid == 32 * kWarpMma || tid == 32 * kWarpProd)) {
+        (tid == 0 || tid == 32 * kEpiWarps || tid == 32 * kWarpMma || tid == 32 * kPWarpProd)) {
         pw[PW_TOTAL] = clock64() - t_begin;
         const int role = tid == 0 ? 0 : tid == 32 * kEpiWarps ? 1 : tid == 32 * kWarpMma ? 2 : 3;
         for (int i = 0; i < PW_COUNT; ++i) prm.prof[((size_t)blockIdx.x * 4 + role) * PW_COUNT + i] = pw[i];

@@ -35,9 +35,9 @@ struct FusedParams {
 };
 
 constexpr int kFEnvWarps = 2;
-constexpr int kFWarpConvC = kWarpFc + 2;                    // warp 20: conv issuer of the critic (warp kWarpMma issues the actor's)
-constexpr int kFWarpEnv = kFWarpConvC + 1;                  // warps 21, 22
-constexpr int kFThreads = 32 * (kFWarpEnv + kFEnvWarps);    // 736
+constexpr int kFWarpConvC = kPWarpProd + 1;                 // warp 21: conv issuer of the critic (split mode; warps 16 / 17 issue the actor's)
+constexpr int kFWarpEnv = kFWarpConvC + 1;                  // warps 22, 23
+constexpr int kFThreads = 32 * (kFWarpEnv + kFEnvWarps);    // 768
 constexpr int kFWorlds = 32 * kFEnvWarps;                   // worlds per CTA tile
 constexpr int kFMaxColRing = 6;  // 192 cell columns / (8 columns x H = 4)
 enum : int {
@@ -342,11 +342,12 @@ __global__ void __launch_bounds__(kFThreads, 1) rollout_fused_kernel(const Fused
             if ((i >= PB_COL_FULL && i < PB_COL_FULL + 4) || (i >= PB_A2_FULL && i < PB_A2_FULL + 2) ||
                 (i >= PB_D3_EMPTY && i < PB_D3_EMPTY + 2))
                 count = 128;
-            if (i >= PB_HEAD_EMPTY && i < PB_HEAD_EMPTY + 2) count = 32 * kEpiWarps + (kSplit ? 2 : 1);
+            if (i >= PB_COL_EMPTY && i < PB_COL_EMPTY + 4) count = 2;  // plain mode: two conv issuers
+            if (i >= PB_HEAD_EMPTY && i < PB_HEAD_EMPTY + 2) count = 32 * kEpiWarps + (kSplit ? 3 : 2);
             if (i >= PB_D1_EMPTY && i < PB_D1_EMPTY + 2) count = 32 * kEpiWarps;
             if (i >= PBS_D1_EMPTY && i < PBS_D1_EMPTY + 4) count = 128;
             if (i >= FB_COL_FULL && i < FB_COL_FULL + kFMaxColRing) count = 128;
-            if (i >= FB_COL_EMPTY && i < FB_COL_EMPTY + kFMaxColRing) count = 2;  // both conv streams have read the column
+            if (i >= FB_COL_EMPTY && i < FB_COL_EMPTY + kFMaxColRing) count = 3;  // the actor's two issuers and the critic's one
             if (i == FB_OBS_FULL) count = 32 * kFEnvWarps;
             if (i == FB_OBS_EMPTY) count = 32 * kLoadWarps;
             if (i == FB_ACT_FULL) count = 128;
@@ -373,18 +374,21 @@ __global__ void __launch_bounds__(kFThreads, 1) rollout_fused_kernel(const Fused
         pair_epilogue_role<kProf, kSplit>(pw, prm, 0, nvt, L, tmem, s_head, bars, FusedOut(fp, s_act, bars));
     } else if (warp < kWarpMma) {
         fused_loader_role<kProf, kSplit>(fp, (uint32_t)nvt, tmem, s_env, sl, bars);
-    } else if (warp == kWarpMma) {
+    } else if (warp == kWarpMma || warp == kWarpConv2) {
+        const int half = warp == kWarpMma ? 0 : 1;
         if (kSplit)
-            pair_conv_role<kProf, 0>(pw, prm, 0, nvt, L, tmem, smem_addr(s_head), bars, (uint32_t)fp.col_ring, FB_COL_FULL, FB_COL_EMPTY);
+            pair_conv_role<kProf, 0>(pw, prm, 0, nvt, L, tmem, smem_addr(s_head), bars, half, 2, (uint32_t)fp.col_ring, FB_COL_FULL,
+                                     FB_COL_EMPTY);
         else
-            pair_conv_role<kProf, -1>(pw, prm, 0, nvt, L, tmem, smem_addr(s_head), bars);
-    } else if (warp == kWarpProd) {
+            pair_conv_role<kProf, -1>(pw, prm, 0, nvt, L, tmem, smem_addr(s_head), bars, half, 2);
+    } else if (warp == kPWarpProd) {
         pair_producer_role<kProf>(pw, prm, 0, nvt, L, smem_addr(s_head), smem_addr(s_wring), bars);
-    } else if (warp < kFWarpConvC) {
+    } else if (warp < kPWarpProd) {
         pair_fc_role<kProf, kSplit>(pw, prm, warp - kWarpFc, 0, nvt, L, tmem, smem_addr(s_wring), bars);
     } else if (warp == kFWarpConvC) {
         if (kSplit)
-            pair_conv_role<kProf, 1>(pw, prm, 0, nvt, L, tmem, smem_addr(s_head), bars, (uint32_t)fp.col_ring, FB_COL_FULL, FB_COL_EMPTY);
+            pair_conv_role<kProf, 1>(pw, prm, 0, nvt, L, tmem, smem_addr(s_head), bars, 0, 1, (uint32_t)fp.col_ring, FB_COL_FULL,
+                                     FB_COL_EMPTY);
     } else {
         fused_env_role<kProf>(fp, s_env, sl, *s_tables, s_tmpl, s_act, bars);
     }

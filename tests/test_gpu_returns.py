@@ -96,10 +96,14 @@ def test_device_resident_valuenorm_statistics_give_the_same_bits_without_a_host_
     r = _dev(rng.choice([0, 0, 3, 20], size=(T, 1, N)).repeat(P, axis=1).astype(np.int32), torch.int32)
     d = _dev((rng.random((T, N)) < 0.05).astype(np.int32), torch.int32)
 
-    class DevVN(_VN):
+    class DevVN(_VN):  # statistics live on the device, like ppo.ValueNormState or a reference ValueNorm moved to the GPU
+        def __init__(self, mean, std):
+            super().__init__(mean, std)
+            m, var = _VN.running_mean_var(self)
+            self.dm, self.dvar = m.cuda(), var.cuda()
+
         def running_mean_var(self):
-            m, var = super().running_mean_var()
-            return m.cuda(), var.cuda()
+            return self.dm, self.dvar
 
     host = R.compute_returns(v, r, d, 0.99, 0.95, True, _VN(1.25, 2.5), normalize=False)
     dev = R.compute_returns(v, r, d, 0.99, 0.95, True, DevVN(1.25, 2.5), normalize=False)

@@ -82,7 +82,7 @@ def run_main_player(ns, envs, device, args, run_dir, episodes=2):
             ep = {"buffer": snapshot(ego.buffer), "scores": list(ego.scores)}
             ego.compute()
             ep["returns"] = ego.buffer.returns.detach().cpu().clone()
-            ep["train_infos"] = {k: float(v) for k, v in ego.train().items()}
+            ep["train_infos"] = {k: float(v.detach() if torch.is_tensor(v) else v) for k, v in ego.train().items()}
             out["episodes"].append(ep)
     out["actor"] = [p.detach().cpu().clone() for p in ego.policy.actor.parameters()]
     out["player"] = ego

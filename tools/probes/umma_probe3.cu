@@ -5,7 +5,10 @@
 //   bmode 2: as 1, alternating between two operands 18 KB apart (hi / lo)
 //   bmode 3: B rotates over 8 [64 x 32] chunks (LBO 128, SBO 512: the FC weights)
 //   dol    : the {0,0,0,0} disable-output-lane form of the instruction (what policy_kernels.cu issues)
-//   traffic: 0 none | 1 eight other warps loop tcgen05.ld 32x32b.x32 | 2 they loop tcgen05.st x16 + wait
+//   traffic: 0 none | 1 eight other warps loop tcgen05.ld 32x32b.x32 | 2 they loop tcgen05.st x16 + wait |
+//            3 they stream shared memory with 16-byte loads (the B operand competes for the 128 B/clk pipe) |
+//            4 they loop ld x32 + 2 x st x16 like the epilogue groups |
+//            5 they run ALU-bound loops (issue-slot competition on the issuer's SM sub-partition)
 //   nA     : distinct A tiles in TMEM
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_probe3_probe umma_probe3.cu
 #include <cuda_runtime.h>
@@ -120,7 +123,43 @@ __global__ void __launch_bounds__(384, 1) probe(int N, int nacc, int nA, int ite
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 r[0] ^= v[3];
+            } else if (traffic == 5) {
+                float f0 = (float)r[0], f1 = (float)r[1], f2 = (float)r[2], f3 = (float)r[3];
+#pragma unroll 16
+                for (int i = 0; i < 256; ++i) {
+                    f0 = fmaf(f0, 1.0001f, 0.5f), f1 = fmaf(f1, 0.9999f, 0.25f), f2 = fmaf(f2, 1.0002f, 0.125f), f3 = fmaf(f3, 0.9998f, 1.0f);
+                }
+                r[0] = __float_as_uint(f0 + f1 + f2 + f3);
+            } else if (traffic == 3) {
+                const uint4* sp = reinterpret_cast<const uint4*>(smem + 64 * 1024) + threadIdx.x;
+                uint4 acc = make_uint4(0, 0, 0, 0);
+#pragma unroll 8
+                for (int i = 0; i < 64; ++i) {
+                    const uint4 q = sp[(i & 7) * 384];
+                    acc.x ^= q.x, acc.y ^= q.y, acc.z ^= q.z, acc.w ^= q.w;
+                }
+                r[0] ^= acc.x ^ acc.y ^ acc.z ^ acc.w;
             } else {
+                if (traffic == 4) {
+                    uint32_t v[32];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] ^= v[i] + v[16 + i];
+                    asm volatile(
+                        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::
+                            "r"(taddr + 32), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+                        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                        : "memory");
+                }
                 asm volatile(
                     "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::
                         "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
@@ -154,10 +193,10 @@ int main() {
     long long* d_out;
     cudaMalloc(&d_out, 16);
     printf("%4s %5s %4s %-28s %4s %-8s %10s\n", "N", "nacc", "nA", "B operand", "dol", "traffic", "cyc/MMA");
-    const char* tn[3] = {"none", "ld x32", "st x16"};
+    const char* tn[6] = {"none", "ld x32", "st x16", "smem", "epi-like", "alu"};
     for (int N : {64, 32})
-        for (int traffic : {0, 1, 2})
-            for (int nA : {1, 12}) {
+        for (int traffic : {0, 5})
+            for (int nA : {12}) {
                 const int nacc = 2;
                 printf("%4d %5d %4d %-28s %4d %-8s %10.1f\n", N, nacc, nA, "same tile", 0, tn[traffic], run<0, 0>(N, nacc, nA, traffic, d_out));
                 printf("%4d %5d %4d %-28s %4d %-8s %10.1f\n", N, nacc, nA, "same tile", 1, tn[traffic], run<0, 1>(N, nacc, nA, traffic, d_out));
