@@ -46,6 +46,8 @@ PROTOTYPES = {
     "ocb_rollout_actions": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "ocb_rollout_random": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "ocb_step_host": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "ocb_step_host_async": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "ocb_step_host_wait": (_i, [_vp]),
     "ocb_get_state": (_i, [_vp, _vp, _sz]),
     "ocb_set_state": (_i, [_vp, _vp, _sz]),
     "ocb_read_episode_stats": (_i, [_vp, _vp, _vp, _vp]),

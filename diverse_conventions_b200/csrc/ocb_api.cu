@@ -51,11 +51,15 @@ struct ocb_env {
     int32_t* d_episodes;
     unsigned long long* d_step_counter;  // device mirror of step_count
     // scratch for the host-buffer entry points
-    int32_t* d_h_actions;
-    int8_t* d_h_obs;
-    int32_t* d_h_rew;
-    int32_t* d_h_done;
-    cudaStream_t own_stream;
+    // double-buffered device staging + streams of the host-buffer pipeline (ocb_step_host / ocb_step_host_async)
+    int32_t* d_h_actions[2];
+    int8_t* d_h_obs[2];
+    int32_t* d_h_rew[2];
+    int32_t* d_h_done[2];
+    cudaStream_t own_stream;   // H2D of the actions + the step kernel
+    cudaStream_t copy_stream;  // D2H of reward / done / observations
+    cudaEvent_t ev_kernel[2], ev_done[2], ev_order;
+    uint64_t host_issued, host_completed;
 };
 
 static int build_tables_or_fail(const ocb_config* cfg, Tables* tb, uint8_t* tmpl) {
@@ -122,11 +126,17 @@ extern "C" int ocb_destroy(ocb_env* e) {
     cudaFree(e->d_ret_sum);
     cudaFree(e->d_episodes);
     cudaFree(e->d_step_counter);
-    cudaFree(e->d_h_actions);
-    cudaFree(e->d_h_obs);
-    cudaFree(e->d_h_rew);
-    cudaFree(e->d_h_done);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(e->d_h_actions[b]);
+        cudaFree(e->d_h_obs[b]);
+        cudaFree(e->d_h_rew[b]);
+        cudaFree(e->d_h_done[b]);
+        if (e->ev_kernel[b]) cudaEventDestroy(e->ev_kernel[b]);
+        if (e->ev_done[b]) cudaEventDestroy(e->ev_done[b]);
+    }
+    if (e->ev_order) cudaEventDestroy(e->ev_order);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
     return OCB_OK;
 }
@@ -365,7 +375,15 @@ extern "C" int ocb_rollout_random(ocb_env* e, int K, int8_t* obs_slab, int32_t* 
     return run_rollout(e, K, nullptr, OCB_ACT_I32, obs_slab, reward, done, actions_out, false, stream);
 }
 
-extern "C" int ocb_step_host(ocb_env* e, const int32_t* h_actions, int8_t* h_obs, int32_t* h_reward, int32_t* h_done) {
+extern "C" int ocb_step_host_wait(ocb_env* e);
+
+// Host-buffer stepping as a two-deep pipeline on the env's own (non-blocking) streams: step t's observation copy
+// (13 MB at config 3, PCIe-bound) overlaps the H2D + kernel of step t + 1 when the caller already has the next actions.
+//   own_stream : [wait ev_done[slot]] H2D actions -> step kernel -> record ev_kernel[slot]
+//   copy_stream: wait ev_kernel[slot] -> D2H reward, done (small, first) -> D2H observations -> record ev_done[slot]
+// Ordering with work the caller issued earlier on blocking streams (torch's default stream) is kept through an event on
+// the legacy default stream, as the previous implementation on stream 0 did implicitly.
+extern "C" int ocb_step_host_async(ocb_env* e, const int32_t* h_actions, int8_t* h_obs, int32_t* h_reward, int32_t* h_done) {
     if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "env is NULL");
     if (h_actions == nullptr) return fail(OCB_ERR_INVALID_ARG, "actions is NULL");
     DeviceGuard guard(e->device);
@@ -378,22 +396,60 @@ extern "C" int ocb_step_host(ocb_env* e, const int32_t* h_actions, int8_t* h_obs
             return fail(OCB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(err__)); \
         }                                                                        \
     } while (0)
-    if (e->d_h_actions == nullptr) OCB_TRY(cudaMalloc(&e->d_h_actions, sizeof(int32_t) * P * N));
-    if (h_obs && e->d_h_obs == nullptr) OCB_TRY(cudaMalloc(&e->d_h_obs, P * N * (size_t)e->SC));
-    if (h_reward && e->d_h_rew == nullptr) OCB_TRY(cudaMalloc(&e->d_h_rew, sizeof(int32_t) * P * N));
-    if (h_done && e->d_h_done == nullptr) OCB_TRY(cudaMalloc(&e->d_h_done, sizeof(int32_t) * N));
-    cudaStream_t s = 0;  // legacy default stream: ordered after earlier calls on it
-    OCB_TRY(cudaMemcpyAsync(e->d_h_actions, h_actions, sizeof(int32_t) * P * N, cudaMemcpyHostToDevice, s));
-    int rc = ocb_step(e, e->d_h_actions, h_obs ? e->d_h_obs : nullptr, h_reward ? e->d_h_rew : nullptr,
-                      h_done ? e->d_h_done : nullptr, s);
+    if (e->own_stream == nullptr) OCB_TRY(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    if (e->copy_stream == nullptr) OCB_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    if (e->ev_order == nullptr) OCB_TRY(cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming));
+    if (e->host_issued - e->host_completed >= 2) {  // pipeline full: retire the oldest step first
+        const int rc = ocb_step_host_wait(e);
+        if (rc < 0) return rc;
+    }
+    const int b = (int)(e->host_issued & 1);
+    if (e->ev_kernel[b] == nullptr) OCB_TRY(cudaEventCreateWithFlags(&e->ev_kernel[b], cudaEventDisableTiming));
+    if (e->ev_done[b] == nullptr) OCB_TRY(cudaEventCreateWithFlags(&e->ev_done[b], cudaEventDisableTiming));
+    if (e->d_h_actions[b] == nullptr) OCB_TRY(cudaMalloc(&e->d_h_actions[b], sizeof(int32_t) * P * N));
+    if (h_obs && e->d_h_obs[b] == nullptr) OCB_TRY(cudaMalloc(&e->d_h_obs[b], P * N * (size_t)e->SC));
+    if (h_reward && e->d_h_rew[b] == nullptr) OCB_TRY(cudaMalloc(&e->d_h_rew[b], sizeof(int32_t) * P * N));
+    if (h_done && e->d_h_done[b] == nullptr) OCB_TRY(cudaMalloc(&e->d_h_done[b], sizeof(int32_t) * N));
+    cudaStream_t sc = e->own_stream, sd = e->copy_stream;
+    if (e->host_issued == e->host_completed) {  // pipeline empty: order after the caller's earlier (blocking-stream) work
+        OCB_TRY(cudaEventRecord(e->ev_order, 0));
+        OCB_TRY(cudaStreamWaitEvent(sc, e->ev_order, 0));
+    }
+    OCB_TRY(cudaStreamWaitEvent(sc, e->ev_done[b], 0));  // the staging buffers of this slot have been copied out
+    OCB_TRY(cudaMemcpyAsync(e->d_h_actions[b], h_actions, sizeof(int32_t) * P * N, cudaMemcpyHostToDevice, sc));
+    int rc = ocb_step(e, e->d_h_actions[b], h_obs ? e->d_h_obs[b] : nullptr, h_reward ? e->d_h_rew[b] : nullptr,
+                      h_done ? e->d_h_done[b] : nullptr, sc);
     if (rc != OCB_OK) return rc;
-    if (h_reward) OCB_TRY(cudaMemcpyAsync(h_reward, e->d_h_rew, sizeof(int32_t) * P * N, cudaMemcpyDeviceToHost, s));
-    if (h_done) OCB_TRY(cudaMemcpyAsync(h_done, e->d_h_done, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, s));
-    if (h_obs) OCB_TRY(cudaMemcpyAsync(h_obs, e->d_h_obs, P * N * (size_t)e->SC, cudaMemcpyDeviceToHost, s));
-    OCB_TRY(cudaStreamSynchronize(s));
-#undef OCB_TRY
+    OCB_TRY(cudaEventRecord(e->ev_kernel[b], sc));
+    OCB_TRY(cudaStreamWaitEvent(sd, e->ev_kernel[b], 0));
+    if (h_reward) OCB_TRY(cudaMemcpyAsync(h_reward, e->d_h_rew[b], sizeof(int32_t) * P * N, cudaMemcpyDeviceToHost, sd));
+    if (h_done) OCB_TRY(cudaMemcpyAsync(h_done, e->d_h_done[b], sizeof(int32_t) * N, cudaMemcpyDeviceToHost, sd));
+    if (h_obs) OCB_TRY(cudaMemcpyAsync(h_obs, e->d_h_obs[b], P * N * (size_t)e->SC, cudaMemcpyDeviceToHost, sd));
+    OCB_TRY(cudaEventRecord(e->ev_done[b], sd));
+    e->host_issued += 1;
     return OCB_OK;
 }
+
+// blocks until the OLDEST step enqueued by ocb_step_host_async has delivered its host buffers; returns the number of
+// steps still in flight (0 or 1), or a negative error code
+extern "C" int ocb_step_host_wait(ocb_env* e) {
+    if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "env is NULL");
+    if (e->host_issued == e->host_completed) return 0;
+    DeviceGuard guard(e->device);
+    OCB_TRY(cudaEventSynchronize(e->ev_done[e->host_completed & 1]));
+    e->host_completed += 1;
+    return (int)(e->host_issued - e->host_completed);
+}
+
+extern "C" int ocb_step_host(ocb_env* e, const int32_t* h_actions, int8_t* h_obs, int32_t* h_reward, int32_t* h_done) {
+    int rc = ocb_step_host_async(e, h_actions, h_obs, h_reward, h_done);
+    if (rc != OCB_OK) return rc;
+    do {
+        rc = ocb_step_host_wait(e);
+    } while (rc > 0);
+    return rc < 0 ? rc : OCB_OK;
+}
+#undef OCB_TRY
 
 // ------------------------------------------------------------------ state I/O
 extern "C" int ocb_get_state(ocb_env* e, int32_t* h_state, size_t n_ints) {

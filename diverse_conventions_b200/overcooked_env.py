@@ -197,6 +197,18 @@ class B200Overcooked(VectorMultiAgentEnv):
         assert h_actions.dtype == torch.int32 and h_actions.device.type == "cpu" and h_actions.is_contiguous()
         _native.check(self._lib.ocb_step_host(self._h, _ptr(h_actions), _ptr(h_obs), _ptr(h_rewards), _ptr(h_dones)))
 
+    def step_host_async(self, h_actions: torch.Tensor, h_obs=None, h_rewards=None, h_dones=None):
+        """ocb_step_host_async: enqueue one step of the two-deep host-buffer pipeline and return (pinned buffers)"""
+        assert h_actions.dtype == torch.int32 and h_actions.device.type == "cpu" and h_actions.is_contiguous()
+        _native.check(self._lib.ocb_step_host_async(self._h, _ptr(h_actions), _ptr(h_obs), _ptr(h_rewards), _ptr(h_dones)))
+
+    def step_host_wait(self) -> int:
+        """ocb_step_host_wait: block until the oldest enqueued step delivered its buffers -> steps still in flight"""
+        rc = self._lib.ocb_step_host_wait(self._h)
+        if rc < 0:
+            _native.check(rc)
+        return rc
+
     def get_state(self) -> np.ndarray:
         L = self._lib.ocb_state_ints_per_world(self._h)
         st = np.empty((self.num_envs, L), dtype=np.int32)

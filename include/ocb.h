@@ -152,6 +152,15 @@ int ocb_rollout_random(ocb_env* env, int K, int8_t* obs_slab, int32_t* reward, i
  * and synchronises.  Pointers are HOST pointers (pinned memory recommended);
  * h_obs / h_reward / h_done may be NULL. */
 int ocb_step_host(ocb_env* env, const int32_t* h_actions, int8_t* h_obs, int32_t* h_reward, int32_t* h_done);
+/* The same step as a two-deep pipeline on the env's own streams: the call enqueues H2D actions -> kernel -> D2H
+ * (reward and done first, then the observation planes) and returns; at most two steps are in flight (a third call first
+ * retires the oldest).  ocb_step_host_wait blocks until the OLDEST enqueued step has delivered its host buffers and
+ * returns how many steps remain in flight (0 / 1) or a negative error code.  With the next actions already at hand (a
+ * scripted / replayed / random partner, or a policy that acts one step late) the 13 MB observation copy of step t
+ * overlaps the upload and kernel of step t + 1.  Host buffers of a step must stay untouched until its wait returns;
+ * retire every step before calling any other entry point on the handle. */
+int ocb_step_host_async(ocb_env* env, const int32_t* h_actions, int8_t* h_obs, int32_t* h_reward, int32_t* h_done);
+int ocb_step_host_wait(ocb_env* env);
 
 /* ------------------------------------------------------- Overcooked: state I/O */
 /* Packed world state, int32 [N, L], L = ocb_state_ints_per_world():

@@ -252,6 +252,45 @@ def test_step_host_matches_device_path():
         assert torch.equal(rew.cpu(), h_rew) and torch.equal(done.cpu(), h_done)
 
 
+def test_step_host_async_pipeline_matches_oracle():
+    """two steps in flight (ocb_step_host_async / ocb_step_host_wait): every retired step's host buffers equal the oracle's
+    step, in order, including across an episode end; mixing with the synchronous call afterwards keeps the order"""
+    N, horizon, T = 333, 9, 25
+    lp = layouts.load_layout("random1", horizon)
+    env = make_env("random1", N, horizon)
+    orc = COracle(lp, N)
+    rng = np.random.default_rng(3)
+    acts = rng.integers(0, 6, size=(T, 2, N)).astype(np.int32)
+    bufs = [dict(a=torch.empty((2, N), dtype=torch.int32).pin_memory(),
+                 o=torch.empty((2, N, lp.width, lp.height, lp.channels), dtype=torch.int8).pin_memory(),
+                 r=torch.empty((2, N), dtype=torch.int32).pin_memory(), d=torch.empty((N,), dtype=torch.int32).pin_memory())
+            for _ in range(2)]
+    retired = 0
+
+    def retire():
+        nonlocal retired
+        left = env.step_host_wait()
+        b = bufs[retired & 1]
+        o, r, d = orc.step(acts[retired])
+        assert np.array_equal(b["o"].numpy(), o) and np.array_equal(b["r"].numpy(), r) and np.array_equal(b["d"].numpy(), d)
+        retired += 1
+        return left
+
+    for t in range(T):
+        if t >= 2:
+            retire()  # the slot about to be reused
+        b = bufs[t & 1]
+        b["a"].copy_(torch.from_numpy(acts[t]))
+        env.step_host_async(b["a"], b["o"], b["r"], b["d"])
+    assert retire() == 1 and retire() == 0 and env.step_host_wait() == 0
+    assert retired == T and env.step_count == T
+    a = rng.integers(0, 6, size=(2, N)).astype(np.int32)
+    bufs[0]["a"].copy_(torch.from_numpy(a))
+    env.step_host(bufs[0]["a"], bufs[0]["o"], bufs[0]["r"], bufs[0]["d"])
+    o, r, d = orc.step(a)
+    assert np.array_equal(bufs[0]["o"].numpy(), o) and np.array_equal(env.get_state(), orc.state)
+
+
 def test_error_codes_through_the_abi():
     L = _native.lib()
     h = ctypes.c_void_p()

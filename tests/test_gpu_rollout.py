@@ -99,6 +99,33 @@ def test_selfplay_rollout_matches_oracle_and_torch(layout, N, T, fused):
     assert ro.rollouts == 2 and env.step_count == 2 * T
 
 
+@pytest.mark.parametrize("layout,N,T", [("simple", 8192, 100), ("simple", 9472 + 37, 40), ("random1", 8192, 60)])
+def test_fused_rollout_at_the_benchmarked_shape_replays_through_the_oracle(layout, N, T):
+    """BASELINE config 4's shape (8,192 worlds = 128 CTAs; 9,509 worlds = 148 CTAs + a second, ragged tile on one of them):
+    every observation, reward and done the fused kernel wrote is what the oracle produces for the sampled actions, and a
+    strided subset of rows agrees with the fp32 torch forward"""
+    horizon = 23
+    lp = layouts.load_layout(layout, horizon)
+    pol, actors, critics = make_policies(lp, 1)
+    env = B200Overcooked(layout, N, 0, horizon=horizon, seed=11)
+    ro = PolicyRollout(env, pol, T, seed=5, fused=True)
+    buf = ro.collect()
+    torch.cuda.synchronize()
+    obs, rew, done, orc = replay_through_oracle(lp, N, buf)
+    assert np.array_equal(buf.rewards.cpu().numpy(), rew) and np.array_equal(buf.dones.cpu().numpy(), done)
+    got = buf.obs.cpu().numpy()
+    assert np.array_equal(got, obs)
+    assert np.array_equal(env.get_state(), orc.state)
+    assert done.sum() == N * (T // horizon) and rew.sum() > 0
+    rows = torch.from_numpy(got).reshape(T + 1, 2 * N, lp.width, lp.height, lp.channels)
+    sub = slice(0, 2 * N, 61)
+    for t in (0, T // 2, T - 1):
+        ref_lp = log_softmax_sample(actors[0].forward(rows[t, sub]), buf.actions[t].cpu().reshape(-1)[sub])
+        assert torch.allclose(buf.action_log_probs[t].cpu().reshape(-1)[sub], ref_lp, atol=ATOL_LOGP), t
+    ref_v = critics[0].forward(rows[T, sub])[:, 0]
+    assert float((buf.value_preds[T].cpu().reshape(-1)[sub] - ref_v).abs().max() / ref_v.abs().max()) < REL_TOL
+
+
 def test_shared_buffer_views_follow_the_reference_axis_order():
     lp = layouts.load_layout("simple", 400)
     pol, _, _ = make_policies(lp, 1)
