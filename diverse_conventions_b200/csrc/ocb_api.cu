@@ -86,9 +86,9 @@ static int pick_launch_shape(const ocb_env* e, int G, int* warps, size_t* smem) 
     int wmax = 4;
     if (const char* ev = getenv("OCB_WARPS_PER_CTA")) {  // tuning experiments only
         const int v = atoi(ev);
-        if (v == 1 || v == 2 || v == 4) wmax = v;
+        if (v >= 1 && v <= 4) wmax = v;
     }
-    for (int w = wmax; w >= 1; w >>= 1) {
+    for (int w = wmax; w >= 1; --w) {
         const size_t b = rollout_smem_bytes(e->P, e->S, e->C, G, w);
         if (b <= 200 * 1024) {
             *warps = w, *smem = b;
@@ -553,7 +553,7 @@ extern "C" int ocb_rollout_policy(ocb_env* e, ocb_policy* pol, int T, const int3
     if (e == nullptr || pol == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL handle");
     if (obs_slab == nullptr || actions == nullptr) return fail(OCB_ERR_INVALID_ARG, "obs_slab and actions are required");
     if (T < 1) return fail(OCB_ERR_INVALID_ARG, "T must be >= 1");
-    if (e->P != 2) return fail(OCB_ERR_UNSUPPORTED, "the policy rollout supports 2 players");
+    if (ocb_policy_obs_bytes(pol) != e->SC) return fail(OCB_ERR_INVALID_ARG, "env and policy were built for different layouts");
     const size_t PN = (size_t)e->P * e->N, obs_step = PN * (size_t)e->SC;
     const int M = (int)PN;
     const uint64_t* ctr = reinterpret_cast<const uint64_t*>(e->d_step_counter);

@@ -14,6 +14,10 @@ int ocb_policy_rollout_fused_launch(ocb_policy* pol, int policy_index, const ocb
                                     uint64_t* d_counter, void* stream, long long* d_trace = nullptr, int trace_u0 = 0,
                                     int trace_n = 0);
 
+// bytes of one observation row the handle was built for (W * H * (5 P + 10)); 1 when shapes outside the tensor-core
+// kernels' range run through policy_generic_kernel
+int ocb_policy_obs_bytes(const ocb_policy* pol);
+int ocb_policy_is_generic(const ocb_policy* pol);
 // number of (actor, critic) weight sets the handle holds
 int ocb_policy_num_sets(const ocb_policy* pol);
 // R_Critic value of the all-zero observation under weight set `policy` (computed on the host at set_weights)

@@ -1268,6 +1268,7 @@ __global__ void __launch_bounds__(kPThreads, 1) policy_pair_kernel(const PolicyP
 
 #include "policy512.cuh"
 #include "rollout_fused.cuh"
+#include "policy_generic.cuh"
 
 // ---------------------------------------------------------------- host-side packing
 uint16_t bf16_bits(float x) {
@@ -1314,6 +1315,10 @@ struct ocb_policy {
     // bootstraps from the never-written slot L, which holds zeros in the reference)
     std::vector<float> zero_value;
     uint32_t rng_rows_per_seat = 0, rng_add0 = 0, rng_add1 = 0;  // ocb_policy_set_sampling_rows
+    // generic mode (policy_generic.cuh): shapes outside the tensor-core kernels' range (P != 2, H > 6, one conv position)
+    int generic = 0;
+    GBlob LG;
+    float* d_gblobs = nullptr;
 };
 
 extern "C" int ocb_policy_destroy(ocb_policy* p) {
@@ -1322,11 +1327,14 @@ extern "C" int ocb_policy_destroy(ocb_policy* p) {
     CaptureRelaxed relaxed;  // safe while another stream is being captured
     cudaFree(p->d_scratch);
     cudaFree(p->d_blobs);
+    cudaFree(p->d_gblobs);
     delete p;
     return OCB_OK;
 }
 
 int ocb_policy_num_sets(const ocb_policy* p) { return p ? p->n_policies : 0; }
+int ocb_policy_obs_bytes(const ocb_policy* p) { return p ? p->SC : 0; }
+int ocb_policy_is_generic(const ocb_policy* p) { return p ? p->generic : 0; }
 float ocb_policy_zero_obs_value(const ocb_policy* p, int policy) {
     return (p && policy >= 0 && policy < (int)p->zero_value.size()) ? p->zero_value[policy] : 0.0f;
 }
@@ -1358,26 +1366,36 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
     if (cfg->struct_size != sizeof(ocb_config)) return fail(OCB_ERR_INVALID_ARG, "ocb_config ABI mismatch");
     if (hidden != kHid && hidden != kH5)
         return fail(OCB_ERR_UNSUPPORTED, "the policy kernels support hidden_size 64 and 512 (got %d)", hidden);
-    if (cfg->num_players != 2) return fail(OCB_ERR_UNSUPPORTED, "the fused policy kernel supports 2 players only");
+    if (cfg->num_players < 1 || cfg->num_players > OCB_MAX_PLAYERS) return fail(OCB_ERR_BAD_LAYOUT, "1..%d players", OCB_MAX_PLAYERS);
     if (cfg->width < 3 || cfg->height < 3) return fail(OCB_ERR_BAD_LAYOUT, "grid smaller than the 3x3 convolution");
-    if ((cfg->width - 2) * (cfg->height - 2) < 2) return fail(OCB_ERR_UNSUPPORTED, "the fused policy kernel needs at least two conv positions");
     if (cfg->width * cfg->height > OCB_MAX_CELLS) return fail(OCB_ERR_BAD_LAYOUT, "grid larger than OCB_MAX_CELLS");
-    if (cfg->height > kMaxH)
-        return fail(OCB_ERR_UNSUPPORTED, "the fused policy kernel supports grids up to %d rows high (got %d)", kMaxH, cfg->height);
     if (n_policies < 1 || n_policies > 4096) return fail(OCB_ERR_INVALID_ARG, "n_policies out of range");
+    // Shapes the tensor-core kernels do not take (they pack 2-player observations and need a grid column per warp-wide
+    // load) run the same networks through policy_generic_kernel (fp32 CUDA cores): schelling, corridor,
+    // multiplayer_schelling, simple_single ...  OCB_POLICY_GENERIC=1 forces that path (tests compare the two).
+    bool generic = cfg->num_players != 2 || cfg->height > kMaxH || (cfg->width - 2) * (cfg->height - 2) < 2;
+    if (const char* e = getenv("OCB_POLICY_GENERIC")) generic = generic || e[0] == '1';
     const int ndev = ocb_device_count();
     if (ndev <= 0) return fail(OCB_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
     if (device < 0 || device >= ndev) return fail(OCB_ERR_INVALID_ARG, "device %d not in 0..%d", device, ndev - 1);
     ocb_policy* p = new (std::nothrow) ocb_policy();
     if (p == nullptr) return fail(OCB_ERR_INVALID_ARG, "out of host memory");
-    p->device = device, p->W = cfg->width, p->H = cfg->height, p->S = p->W * p->H, p->C = 20, p->SC = p->S * 20;
+    p->device = device, p->W = cfg->width, p->H = cfg->height, p->S = p->W * p->H, p->C = 5 * cfg->num_players + 10;
+    p->SC = p->S * p->C;
+    p->generic = generic ? 1 : 0;
     p->npos = (p->W - 2) * (p->H - 2), p->n_policies = n_policies, p->calls = 0, p->d_blobs = nullptr;
     p->hidden = hidden, p->d_scratch = nullptr, p->scratch_tiles = 0, p->L5 = blob5_layout(p->npos);
     p->ring = 0, p->smem_bytes = 0, p->pair_ring = 0, p->pair_smem_bytes = 0, p->use_pair = 0;
     p->terrain.assign(cfg->terrain, cfg->terrain + p->S);
     p->L = blob_layout(p->npos);
     p->stage_stride = (5 * p->H) | 1;
-    if (hidden == kHid) {
+    if (generic) {
+        p->LG = gblob_layout(p->C, hidden, p->npos);
+        if (generic_smem_bytes(p->SC, hidden) > (size_t)kSmemBudget) {
+            delete p;
+            return fail(OCB_ERR_UNSUPPORTED, "layout too large for the generic policy kernel (%d x %d)", cfg->width, cfg->height);
+        }
+    } else if (hidden == kHid) {
     // weight ring: as many 8 KB chunks as fit; all of them (resident weights) when possible
     const int fixed = smem_layout(p->H, p->npos, 0, p->stage_stride).total;
     int ring = (kSmemBudget - fixed) / kChunk;
@@ -1405,10 +1423,17 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
         return fail(OCB_ERR_UNSUPPORTED, "layout too large for the hidden-512 conv kernel (%d x %d)", cfg->width, cfg->height);
     }
     DeviceGuard guard(device);
-    const size_t bytes = (size_t)n_policies * 2 * (hidden == kHid ? (size_t)p->L.total : p->L5.total);
+    const size_t bytes = generic ? 256 : (size_t)n_policies * 2 * (hidden == kHid ? (size_t)p->L.total : p->L5.total);
     cudaError_t err = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (err == cudaSuccess) err = cudaMalloc(&p->d_blobs, bytes);
     if (err == cudaSuccess) err = cudaMemset(p->d_blobs, 0, bytes);
+    if (generic) {
+        const size_t gbytes = (size_t)n_policies * 2 * p->LG.total * sizeof(float);
+        if (err == cudaSuccess) err = cudaMalloc(&p->d_gblobs, gbytes);
+        if (err == cudaSuccess) err = cudaMemset(p->d_gblobs, 0, gbytes);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_generic_kernel<kHid>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 128);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_generic_kernel<kH5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 128);
+    }
     // the opt-in limit is per function, not per handle: always raise it to the full budget
     const int smem_max = kSmemBudget + 128;
     if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
@@ -1537,7 +1562,7 @@ static int policy_launch512(ocb_policy* p, PolicyParams& prm, cudaStream_t strea
 // pre-size internal scratch for forwards of up to M rows (no-op for hidden 64, which has none)
 extern "C" int ocb_policy_reserve(ocb_policy* p, int M) {
     if (p == nullptr || M < 1) return fail(OCB_ERR_INVALID_ARG, "bad handle / M");
-    if (p->hidden != kH5) return OCB_OK;
+    if (p->hidden != kH5 || p->generic) return OCB_OK;
     DeviceGuard guard(p->device);
     return reserve512(p, (size_t)((M + kRows - 1) / kRows), nullptr);
 }
@@ -1554,6 +1579,37 @@ extern "C" int ocb_policy_set_weights(ocb_policy* p, int policy, int net, const 
     if (net == 1) {
         p->zero_value.resize((size_t)p->n_policies, 0.0f);
         p->zero_value[policy] = zero_obs_value(p->hidden, p->npos, conv_b, fc1_w, fc1_b, fc2_w, fc2_b, head_w, head_b);
+    }
+    if (p->generic) {  // fp32, transposed so that consecutive output units are consecutive words (policy_generic.cuh)
+        const GBlob& G = p->LG;
+        const int C = p->C, h = p->hidden, CO = h / 2, np = p->npos, head_out = net == 0 ? 6 : 1;
+        std::vector<float> blob(G.total, 0.0f);
+        for (int co = 0; co < CO; ++co) {
+            blob[G.conv_b + co] = conv_b[co];
+            for (int c = 0; c < C; ++c)
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j)
+                        blob[G.conv_w + (size_t)((i * 3 + j) * C + c) * CO + co] = conv_w[((size_t)(co * C + c) * 3 + i) * 3 + j];
+        }
+        for (int n = 0; n < h; ++n) {
+            blob[G.b1 + n] = fc1_b[n], blob[G.b2 + n] = fc2_b[n];
+            for (int pos = 0; pos < np; ++pos)
+                for (int co = 0; co < CO; ++co)
+                    blob[G.w1 + ((size_t)pos * CO + co) * h + n] = fc1_w[(size_t)n * (CO * np) + (size_t)co * np + pos];
+            for (int k = 0; k < h; ++k) blob[G.w2 + (size_t)k * h + n] = fc2_w[(size_t)n * h + k];
+        }
+        for (int a = 0; a < head_out; ++a) {
+            blob[G.bh + a] = head_b[a];
+            for (int k = 0; k < h; ++k) blob[G.wh + (size_t)a * h + k] = head_w[(size_t)a * h + k];
+        }
+        DeviceGuard guard(p->device);
+        cudaError_t err = cudaMemcpy(p->d_gblobs + ((size_t)policy * 2 + net) * G.total, blob.data(), G.total * sizeof(float),
+                                     cudaMemcpyHostToDevice);
+        if (err != cudaSuccess) {
+            cudaGetLastError();
+            return fail(OCB_ERR_CUDA, "ocb_policy_set_weights: %s", cudaGetErrorString(err));
+        }
+        return OCB_OK;
     }
     if (p->hidden == kH5) return set_weights512(p, policy, net, conv_w, conv_b, fc1_w, fc1_b, fc2_w, fc2_b, head_w, head_b);
     const BlobLayout& L = p->L;
@@ -1629,7 +1685,7 @@ static int policy_launch(ocb_policy* p, int net_mask, const int8_t* obs, int M, 
                          const EvalArgs* ev = nullptr) {
     if (p == nullptr || obs == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL argument");
     if (M < 1) return fail(OCB_ERR_INVALID_ARG, "M must be >= 1");
-    if ((reinterpret_cast<uintptr_t>(obs) & 3u) != 0) return fail(OCB_ERR_INVALID_ARG, "obs must be 4-byte aligned");
+    if (!p->generic && (reinterpret_cast<uintptr_t>(obs) & 3u) != 0) return fail(OCB_ERR_INVALID_ARG, "obs must be 4-byte aligned");
     DeviceGuard guard(p->device);
     PolicyParams prm;
     memset(&prm, 0, sizeof(prm));
@@ -1644,6 +1700,22 @@ static int policy_launch(ocb_policy* p, int net_mask, const int8_t* obs, int M, 
     prm.pair_ring = p->pair_ring;
     prm.prof = prof;
     if (ev != nullptr) prm.row_index = ev->row_index, prm.given_actions = ev->given_actions, prm.entropy = ev->entropy;
+    if (p->generic) {
+        if (prof != nullptr) return fail(OCB_ERR_UNSUPPORTED, "the role profile exists for the tensor-core kernels only");
+        GParams gp;
+        gp.base = prm, gp.blobs = p->d_gblobs, gp.C = p->C, gp.hidden = p->hidden;
+        const int ctas = (M + kGRows - 1) / kGRows;
+        const size_t smem = generic_smem_bytes(p->SC, p->hidden);
+        if (ctas_out) *ctas_out = ctas;
+        if (p->hidden == kHid)
+            policy_generic_kernel<kHid><<<ctas, kGenThreads, smem, (cudaStream_t)stream>>>(gp);
+        else
+            policy_generic_kernel<kH5><<<ctas, kGenThreads, smem, (cudaStream_t)stream>>>(gp);
+        cudaError_t gerr = cudaGetLastError();
+        if (gerr != cudaSuccess) return fail(OCB_ERR_CUDA, "generic policy kernel launch failed: %s", cudaGetErrorString(gerr));
+        p->calls += 1;
+        return OCB_OK;
+    }
     if (p->hidden == kH5) {
         if (prof != nullptr) return fail(OCB_ERR_UNSUPPORTED, "the role profile exists for hidden 64 only");
         if (ctas_out) *ctas_out = 0;
@@ -1759,6 +1831,7 @@ int ocb_policy_rollout_fused_launch(ocb_policy* p, int policy_index, const Rollo
                                     int32_t* done, int deterministic, uint64_t seed, const uint64_t* d_offset,
                                     uint64_t* d_counter, void* stream, long long* d_trace, int trace_u0, int trace_n) {
     if (p == nullptr) return fail(OCB_ERR_INVALID_ARG, "policy is NULL");
+    if (p->generic) return fail(OCB_ERR_UNSUPPORTED, "the fused rollout kernel needs the tensor-core policy path (2 players, grids up to %d rows)", kMaxH);
     if (p->hidden != kHid) return fail(OCB_ERR_UNSUPPORTED, "the fused rollout kernel exists for hidden_size 64 only");
     if (policy_index < 0 || policy_index >= p->n_policies) return fail(OCB_ERR_INVALID_ARG, "policy index out of range");
     if (env_w != p->W || env_h != p->H) return fail(OCB_ERR_INVALID_ARG, "env and policy were built for different layouts");

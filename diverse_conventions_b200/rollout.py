@@ -139,8 +139,8 @@ class PolicyRollout:
         ``fused``: run the rollout as ONE persistent launch (``ocb_rollout_policy_fused``: self-play of weight
         set ``policy_index``, hidden 64, critic on); ``None`` = use it whenever it applies, ``False`` = always the
         2T+1-launch path.  Both paths fill bit-identical buffers."""
-        if env.num_players != 2:
-            raise ValueError("the policy rollout supports 2 players")
+        if env.num_players != policy.layout.num_players:
+            raise ValueError("env and policy were built for different player counts")
         if env.sim_device != policy.device:
             raise ValueError("env and policy live on different devices")
         if (policy.layout.width, policy.layout.height) != (env.width, env.height):
@@ -155,7 +155,9 @@ class PolicyRollout:
         self.buf = RolloutBuffer(env, T, with_critic, with_logp)
         self._lib = _native.lib()
         self.policy_index = policy_index
-        can_fuse = tile_policy is None and with_critic and policy.hidden == 64
+        # one persistent launch needs the tensor-core policy path: 2 players, grids up to 6 rows (else per-step launches,
+        # which run any shape — the generic policy kernel covers schelling / corridor / multiplayer_schelling ...)
+        can_fuse = tile_policy is None and with_critic and policy.hidden == 64 and env.num_players == 2
         if fused and not can_fuse:
             raise ValueError("the fused rollout needs self-play of one policy (no tile_policy), hidden 64 and the critic")
         self.fused = can_fuse if fused is None else bool(fused)

@@ -11,6 +11,7 @@ import pytest
 import torch
 
 from diverse_conventions_b200 import layouts
+from diverse_conventions_b200.overcooked_env import B200Overcooked
 from diverse_conventions_b200.policy import FusedPolicy, PolicyNet, log_softmax_sample
 from oracle.c_oracle import COracle
 
@@ -110,10 +111,57 @@ def test_unsupported_shapes_fail_loudly():
     from diverse_conventions_b200 import _native
     with pytest.raises(_native.NativeError):
         FusedPolicy(layouts.load_layout("simple", 400), hidden=128)
-    with pytest.raises(_native.NativeError):
-        FusedPolicy(layouts.load_layout("multiplayer_schelling", 400), hidden=64)  # 4 players
-    with pytest.raises(_native.NativeError):
-        FusedPolicy(layouts.load_layout("corridor", 400), hidden=64)  # 9 rows high
+
+
+@pytest.mark.parametrize("hidden", [64, 512])
+@pytest.mark.parametrize("layout,N", [("schelling", 75), ("multiplayer_schelling", 41), ("corridor", 30), ("simple_single", 130)])
+def test_shapes_outside_the_tensor_core_range_run_the_generic_kernel(layout, N, hidden):
+    """7- and 9-row grids, 4 players (30 channels, rows of 1,470 bytes) and 1 player: the reference's CNNBase takes any
+    shape (train/MAPPO/utils/cnn.py:22-42); here they run policy_generic_kernel behind the same entry points"""
+    lp = layouts.load_layout(layout, 400)
+    actor = PolicyNet("actor", lp.width, lp.height, lp.channels, hidden).init_like_reference(3, gain=1.5)
+    critic = PolicyNet("critic", lp.width, lp.height, lp.channels, hidden).init_like_reference(4)
+    for net in (actor, critic):
+        for b in (net.conv_b, net.fc1_b, net.fc2_b, net.head_b):
+            b.uniform_(-0.1, 0.1)
+    pol = FusedPolicy(lp, hidden, 2)
+    pol.set_weights(1, actor, critic)
+    from oracle.c_oracle import COracle
+    orc = COracle(lp, N)
+    rng = np.random.default_rng(1)
+    for _ in range(40):
+        o, _, _ = orc.step(rng.integers(0, 6, size=(lp.num_players, N)))
+    obs = torch.from_numpy(o.reshape(-1, lp.width, lp.height, lp.channels).copy()).cuda()
+    M = obs.shape[0]
+    tiles = torch.ones(((M + 127) // 128,), dtype=torch.int32, device="cuda")
+    out = pol.forward(obs, tile_policy=tiles, deterministic=True, want_logits=True)
+    torch.cuda.synchronize()
+    ref_l, ref_v = actor.forward(obs.cpu()), critic.forward(obs.cpu())[:, 0]
+    assert torch.allclose(out["logits"].cpu(), ref_l, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(out["values"].cpu(), ref_v, rtol=1e-4, atol=1e-5)
+    assert torch.equal(out["actions"].cpu().long(), out["logits"].cpu().argmax(-1))
+    a = pol.act(obs, tile_policy=tiles, seed=3, offset=9, want_logits=True)
+    assert torch.allclose(a["logp"].cpu(), log_softmax_sample(a["logits"].cpu(), a["actions"].cpu()), atol=1e-6)
+    assert torch.equal(pol.value(obs, tile_policy=tiles), out["values"])
+
+
+def test_generic_kernel_agrees_with_the_tensor_core_kernels(monkeypatch):
+    """the same handle shape through both paths (OCB_POLICY_GENERIC=1 forces the generic kernel): same sampled actions,
+    logits within the tensor-core path's tolerance"""
+    lp = layouts.load_layout("random1", 400)
+    actor = PolicyNet("actor", lp.width, lp.height, lp.channels, 64).init_like_reference(8, gain=2.0)
+    critic = PolicyNet("critic", lp.width, lp.height, lp.channels, 64).init_like_reference(9)
+    env = B200Overcooked("random1", 300, 0, horizon=400, seed=2)
+    obs = env.rollout_random(25)["obs"][-1].contiguous()
+    tc = FusedPolicy(lp, 64, 1)
+    tc.set_weights(0, actor, critic)
+    monkeypatch.setenv("OCB_POLICY_GENERIC", "1")
+    gen = FusedPolicy(lp, 64, 1)
+    gen.set_weights(0, actor, critic)
+    a = tc.forward(obs, seed=5, offset=2, want_logits=True)
+    b = gen.forward(obs, seed=5, offset=2, want_logits=True)
+    assert torch.allclose(a["logits"], b["logits"], rtol=2e-4, atol=2e-5) and torch.allclose(a["values"], b["values"], rtol=2e-4, atol=2e-5)
+    assert float((a["actions"] == b["actions"]).float().mean()) > 0.999  # same counters; ties in the inverse CDF aside
 
 
 @pytest.mark.parametrize("layout", ["simple", "random0", "random3", "unident_s", "scenario3"])

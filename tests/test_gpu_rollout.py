@@ -126,6 +126,37 @@ def test_fused_rollout_at_the_benchmarked_shape_replays_through_the_oracle(layou
     assert float((buf.value_preds[T].cpu().reshape(-1)[sub] - ref_v).abs().max() / ref_v.abs().max()) < REL_TOL
 
 
+@pytest.mark.parametrize("layout,N,T", [("multiplayer_schelling", 96, 30), ("corridor", 70, 24), ("schelling", 128, 20)])
+def test_rollout_on_layouts_outside_the_tensor_core_range(layout, N, T):
+    """4 players / 7- and 9-row grids: the per-step rollout (generic policy kernel + the P <= 4 env kernels) writes the
+    trajectory the oracle reproduces from the sampled actions, with log-probs / values of the fp32 torch networks"""
+    horizon = 11
+    lp = layouts.load_layout(layout, horizon)
+    P = lp.num_players
+    actor = PolicyNet("actor", lp.width, lp.height, lp.channels, 64).init_like_reference(21, gain=2.0)
+    critic = PolicyNet("critic", lp.width, lp.height, lp.channels, 64).init_like_reference(22)
+    pol = FusedPolicy(lp, 64, 1)
+    pol.set_weights(0, actor, critic)
+    env = B200Overcooked(layout, N, 0, horizon=horizon, seed=3)
+    ro = PolicyRollout(env, pol, T, seed=17)
+    assert not ro.fused or P == 2  # the persistent kernel declines; collect() falls back to per-step launches
+    buf = ro.collect()
+    torch.cuda.synchronize()
+    assert not ro.fused
+    obs, rew, done, orc = replay_through_oracle(lp, N, buf)
+    assert np.array_equal(buf.obs.cpu().numpy(), obs)
+    assert np.array_equal(buf.rewards.cpu().numpy(), rew) and np.array_equal(buf.dones.cpu().numpy(), done)
+    assert np.array_equal(env.get_state(), orc.state) and done.sum() == N * (T // horizon)
+    rows = buf.obs.cpu().reshape(T + 1, P * N, lp.width, lp.height, lp.channels)
+    for t in (0, T // 2, T - 1):
+        ref_lp = log_softmax_sample(actor.forward(rows[t]), buf.actions[t].cpu().reshape(-1))
+        assert torch.allclose(buf.action_log_probs[t].cpu().reshape(-1), ref_lp, atol=ATOL_LOGP), t
+    ref_v = critic.forward(rows[T])[:, 0]
+    assert float((buf.value_preds[T].cpu().reshape(-1) - ref_v).abs().max() / ref_v.abs().max()) < REL_TOL
+    v = buf.shared_buffer_views()
+    assert v["obs"].shape == (T + 1, N, P, lp.width, lp.height, lp.channels) and v["masks"].shape == (T + 1, N, P, 1)
+
+
 def test_shared_buffer_views_follow_the_reference_axis_order():
     lp = layouts.load_layout("simple", 400)
     pol, _, _ = make_policies(lp, 1)
