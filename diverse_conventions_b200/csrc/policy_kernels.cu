@@ -962,12 +962,19 @@ __device__ __forceinline__ void pair_conv_role(long long* pw, const PolicyParams
     const uint32_t idesc = make_idesc(kRows, kN);  // N = 64: actor channels 0-31 | critic channels 32-63
     const uint32_t a_wchi = a_head + (kNet == 1 ? kPConvBytes : 0), a_wclo = a_wchi + 2 * kPConvBytes;
     const int b_full = kNet < 0 ? PB_D1_FULL : PBS_D1_FULL + 2 * kNet, b_empty = kNet < 0 ? PB_D1_EMPTY : PBS_D1_EMPTY + 2 * kNet;
-    uint32_t gcb = 0;            // running column index of grid column 0 of the tile
     uint32_t head_gen = 0, u = 0;
     uint32_t uses[2] = {0, 0};   // conv positions THIS issuer put into each accumulator stage so far
     const bool tracer = kNet <= 0;
+    // Ring bookkeeping without divisions (ring is a runtime value in the fused kernel; a `% ring` costs ~40 uniform-datapath
+    // instructions in front of every issue block): (slot, round) of grid column 0 of the tile, of the next column to wait
+    // for and of the next column to release advance by one column at a time.
+    uint32_t t_slot = 0, t_round = 0;  // grid column 0 of the current tile
+    auto advance = [&](uint32_t& slot, uint32_t& round, int n) {
+        for (int i = 0; i < n; ++i)
+            if (++slot == ring) slot = 0, ++round;
+    };
 
-    for (int t = t0; t < t1; ++t, ++u, gcb += W) {
+    for (int t = t0; t < t1; ++t, ++u) {
         if (blob_changed(prm, t, t0)) {
             mbar_wait_p<kProf>(bars + 8 * PB_HEAD_FULL, head_gen & 1, pw[PW_HEAD_FULL]);
             ++head_gen;
@@ -980,12 +987,16 @@ __device__ __forceinline__ void pair_conv_role(long long* pw, const PolicyParams
             const uint32_t cum = (u + 1) * (uint32_t)((npos + 1 - s_last) / 2);
             mbar_wait_p<kProf>(bars + 8 * (PBS_D1_FULL + s_last), (cum - 1) & 1, pw[PW_D3_FULL]);
         }
-        int cols_seen = 0, released = 0;  // grid columns of this tile waited for / released by this issuer
+        uint32_t w_slot = t_slot, w_round = t_round;  // next column to wait for
+        uint32_t r_slot = t_slot;                     // next column to release
+        uint32_t c_slot = t_slot;                     // slot of grid column ox (the window's first column)
+        int cols_seen = 0, released = 0, ox = 0, oy = cp0;
+        while (oy >= PH) oy -= PH, ++ox, c_slot = (c_slot + 1 == ring) ? 0 : c_slot + 1;
         for (int cp = cp0; cp < npos; cp += cpstep) {
-            const int ox = cp / PH, oy = cp - ox * PH, st = cp & 1;
+            const int st = cp & 1;
             for (; cols_seen < ox + 3; ++cols_seen) {  // new window column(s)
-                const uint32_t g = gcb + cols_seen;
-                mbar_wait_p<kProf>(bars + 8 * (col_full + g % ring), (g / ring) & 1, pw[PW_COL_FULL]);
+                mbar_wait_p<kProf>(bars + 8 * (col_full + w_slot), w_round & 1, pw[PW_COL_FULL]);
+                if (++w_slot == ring) w_slot = 0, ++w_round;
             }
             // the stage's previous conv position has been loaded by its reader(s): with cpstep = 2 the stage belongs to this
             // issuer alone; with cpstep = 1 the issuer alternates stages and counts per stage
@@ -994,29 +1005,42 @@ __device__ __forceinline__ void pair_conv_role(long long* pw, const PolicyParams
             if (u > 0 && cp < 2) mbar_wait_p<kProf>(bars + 8 * (PB_D3_EMPTY + (kNet < 0 ? cp : kNet)), (u - 1) & 1, pw[PW_D3_FULL]);
             tc_fence_after();
             const uint32_t d1 = tmem + kPColD1 + (kNet < 0 ? st * kHid : kNet * kHid + st * kCo);
-            const int nxt = cp + cpstep;
-            const int keep = nxt < npos ? nxt / PH : W;  // first grid column a later position of this issuer still reads
+            // position of the next conv of this issuer -> first grid column it still reads
+            int nox = ox, noy = oy + cpstep;
+            uint32_t n_slot = c_slot;
+            while (noy >= PH) noy -= PH, ++nox, n_slot = (n_slot + 1 == ring) ? 0 : n_slot + 1;
+            const int keep = cp + cpstep < npos ? nox : W;
+            const uint32_t s1 = (c_slot + 1 >= ring) ? c_slot + 1 - ring : c_slot + 1;
+            const uint32_t s2 = (c_slot + 2 >= ring) ? c_slot + 2 - ring : c_slot + 2;
+            const uint32_t cellb = tmem + kColCells + (uint32_t)oy * kCellCols, colw = (uint32_t)H * kCellCols;
+            const uint32_t cb0 = cellb + c_slot * colw, cb1 = cellb + s1 * colw, cb2 = cellb + s2 * colw;
             const long long ti0 = kProf ? clock64() : 0;
             if (cp == 3 && tracer) trace_ev<kProf>(prm, t - t0, 54);  // waits of conv 3 done, issue starts
             if (elect_one()) {
 #pragma unroll
                 for (int j = 0; j < 9; ++j) {
                     const int dx = j / 3, dy = j - dx * 3;
-                    const uint32_t ta = tmem + kColCells + (((gcb + ox + dx) % ring) * H + oy + dy) * kCellCols;
+                    const uint32_t ta = (dx == 0 ? cb0 : dx == 1 ? cb1 : cb2) + dy * kCellCols;
                     umma_bf16_ts(d1, ta, make_desc(a_wchi + j * 256, 128, 2304), idesc, j > 0);
                     umma_bf16_ts(d1, ta, make_desc(a_wclo + j * 256, 128, 2304), idesc, 1);
                 }
                 umma_commit(bars + 8 * (b_full + st));
-                for (int c = released; c < keep; ++c) umma_commit(bars + 8 * (col_empty + (gcb + c) % ring));
+                uint32_t rs = r_slot;
+                for (int c = released; c < keep; ++c) {
+                    umma_commit(bars + 8 * (col_empty + rs));
+                    rs = (rs + 1 == ring) ? 0 : rs + 1;
+                }
                 // last conv of this issuer in the tile: its reads of the conv weights are done once these MMAs complete
-                if (nxt >= npos) umma_commit(bars + 8 * (PB_HEAD_EMPTY + (u & 1)));
+                if (cp + cpstep >= npos) umma_commit(bars + 8 * (PB_HEAD_EMPTY + (u & 1)));
             }
             __syncwarp();
-            released = keep > released ? keep : released;
+            for (; released < keep; ++released) r_slot = (r_slot + 1 == ring) ? 0 : r_slot + 1;
             if (kProf) pw[PW_ISSUE_CONV] += clock64() - ti0;
             if (cp < 8 && tracer) trace_ev<kProf>(prm, t - t0, 16 + cp);
             ++uses[st];
+            ox = nox, oy = noy, c_slot = n_slot;
         }
+        advance(t_slot, t_round, W);
     }
 }
 
