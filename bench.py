@@ -253,45 +253,100 @@ def run_reference_arm(args):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock / throttle-reason samples of one GPU while the bench runs.  NVML in a thread (20 ms period; the pipe of
+    `nvidia-smi -lms` is block-buffered on some boxes and delivered nothing inside a short run), `nvidia-smi` as the
+    fallback when NVML cannot be loaded.  `index` is torch's device index: the NVML handle is looked up by UUID, so
+    CUDA_VISIBLE_DEVICES does not confuse the two numberings."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows, self.proc = [], None
+    def __init__(self, index, uuid=None):
+        self.rows, self.proc, self.nvml, self.source = [], None, None, None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid is not None:
+                for cand in ("GPU-" + str(uuid), str(uuid)):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if not isinstance(cand, bytes) else cand)
+                        break
+                    except Exception:
+                        try:
+                            h = pynvml.nvmlDeviceGetHandleByUUID(cand)
+                            break
+                        except Exception:
+                            h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml, self.handle = pynvml, h
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
-
-    def stop(self, t_begin, t_end):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t_begin - 0.05 <= t <= t_end + 0.15] or [r for _, r in self.rows]
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        bits = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+        while not self._stop.is_set():
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                try:
+                    util = int(nv.nvmlDeviceGetUtilizationRates(h).gpu)
+                except Exception:
+                    util = -1
+                self.rows.append((time.perf_counter(), (sm, self.sm_max, [n for n, b in bits if mask & b], util)))
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def _pump(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
+            try:
+                row = (float(f[0]), float(f[1]), [nm for nm, v in zip(names, f[3:7]) if v.lower().startswith("active")], -1)
             except Exception:
                 continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            self.rows.append((time.perf_counter(), row))
+
+    def stop(self, t_begin, t_end):
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"], "samples": 0}
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        self._stop.set()
+        rows = [r for t, r in self.rows if t_begin - 0.05 <= t <= t_end + 0.15] or [r for _, r in self.rows]
+        busy = [r for r in rows if r[3] != 0] or rows  # NVML utilisation 0 = a sample between two legs (host-side setup)
+        sm = [r[0] for r in busy]
+        reasons = set()
+        for r in rows:
+            reasons.update(r[2])
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": max(r[1] for r in rows) if rows else None,
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def measured_peaks():
@@ -528,7 +583,7 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None  # nvidia-smi needs ~0.2 s to deliver its first sample
+    sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) if rank == 0 else None
     t_sampler = time.perf_counter()
     # A freshly leased GPU runs its first seconds of work measurably slower (the same binary measured 30 us in the first
     # process of a box and 24.7 us ten seconds later, profiles/README.md): bring the device to its steady state with

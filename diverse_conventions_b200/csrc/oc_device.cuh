@@ -24,6 +24,36 @@ __device__ __forceinline__ void bulk_wait_read_all() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// ---- rebuild of a warp tile's planes by ONE bulk copy per view (global template tile -> shared), tracked by an mbarrier.
+// The per-lane rebuild (obs_phase1 with full = true) costs SC / 4 shared stores per world and view; at one env step per
+// launch that loop was the largest single item of the kernel (ncu source view, 16 % of the instructions).
+__device__ __forceinline__ void tile_fill_begin(uint32_t bar, uint32_t planes_s, int view_stride, const uint8_t* tile,
+                                                uint32_t bytes, int views) {  // one lane
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (uint32_t)views) : "memory");
+    for (int v = 0; v < views; ++v)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         planes_s + (uint32_t)(v * view_stride)),
+                     "l"(tile), "r"(bytes), "r"(bar)
+                     : "memory");
+}
+__device__ __forceinline__ void tile_fill_wait(uint32_t bar) {  // every lane that goes on to touch the planes
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(0u)
+            : "memory");
+        if (ok) return;
+        if (spins > (1u << 24)) __trap();
+    }
+}
+
 __device__ __forceinline__ int load_action(const void* a, int dtype, size_t idx) {
     int v;
     switch (dtype) {
@@ -71,21 +101,20 @@ __device__ __forceinline__ void load_world(const Tables& tb, const Consts& c, co
     w.timestep = prm.timestep[nl];
     // `myobjs` is this LANE's private column of the warp's [S][32] object array: the G lanes of a world split the
     // global loads and write each value into all G sibling columns (disjoint cells per writer), after which every
-    // lane only ever touches its own column
+    // lane only ever touches its own column.  Only counters and pots can hold an object (step_world, import check):
+    // the other cells are neither loaded nor stored, nor ever read from shared memory.
     uint16_t* col0 = myobjs - g;  // column of the world's lane 0
-    for (int cell = g; cell < tb.S; cell += G) {
-        const uint16_t v = prm.objs[(size_t)cell * N + nl];
-#pragma unroll
-        for (int h = 0; h < G; ++h) col0[cell * 32 + h] = v;
-    }
-    __syncwarp();
     int cd = 0, np = 0;
     for (int idx = g; idx < c.n_objcells; idx += G) {
-        const uint32_t ci = tb.cell_info[tb.objcells[idx]];
-        const uint32_t o = myobjs[info_cell(ci) * 32];
-        cd += (info_terrain(ci) == T_COUNTER && obj_name(o) == O_DISH);
-        np += (info_terrain(ci) == T_POT) ? pot_counts(o) : 0;
+        const int cell = (int)tb.objcells[idx];
+        const uint32_t o = prm.objs[(size_t)cell * N + nl];
+#pragma unroll
+        for (int h = 0; h < G; ++h) col0[cell * 32 + h] = (uint16_t)o;
+        const int t = info_terrain(tb.cell_info[cell]);
+        cd += (t == T_COUNTER && obj_name(o) == O_DISH);
+        np += (t == T_POT) ? pot_counts(o) : 0;
     }
+    __syncwarp();
 #pragma unroll
     for (int m = 1; m < G; m <<= 1) {
         cd += __shfl_xor_sync(0xffffffffu, cd, m);
@@ -93,6 +122,16 @@ __device__ __forceinline__ void load_world(const Tables& tb, const Consts& c, co
     }
     w.counter_dishes = cd;
     w.nonempty_pots = np;
+}
+
+// shared memory -> HBM: the cells that can hold an object (the counterpart of load_world)
+template <int G>
+__device__ __forceinline__ void store_world_objs(const Tables& tb, const Consts& c, const RolloutParams& prm, int n, int g,
+                                                 const uint16_t* myobjs) {
+    for (int idx = g; idx < c.n_objcells; idx += G) {
+        const int cell = (int)tb.objcells[idx];
+        prm.objs[(size_t)cell * prm.N + n] = myobjs[cell * 32];
+    }
 }
 
 }  // namespace ocb

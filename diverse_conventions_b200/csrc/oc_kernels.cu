@@ -27,16 +27,18 @@
 namespace ocb {
 
 // shared-memory carve-up of one CTA (all offsets 16-byte aligned):
-//   Tables | template[SC] | per warp: planes[P][view_stride] , objs[S][32] u16 (one column per LANE)
+//   Tables | template[SC] | mbarriers | per warp: planes[P][view_stride] , objs[S][32] u16 (one column per LANE)
+constexpr int kFillBarBytes = 64;
 template <int P, int G>
 struct Carve {
     static constexpr int WPW = 32 / G;
     int view_stride;
-    size_t warp_bytes, warp0;
+    size_t warp_bytes, warp0, bars;
     __device__ Carve(int S, int SC) {
         view_stride = (int)align16((size_t)WPW * SC);
         warp_bytes = (size_t)P * view_stride + align16((size_t)S * 32 * 2);
-        warp0 = align16(sizeof(Tables)) + align16((size_t)SC);
+        bars = align16(sizeof(Tables)) + align16((size_t)SC);  // one mbarrier per warp (tile_fill_begin)
+        warp0 = bars + kFillBarBytes;
     }
 };
 
@@ -77,8 +79,19 @@ __global__ void __launch_bounds__(kThreadsPerCta, (G == 8 ? 6 : 4)) oc_rollout_k
     const bool valid = n < N;
     const int nl = valid ? n : N - 1;
 
+    // planes <- static template of the whole tile, by bulk copy, while the state loads and the first transition runs
+    const bool want_obs0 = prm.obs != nullptr;
+    const int tile_bytes = WPW * SC;
+    const bool tile_fill = want_obs0 && (tile_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(prm.tmpl) & 15u) == 0;
+    const uint32_t fill_bar = smem_u32(smem + cv.bars) + 8u * (uint32_t)warp;
+    if (tile_fill && lane == 0) tile_fill_begin(fill_bar, smem_u32(planes), view_stride, prm.tmpl, (uint32_t)tile_bytes, P);
+    __syncwarp();
+
     World<P> w;
     load_world<P, G>(tb, c, prm, nl, g, myobjs, w);
+    // (waited for here, not inside the step loop: the loop runs at the register limit of its launch bounds)
+    if (tile_fill) tile_fill_wait(fill_bar);
+    bool rebuild1 = !tile_fill;  // first step of the launch: phase 1 copies the template unless the bulk copy did
     int cur_return = prm.cur_return[nl];
     long long ret_add = 0;
     int ep_add = 0;
@@ -161,7 +174,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, (G == 8 ? 6 : 4)) oc_rollout_k
                 tma_pending = false;
             }
             __syncwarp();
-            obs_phase1<P, G>(tb, myplanes, view_stride, tmpl, full, g, oldslot);
+            obs_phase1<P, G>(tb, myplanes, view_stride, tmpl, rebuild1 || done, g, oldslot);
+            rebuild1 = false;
             __syncwarp();
             obs_phase2<P, G>(tb, c, myplanes, view_stride, myobjs, 32, full, g, w, dirty);
             if (tma_ok) {
@@ -193,7 +207,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, (G == 8 ? 6 : 4)) oc_rollout_k
 #pragma unroll
         for (int i = 0; i < P; ++i)
             if (i % G == g) prm.players[(size_t)i * N + n] = player_pack(w.pos[i], w.orient[i], w.held[i]);
-        for (int cell = g; cell < S; cell += G) prm.objs[(size_t)cell * N + n] = myobjs[cell * 32];
+        store_world_objs<G>(tb, c, prm, n, g, myobjs);
         if (g == 0) {
             prm.timestep[n] = w.timestep;
             prm.cur_return[n] = cur_return;
@@ -230,13 +244,22 @@ __global__ void __launch_bounds__(kThreadsPerCta) oc_observe_kernel(const Rollou
     const int nvalid = min(WPW, N - n0);
     const int nl = min(n0 + wi, N - 1);
 
+    const int tile_bytes = WPW * SC;
+    const bool tile_fill = (tile_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(prm.tmpl) & 15u) == 0;
+    const uint32_t fill_bar = smem_u32(smem + cv.bars) + 8u * (uint32_t)warp;
+    if (tile_fill && lane == 0) tile_fill_begin(fill_bar, smem_u32(planes), view_stride, prm.tmpl, (uint32_t)tile_bytes, P);
+    __syncwarp();
+
     World<P> w;
     load_world<P, G>(tb, c, prm, nl, g, myobjs, w);
     int noslot[P];
     uint32_t nodirty[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) noslot[i] = 0, nodirty[i] = 0xFFFFFFFFu;
-    obs_phase1<P, G>(tb, myplanes, view_stride, tmpl, true, g, noslot);
+    if (tile_fill)
+        tile_fill_wait(fill_bar);
+    else
+        obs_phase1<P, G>(tb, myplanes, view_stride, tmpl, true, g, noslot);
     __syncwarp();
     obs_phase2<P, G>(tb, c, myplanes, view_stride, myobjs, 32, true, g, w, nodirty);
     __syncwarp();
@@ -364,7 +387,7 @@ size_t rollout_smem_bytes(int P, int S, int C, int G, int warps_per_cta) {
     const int WPW = 32 / G;
     const size_t SC = (size_t)S * C;
     const size_t per_warp = (size_t)P * align16(WPW * SC) + align16((size_t)S * 32 * 2);
-    return align16(sizeof(Tables)) + align16(SC) + warps_per_cta * per_warp;
+    return align16(sizeof(Tables)) + align16(SC) + kFillBarBytes + warps_per_cta * per_warp;
 }
 
 template <int P>

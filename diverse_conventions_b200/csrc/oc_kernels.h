@@ -14,7 +14,9 @@ __host__ __device__ constexpr size_t align16(size_t x) { return (x + 15) & ~(siz
 
 struct RolloutParams {
     const Tables* tables;  // device copy of the static layout tables
-    const uint8_t* tmpl;   // device, [S*C] static part of one observation plane
+    const uint8_t* tmpl;   // device, [32][S*C]: the static part of one observation plane, repeated for the 32 worlds of a
+                           // warp tile (row 0 is what the per-world rebuild reads; the whole tile is the source of the bulk
+                           // copy that rebuilds a warp's planes at the start of a launch)
     // world state, structure-of-arrays in HBM
     uint32_t* players;   // [P][N]  pos | orient<<12 | held<<16
     uint16_t* objs;      // [S][N]  packed object per cell

@@ -6,6 +6,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include <new>
 
 #include "api_common.h"
@@ -79,6 +81,13 @@ static int default_lanes(int N, int SC) {
     if (N < 16384) return big ? 2 : 4;
     return big ? 2 : 1;
 }
+
+// lanes per world of single-step / observe launches.  The planes of a tile are rebuilt by one bulk copy per view
+// (tile_fill_begin), so what is left per world is the state load and the sequential transition: from a few thousand worlds
+// on two lanes per world win (tools/step_single.py on B200: 262,144 worlds of coordination_ring 113 us at G = 2 against
+// 144 / 160 / 190 at 4 / 8 / 1; 32,768 worlds 21.1 against 23.3 / 27.4 / 23.4; 8,192 worlds of cramped_room 10.3 against
+// 10.9 / 11.4 / 13.0); below that the launch is latency-bound (10 us) and more lanes hide the transition better.
+static int default_step_lanes(int N) { return N >= 4096 ? 2 : 8; }
 
 static int pick_launch_shape(const ocb_env* e, int G, int* warps, size_t* smem) {
     // 4 warps per CTA measured best on B200 even when that leaves some SMs without a CTA
@@ -164,7 +173,7 @@ extern "C" int ocb_create(const ocb_config* cfg, int device, uint32_t num_worlds
     e->L = 1 + 6 * e->P + 4 * e->S;
     e->seed = seed;
     e->lanes_per_world = default_lanes(e->N, e->SC);
-    e->step_lanes = 8;
+    e->step_lanes = default_step_lanes(e->N);
     e->use_tma = 1;
 
     DeviceGuard guard(device);
@@ -180,7 +189,7 @@ extern "C" int ocb_create(const ocb_config* cfg, int device, uint32_t num_worlds
         }                                                                                     \
     } while (0)
     OCB_TRY(cudaMalloc(&e->d_tables, sizeof(Tables)));
-    OCB_TRY(cudaMalloc(&e->d_tmpl, align16(e->SC)));
+    OCB_TRY(cudaMalloc(&e->d_tmpl, align16((size_t)32 * e->SC)));
     OCB_TRY(cudaMalloc(&e->d_players, sizeof(uint32_t) * e->P * N));
     OCB_TRY(cudaMalloc(&e->d_objs, sizeof(uint16_t) * e->S * N));
     OCB_TRY(cudaMalloc(&e->d_timestep, sizeof(int32_t) * N));
@@ -190,7 +199,11 @@ extern "C" int ocb_create(const ocb_config* cfg, int device, uint32_t num_worlds
     OCB_TRY(cudaMalloc(&e->d_step_counter, sizeof(unsigned long long)));
     OCB_TRY(cudaMemset(e->d_step_counter, 0, sizeof(unsigned long long)));
     OCB_TRY(cudaMemcpy(e->d_tables, &e->h_tables, sizeof(Tables), cudaMemcpyHostToDevice));
-    OCB_TRY(cudaMemcpy(e->d_tmpl, tmpl, e->SC, cudaMemcpyHostToDevice));
+    {   // 32 copies: one bulk copy rebuilds the planes of a whole warp tile (oc_kernels.cu: tile_fill_begin)
+        std::vector<uint8_t> tile((size_t)32 * e->SC);
+        for (int r = 0; r < 32; ++r) memcpy(tile.data() + (size_t)r * e->SC, tmpl, (size_t)e->SC);
+        OCB_TRY(cudaMemcpy(e->d_tmpl, tile.data(), tile.size(), cudaMemcpyHostToDevice));
+    }
     OCB_TRY(cudaMemset(e->d_ret_sum, 0, sizeof(long long) * N));
     OCB_TRY(cudaMemset(e->d_episodes, 0, sizeof(int32_t) * N));
     OCB_TRY(launch_reset(e->d_tables, e->d_players, e->d_objs, e->d_timestep, e->d_cur_return, e->N,
@@ -254,7 +267,7 @@ extern "C" int ocb_set_tuning(ocb_env* e, int lanes_per_world, int use_tma) {
     int rc = pick_launch_shape(e, lanes_per_world, &warps, &smem);
     if (rc != OCB_OK) return rc;
     e->lanes_per_world = lanes_per_world;
-    e->step_lanes = explicit_lanes ? lanes_per_world : 8;
+    e->step_lanes = explicit_lanes ? lanes_per_world : default_step_lanes(e->N);
     e->use_tma = use_tma ? 1 : 0;
     return OCB_OK;
 }

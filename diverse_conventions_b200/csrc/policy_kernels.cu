@@ -131,6 +131,7 @@ struct PolicyParams {
     long long* prof;          // diagnostic build: [ctas][4 roles][PW_COUNT] stall cycles
     long long* trace;         // diagnostic build of the fused rollout: [trace_n steps][kTraceEvents] clock64 stamps of CTA 0
     int trace_u0, trace_n;    // first traced virtual tile (step) and number of traced steps
+    int single;               // policy_pair_kernel: 0 = both networks of a tile, 1 = the actor only, 2 = the critic only (one stream)
 };
 
 // shared-memory carve-up (byte offsets from a 128-byte aligned base)
@@ -888,7 +889,8 @@ __host__ __device__ inline PairSmemLayout pair_smem_layout(int npos, int ring, i
 template <bool kProf>
 __device__ __forceinline__ void pair_producer_role(long long* pw, const PolicyParams& prm, int t0, int t1, const BlobLayout L,
                                                    uint32_t s_head, uint32_t s_wring, uint32_t bars) {
-    const int R = prm.pair_ring, nch = 2 * L.chunks;
+    const int nets = prm.single ? 1 : 2;  // single mode: the one network takes the actor's places (stream 0, ring slots 0, 1, ...)
+    const int R = prm.pair_ring, nch = nets * L.chunks;
     const bool resident = R >= nch;
     const bool static_w = resident && prm.tile_policy == nullptr;  // nothing to do after the first tile (pair_fc_role)
     const int Reff = resident ? nch : R;
@@ -898,19 +900,21 @@ __device__ __forceinline__ void pair_producer_role(long long* pw, const PolicyPa
     for (int t = t0; t < t1; ++t, ++u) {
         if (static_w && u > 0) break;
         const bool chg = blob_changed(prm, t, t0);
-        const uint8_t* blob_a = prm.blobs + (size_t)tile_pol(prm, t) * 2 * prm.blob_stride;
+        const uint8_t* blob_a = prm.blobs + ((size_t)tile_pol(prm, t) * 2 + (prm.single == 2 ? 1 : 0)) * prm.blob_stride;
         const uint8_t* blob_c = blob_a + prm.blob_stride;
         if (chg) {
             if (u > 0) mbar_wait_p<kProf>(bars + 8 * (PB_HEAD_EMPTY + ((u - 1) & 1)), ((u - 1) >> 1) & 1, pw[PW_HEAD_EMPTY]);
             if (elect_one()) {
                 const uint32_t hb = bars + 8 * PB_HEAD_FULL;
-                mbar_arrive_expect_tx(hb, 4u * kPConvBytes + 2u * rest);
+                mbar_arrive_expect_tx(hb, (uint32_t)nets * (2u * kPConvBytes + rest));
                 bulk_g2s(s_head, blob_a + L.wc_hi, kPConvBytes, hb);
-                bulk_g2s(s_head + kPConvBytes, blob_c + L.wc_hi, kPConvBytes, hb);
                 bulk_g2s(s_head + 2 * kPConvBytes, blob_a + L.wc_lo, kPConvBytes, hb);
-                bulk_g2s(s_head + 3 * kPConvBytes, blob_c + L.wc_lo, kPConvBytes, hb);
                 bulk_g2s(s_head + kPRestOff, blob_a + L.bias1, rest, hb);
-                bulk_g2s(s_head + kPRestOff + rest, blob_c + L.bias1, rest, hb);
+                if (nets == 2) {
+                    bulk_g2s(s_head + kPConvBytes, blob_c + L.wc_hi, kPConvBytes, hb);
+                    bulk_g2s(s_head + 3 * kPConvBytes, blob_c + L.wc_lo, kPConvBytes, hb);
+                    bulk_g2s(s_head + kPRestOff + rest, blob_c + L.bias1, rest, hb);
+                }
             }
             __syncwarp();
         }
@@ -918,6 +922,7 @@ __device__ __forceinline__ void pair_producer_role(long long* pw, const PolicyPa
         for (int j = 0; j < L.chunks; ++j) {
 #pragma unroll
             for (int g = 0; g < 2; ++g) {  // ring order: (actor, j), (critic, j) -> pair_fc_role g takes every other chunk
+                if (g >= nets) break;
                 if (round > 0) mbar_wait_p<kProf>(bars + 8 * (PB_W_EMPTY + slot), (round - 1) & 1, pw[PW_W_EMPTY]);
                 if (load) {
                     if (elect_one()) {
@@ -1049,7 +1054,8 @@ template <bool kProf, bool kSplit>
 __device__ __forceinline__ void pair_fc_role(long long* pw, const PolicyParams& prm, const int g, int t0, int t1, const BlobLayout L,
                                              uint32_t tmem, uint32_t a_wring, uint32_t bars) {
     const int npos = prm.npos;
-    const int R = prm.pair_ring, nch = 2 * L.chunks;
+    const int nets = prm.single ? 1 : 2;
+    const int R = prm.pair_ring, nch = nets * L.chunks;
     const bool resident = R >= nch;
     const bool static_w = resident && prm.tile_policy == nullptr;  // one weight set for the whole launch: loaded once
     const int Reff = resident ? nch : R;
@@ -1095,7 +1101,7 @@ __device__ __forceinline__ void pair_fc_role(long long* pw, const PolicyParams& 
             if (kProf) pw[PW_ISSUE_FC] += clock64() - tf0;
             if (g == 0 && j < 8) trace_ev<kProf>(prm, t - t0, 24 + j);
             if (g == 1 && j == npos) trace_ev<kProf>(prm, t - t0, 58);
-            slot += 2;
+            slot += nets;
             if (slot >= Reff) slot -= Reff, ++wround;
         }
     }
@@ -1115,6 +1121,7 @@ __device__ __forceinline__ void pair_epilogue_role(long long* pw, const PolicyPa
     const float* s_wh = reinterpret_cast<const float*>(rest + L.wh);
     const float* s_bh = reinterpret_cast<const float*>(rest + L.bh);
     const uint32_t a2 = trow + kPColA2 + g * kA2Cols;
+    const int net = prm.single == 2 ? 1 : g;  // head layout / outputs: 0 = actor (6 logits), 1 = critic (value)
 
     uint32_t u = 0, head_gen = 0, item = 0, d1_par = 0;  // d1_par: phase parity bit per conv accumulator stage
     int trace_vt = 0, trace_item = 0;
@@ -1175,7 +1182,7 @@ __device__ __forceinline__ void pair_epilogue_role(long long* pw, const PolicyPa
         }
 
         // ---- FC2 epilogue + head (fp32 on CUDA cores), all 64 hidden units of this network
-        const uint32_t drawn = g == 0 ? out.draw(t, trow_id) : 0u;  // off the critical path: while FC2 runs
+        const uint32_t drawn = net == 0 ? out.draw(t, trow_id) : 0u;  // off the critical path: while FC2 runs
         mbar_wait_p<kProf>(bars + 8 * (PB_D3_FULL + g), u & 1, pw[PW_D3_FULL]);
         if (kProf && (warp & 3) == 0) trace_ev<kProf>(prm, trace_vt, g == 0 ? 49 : 52);
         tc_fence_after();
@@ -1190,11 +1197,11 @@ __device__ __forceinline__ void pair_epilogue_role(long long* pw, const PolicyPa
                 tc_fence_before();
                 mbar_arrive(bars + 8 * (PB_D3_EMPTY + g));
             }
-            head_accumulate(g, v, s_b2 + half * 32, s_wh, half * 32, head);
+            head_accumulate(net, v, s_b2 + half * 32, s_wh, half * 32, head);
         }
         mbar_arrive(bars + 8 * (PB_HEAD_EMPTY + (u & 1)));  // done with the head block of this tile
         if (kProf && (warp & 3) == 0) trace_ev<kProf>(prm, trace_vt, g == 0 ? 50 : 53);
-        out(t, trow_id, g, head, drawn);
+        out(t, trow_id, net, head, drawn);
         if (kProf && warp == 0) trace_ev<kProf>(prm, trace_vt, 51);
     }
 }
@@ -1209,10 +1216,10 @@ struct PairForwardOut {
         if (prm.deterministic || prm.given_actions != nullptr || !(prm.actions || prm.logp)) return 0u;
         return policy_draw(prm, (uint32_t)((long long)t * kRows + trow_id), offset);
     }
-    __device__ __forceinline__ void operator()(int t, int trow_id, int g, const float (&head)[6], uint32_t drawn) const {
+    __device__ __forceinline__ void operator()(int t, int trow_id, int net, const float (&head)[6], uint32_t drawn) const {
         const long long row = (long long)t * kRows + trow_id;
         if (row < prm.M) {
-            if (g == 1) {
+            if (net == 1) {
                 if (prm.values) prm.values[row] = head[0];
             } else {
                 emit_actor_row(prm, row, (uint32_t)row, head, offset, false, &drawn);
@@ -1248,8 +1255,9 @@ __global__ void __launch_bounds__(kPThreads, 1) policy_pair_kernel(const PolicyP
                 (i >= PB_D3_EMPTY && i < PB_D3_EMPTY + 2))
                 count = 128;
             if (i >= PB_COL_EMPTY && i < PB_COL_EMPTY + 4) count = 2;  // both conv issuers are done with the column
-            if (i >= PB_HEAD_EMPTY && i < PB_HEAD_EMPTY + 2) count = 32 * kEpiWarps + 2;
+            if (i >= PB_HEAD_EMPTY && i < PB_HEAD_EMPTY + 2) count = (prm.single ? 128 : 32 * kEpiWarps) + 2;
             if (i >= PB_D1_EMPTY && i < PB_D1_EMPTY + 2) count = 32 * kEpiWarps;
+            if (i >= PBS_D1_EMPTY && i < PBS_D1_EMPTY + 4) count = 128;  // single mode runs the split-mode stream of "network 0"
             mbar_init(bars + 8 * i, count);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1266,7 +1274,21 @@ __global__ void __launch_bounds__(kPThreads, 1) policy_pair_kernel(const PolicyP
 
     long long pw[kProf ? PW_COUNT : 1] = {};
     const long long t_begin = kProf ? clock64() : 0;
-    if (warp < kEpiWarps) {
+    if (prm.single) {
+        // ONE network per tile (ocb_policy_act / _value, cross-play evaluation): the split-mode stream of "network 0" — N = 32
+        // conv from two issuers, one FC issuer, epilogue group 0; warps 4-7 and the second FC issuer have nothing to do
+        if (warp < 4) {
+            pair_epilogue_role<kProf, true>(pw, prm, ur.t0, ur.t1, L, tmem, s_head, bars, PairForwardOut(prm));
+        } else if (warp >= kEpiWarps && warp < kWarpMma) {
+            loader_role<kProf>(pw, prm, ur, tmem, s_stage, bars);
+        } else if (warp == kWarpMma || warp == kWarpConv2) {
+            pair_conv_role<kProf, 0>(pw, prm, ur.t0, ur.t1, L, tmem, smem_addr(s_head), bars, warp == kWarpMma ? 0 : 1, 2);
+        } else if (warp == kPWarpProd) {
+            pair_producer_role<kProf>(pw, prm, ur.t0, ur.t1, L, smem_addr(s_head), smem_addr(s_wring), bars);
+        } else if (warp == kWarpFc) {
+            pair_fc_role<kProf, true>(pw, prm, 0, ur.t0, ur.t1, L, tmem, smem_addr(s_wring), bars);
+        }
+    } else if (warp < kEpiWarps) {
         pair_epilogue_role<kProf, false>(pw, prm, ur.t0, ur.t1, L, tmem, s_head, bars, PairForwardOut(prm));
     } else if (warp < kWarpMma) {
         loader_role<kProf>(pw, prm, ur, tmem, s_stage, bars);
@@ -1326,6 +1348,7 @@ struct ocb_policy {
     int pair_ring;            // 0: the pair kernel is not usable for this layout
     size_t pair_smem_bytes;
     int use_pair;             // run ocb_policy_forward through policy_pair_kernel (env OCB_POLICY_PAIR=0 disables)
+    int use_single;           // ... and the single-network calls through its one-stream mode (env OCB_POLICY_SINGLE=0: policy_fwd_kernel)
     std::vector<uint8_t> terrain;
     BlobLayout L;
     uint8_t* d_blobs;
@@ -1409,7 +1432,7 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
     p->generic = generic ? 1 : 0;
     p->npos = (p->W - 2) * (p->H - 2), p->n_policies = n_policies, p->calls = 0, p->d_blobs = nullptr;
     p->hidden = hidden, p->d_scratch = nullptr, p->scratch_tiles = 0, p->L5 = blob5_layout(p->npos);
-    p->ring = 0, p->smem_bytes = 0, p->pair_ring = 0, p->pair_smem_bytes = 0, p->use_pair = 0;
+    p->ring = 0, p->smem_bytes = 0, p->pair_ring = 0, p->pair_smem_bytes = 0, p->use_pair = 0, p->use_single = 0;
     p->terrain.assign(cfg->terrain, cfg->terrain + p->S);
     p->L = blob_layout(p->npos);
     p->stage_stride = (5 * p->H) | 1;
@@ -1441,6 +1464,8 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
         p->pair_smem_bytes = p->pair_ring ? (size_t)pair_smem_layout(p->npos, p->pair_ring, p->stage_stride).total : 0;
         const char* e = getenv("OCB_POLICY_PAIR");
         p->use_pair = p->pair_ring != 0 && !(e != nullptr && e[0] == '0');
+        const char* e1 = getenv("OCB_POLICY_SINGLE");
+        p->use_single = !(e1 != nullptr && e1[0] == '0');
     }
     } else if (c5_smem_layout(p->npos, p->stage_stride).total > kSmemBudget + 128) {
         delete p;
@@ -1747,7 +1772,8 @@ static int policy_launch(ocb_policy* p, int net_mask, const int8_t* obs, int M, 
     }
     // persistent grid: one CTA per SM
     int ctas;
-    if (net_mask == 3 && p->use_pair) {  // both networks of a tile in one CTA
+    if (p->use_pair && (net_mask == 3 || p->use_single)) {  // both networks of a tile in one CTA, or the one asked for as one stream
+        prm.single = net_mask == 3 ? 0 : net_mask;
         ctas = prm.tiles < p->sm_count ? prm.tiles : p->sm_count;
         if (ctas_out) *ctas_out = ctas;
         if (prof != nullptr)

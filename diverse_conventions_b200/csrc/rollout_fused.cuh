@@ -170,7 +170,7 @@ __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s
     constexpr int P = 2;
     const int ew = (threadIdx.x >> 5) - kFWarpEnv, lane = threadIdx.x & 31;
     const Consts c = load_consts(tb);
-    const int SC = tb.SC, S = tb.S, N = fp.env.N, T = fp.T;
+    const int SC = tb.SC, N = fp.env.N, T = fp.T;
     const int view_stride = sl.view_stride;
     uint8_t* planes = s_env + ew * sl.env_warp_bytes;                                          // [P][32][SC]
     uint16_t* myobjs = reinterpret_cast<uint16_t*>(planes + (size_t)P * view_stride) + lane;  // [S][32]
@@ -264,7 +264,7 @@ __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s
         if (valid) {
             fp.env.players[n] = player_pack(w.pos[0], w.orient[0], w.held[0]);
             fp.env.players[(size_t)N + n] = player_pack(w.pos[1], w.orient[1], w.held[1]);
-            for (int cell = 0; cell < S; ++cell) fp.env.objs[(size_t)cell * N + n] = myobjs[cell * 32];
+            store_world_objs<1>(tb, c, fp.env, n, 0, myobjs);
             fp.env.timestep[n] = w.timestep;
             fp.env.cur_return[n] = cur_return;
             if (ep_add) {

@@ -26,7 +26,7 @@ from diverse_conventions_b200.rollout import RolloutBuffer  # noqa: E402
 NAMES = {0: "env_got_actions", 1: "env_stepped", 2: "env_planes_free", 3: "env_planes_published", 8: "loader_sees_planes",
          9: "loader_first_col", 10: "loader_last_col", 48: "epi_sees_D2", 49: "epi_sees_D3", 50: "head_done",
          51: "actions_handed", 52: "critic_sees_D3", 53: "critic_head_done"}
-NAMES.update({54: "conv3_issue_starts", 55: "FC2a_issue_starts", 56: "FC2a_mmas_issued", 57: "FC2a_critic_issue_starts",
+NAMES.update({54: "conv3_issue_starts", 55: "FC2a_issue_starts", 56: "conv3_first_mma", 63: "conv3_mmas_issued", 57: "FC2a_critic_issue_starts",
               58: "FC2a_critic_issued", 59: "epi_conv2_in_regs", 60: "epi_conv2_split_done", 61: "epi_conv2_stored",
               62: "FC2a_operand_seen"})
 for p in range(8):
