@@ -86,7 +86,7 @@ __device__ __forceinline__ void warp_copy_out(int8_t* __restrict__ dst, const ui
 }
 
 // HBM -> registers / shared memory
-template <int P, int G>
+template <int P, int G, int kBatch = 8>
 __device__ __forceinline__ void load_world(const Tables& tb, const Consts& c, const RolloutParams& prm, int nl, int g,
                                            uint16_t* myobjs, World<P>& w) {
     const int N = prm.N;
@@ -105,14 +105,26 @@ __device__ __forceinline__ void load_world(const Tables& tb, const Consts& c, co
     // the other cells are neither loaded nor stored, nor ever read from shared memory.
     uint16_t* col0 = myobjs - g;  // column of the world's lane 0
     int cd = 0, np = 0;
-    for (int idx = g; idx < c.n_objcells; idx += G) {
-        const int cell = (int)tb.objcells[idx];
-        const uint32_t o = prm.objs[(size_t)cell * N + nl];
+    // batches of independent loads: one at a time (a dependent chain objcells[idx] -> address -> value -> store) left a
+    // single-step launch waiting ~700 cycles per cell (a third of its stall samples, ncu source view)
+    for (int i0 = g; i0 < c.n_objcells; i0 += kBatch * G) {
+        int cell[kBatch];
+        uint32_t o[kBatch];
 #pragma unroll
-        for (int h = 0; h < G; ++h) col0[cell * 32 + h] = (uint16_t)o;
-        const int t = info_terrain(tb.cell_info[cell]);
-        cd += (t == T_COUNTER && obj_name(o) == O_DISH);
-        np += (t == T_POT) ? pot_counts(o) : 0;
+        for (int j = 0; j < kBatch; ++j) {
+            const int idx = i0 + j * G;
+            cell[j] = idx < c.n_objcells ? (int)tb.objcells[idx] : -1;
+            o[j] = cell[j] >= 0 ? (uint32_t)prm.objs[(size_t)cell[j] * N + nl] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            if (cell[j] < 0) continue;
+#pragma unroll
+            for (int h = 0; h < G; ++h) col0[cell[j] * 32 + h] = (uint16_t)o[j];
+            const int t = info_terrain(tb.cell_info[cell[j]]);
+            cd += (t == T_COUNTER && obj_name(o[j]) == O_DISH);
+            np += (t == T_POT) ? pot_counts(o[j]) : 0;
+        }
     }
     __syncwarp();
 #pragma unroll

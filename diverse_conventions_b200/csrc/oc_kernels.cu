@@ -49,11 +49,19 @@ __device__ __forceinline__ void stage_tables(uint8_t* smem, const RolloutParams&
     __syncthreads();
     const int SC = reinterpret_cast<const Tables*>(smem)->SC;
     uint8_t* tmpl = smem + align16(sizeof(Tables));
-    for (int i = threadIdx.x; i < SC; i += blockDim.x) tmpl[i] = prm.tmpl[i];
+    if ((SC & 3) == 0) {  // the device template is 16-byte aligned
+        const uint32_t* t4 = reinterpret_cast<const uint32_t*>(prm.tmpl);
+        for (int i = threadIdx.x; i < (SC >> 2); i += blockDim.x) reinterpret_cast<uint32_t*>(tmpl)[i] = t4[i];
+    } else {
+        for (int i = threadIdx.x; i < SC; i += blockDim.x) tmpl[i] = prm.tmpl[i];
+    }
     __syncthreads();
 }
 
-template <int P, int G>
+// kFill: rebuild the planes of the tile at the start of the launch by one bulk copy per view (single-step launches, where
+// that rebuild is most of the work; the K-step launches keep the per-lane copy of their first step: their step loop runs
+// at the register limit of its launch bounds and measured 1-2 % slower with the extra state around it)
+template <int P, int G, bool kFill>
 __global__ void __launch_bounds__(kThreadsPerCta, (G == 8 ? 6 : 4)) oc_rollout_kernel(const RolloutParams prm) {
     constexpr int WPW = 32 / G;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -82,13 +90,13 @@ __global__ void __launch_bounds__(kThreadsPerCta, (G == 8 ? 6 : 4)) oc_rollout_k
     // planes <- static template of the whole tile, by bulk copy, while the state loads and the first transition runs
     const bool want_obs0 = prm.obs != nullptr;
     const int tile_bytes = WPW * SC;
-    const bool tile_fill = want_obs0 && (tile_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(prm.tmpl) & 15u) == 0;
+    const bool tile_fill = kFill && want_obs0 && (tile_bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(prm.tmpl) & 15u) == 0;
     const uint32_t fill_bar = smem_u32(smem + cv.bars) + 8u * (uint32_t)warp;
     if (tile_fill && lane == 0) tile_fill_begin(fill_bar, smem_u32(planes), view_stride, prm.tmpl, (uint32_t)tile_bytes, P);
     __syncwarp();
 
     World<P> w;
-    load_world<P, G>(tb, c, prm, nl, g, myobjs, w);
+    load_world<P, G, kFill ? 8 : 1>(tb, c, prm, nl, g, myobjs, w);
     // (waited for here, not inside the step loop: the loop runs at the register limit of its launch bounds)
     if (tile_fill) tile_fill_wait(fill_bar);
     bool rebuild1 = !tile_fill;  // first step of the launch: phase 1 copies the template unless the bulk copy did
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(kThreadsPerCta) oc_observe_kernel(const Rollou
     __syncwarp();
 
     World<P> w;
-    load_world<P, G>(tb, c, prm, nl, g, myobjs, w);
+    load_world<P, G, 8>(tb, c, prm, nl, g, myobjs, w);
     int noslot[P];
     uint32_t nodirty[P];
 #pragma unroll
@@ -374,7 +382,7 @@ static cudaError_t launch_pg(const RolloutParams& prm, int warps_per_cta, size_t
     constexpr int WPW = 32 / G;
     const int tiles = (prm.N + WPW - 1) / WPW;
     const int ctas = (tiles + warps_per_cta - 1) / warps_per_cta;
-    auto kern = observe_only ? oc_observe_kernel<P, G> : oc_rollout_kernel<P, G>;
+    auto kern = observe_only ? oc_observe_kernel<P, G> : (prm.K <= 2 ? oc_rollout_kernel<P, G, true> : oc_rollout_kernel<P, G, false>);
     if (smem_bytes > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;

@@ -242,7 +242,7 @@ __device__ __forceinline__ void mbar_wait_p(uint32_t mbar, uint32_t parity, long
 }
 // stall accounts written by ocb_policy_debug_profile: per CTA, per role, [0] = total cycles of the role
 enum : int { PW_TOTAL = 0, PW_COL_EMPTY, PW_HEAD_FULL, PW_COL_FULL, PW_A2_FULL, PW_W_FULL, PW_D1_FULL, PW_D2_FULL,
-             PW_A2_EMPTY, PW_D3_FULL, PW_HEAD_EMPTY, PW_W_EMPTY, PW_ISSUE_CONV, PW_ISSUE_FC, PW_LDG, PW_COUNT = 16 };
+             PW_A2_EMPTY, PW_D3_FULL, PW_HEAD_EMPTY, PW_W_EMPTY, PW_ISSUE_CONV, PW_ISSUE_FC, PW_LDG, PW_CVT, PW_COUNT = 16 };
 
 // event trace of the fused rollout (ocb_rollout_fused_debug_trace): one clock64 stamp per (step, event) of CTA 0.
 // Events: 0 env got actions | 1 env stepped | 2 env planes free | 3 env planes published | 8 loader sees planes |
@@ -396,6 +396,7 @@ __device__ __forceinline__ void loader_role(long long* pw, const PolicyParams& p
             tc_fence_after();
         }
         const uint32_t* mine = stg + lane * stride;
+        const long long tc0 = kProf ? clock64() : 0;
         for (int y = 0; y < H; ++y) {
             uint32_t w[5];
 #pragma unroll
@@ -408,6 +409,7 @@ __device__ __forceinline__ void loader_role(long long* pw, const PolicyParams& p
             tmem_st8(tcells + (slot * H + y) * kCellCols, c0, c1);
         }
         tmem_st_wait();
+        if (kProf) pw[PW_CVT] += clock64() - tc0;
         tc_fence_before();
         mbar_arrive(bars + 8 * (B_COL_FULL + slot));
         __syncwarp();  // the staging rows are rewritten by the next column
@@ -1007,7 +1009,9 @@ __device__ __forceinline__ void pair_conv_role(long long* pw, const PolicyParams
             // issuer alone; with cpstep = 1 the issuer alternates stages and counts per stage
             if (uses[st] > 0) mbar_wait_p<kProf>(bars + 8 * (b_empty + st), (uses[st] - 1) & 1, pw[PW_D1_FULL]);
             // ... and stage cp (< 2) was (part of) D3 of a network of the previous tile until its head epilogue read it
-            if (u > 0 && cp < 2) mbar_wait_p<kProf>(bars + 8 * (PB_D3_EMPTY + (kNet < 0 ? cp : kNet)), (u - 1) & 1, pw[PW_D3_FULL]);
+            // (single mode keeps D3 in the idle FC1 accumulator of "network 1": the next tile's conv does not wait for the head)
+            if (u > 0 && cp < 2 && !prm.single)
+                mbar_wait_p<kProf>(bars + 8 * (PB_D3_EMPTY + (kNet < 0 ? cp : kNet)), (u - 1) & 1, pw[PW_D3_FULL]);
             tc_fence_after();
             const uint32_t d1 = tmem + kPColD1 + (kNet < 0 ? st * kHid : kNet * kHid + st * kCo);
             // position of the next conv of this issuer -> first grid column it still reads
@@ -1205,6 +1209,152 @@ __device__ __forceinline__ void pair_epilogue_role(long long* pw, const PolicyPa
         if (kProf && warp == 0) trace_ev<kProf>(prm, trace_vt, 51);
     }
 }
+// ---------------------------------------------------------------- single mode: ONE network per tile
+// ocb_policy_act / ocb_policy_value / cross-play evaluation.  The conv is the split-mode stream of "network 0" (N = 32, two
+// issuers by position parity = accumulator stage).  BOTH epilogue groups work on the tile: group g takes the conv positions of
+// parity g (it reads accumulator stage g and owns A-operand stage g) and K half g of FC2's input; ONE FC issuer consumes the
+// items in position order, so every output element sums the same products in the same order as in the pair kernel; group 1
+// evaluates the head while group 0 is already at the next tile's positions.  D3 sits in the FC1 accumulator columns of the
+// absent second network, so the next tile's conv never waits for the head.  (Round 2a ran this mode on group 0 alone: the
+// epilogue group was the bottleneck, 14 k cycles per coordination_ring tile.)
+constexpr int kSColD3 = kPColD2 + kHid;
+constexpr int kSHeadGroup = 1;
+// Measured and dropped (524,288 rows of coordination_ring, 206 us): a second A-operand stage per group in the conv
+// accumulator columns of the absent second network (218 us), a nanosleep back-off in the loaders' ring-slot wait (209 us:
+// try_wait polls are 14 % of the issued instructions, but not what the working warps wait for).  ncu: 47.7 k warp
+// instructions per tile at ~79 % issue utilisation — the kernel is bound by instruction issue (loads, conversions, splits).
+
+template <bool kProf>
+__device__ __forceinline__ void single_fc_role(long long* pw, const PolicyParams& prm, int t0, int t1, const BlobLayout L, uint32_t tmem,
+                                               uint32_t a_wring, uint32_t bars) {
+    const int npos = prm.npos;
+    const int R = prm.pair_ring, nch = L.chunks;
+    const bool resident = R >= nch;
+    const bool static_w = resident && prm.tile_policy == nullptr;
+    const int Reff = resident ? nch : R;
+    const uint32_t idesc = make_idesc(kRows, kHid);
+    uint32_t u = 0, w_gen = 0, wround = 0;
+    uint32_t cnt0 = 0, cnt1 = 0;  // items consumed from group 0 / group 1
+    int slot = 0;
+    for (int t = t0; t < t1; ++t, ++u) {
+        const bool chg = blob_changed(prm, t, t0);
+        const bool w_loaded = !resident || chg;
+        if (resident && w_loaded) ++w_gen;
+        for (int j = 0; j < npos + 2; ++j) {
+            const int sg = j < npos ? (j & 1) : (j - npos);  // the group that published this item
+            const uint32_t k = sg ? cnt1 : cnt0;
+            mbar_wait_p<kProf>(bars + 8 * (PB_A2_FULL + sg), k & 1, pw[PW_A2_FULL]);
+            if (sg) ++cnt1; else ++cnt0;
+            // D3 of the previous tile must have been loaded by the head group before FC2 overwrites it
+            if (j == npos && u > 0) mbar_wait_p<kProf>(bars + 8 * PB_D3_EMPTY, (u - 1) & 1, pw[PW_D3_FULL]);
+            if (w_loaded) mbar_wait_p<kProf>(bars + 8 * (PB_W_FULL + slot), resident ? ((w_gen - 1) & 1) : (wround & 1), pw[PW_W_FULL]);
+            tc_fence_after();
+            const uint32_t dst = tmem + (j < npos ? kPColD2 : kSColD3);
+            const bool first = (j == 0 || j == npos);
+            const uint32_t a_hi = tmem + kPColA2 + sg * kA2Cols, a_lo = a_hi + 16;
+            const uint32_t b_hi = a_wring + slot * kChunk, b_lo = b_hi + 4096;
+            const long long tf0 = kProf ? clock64() : 0;
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const uint64_t bhi = make_desc(b_hi + ks * 256, 128, 512), blo = make_desc(b_lo + ks * 256, 128, 512);
+                    umma_bf16_ts(dst, a_hi + ks * 8, bhi, idesc, (!first || ks != 0) ? 1u : 0u);
+                    umma_bf16_ts(dst, a_hi + ks * 8, blo, idesc, 1);
+                    umma_bf16_ts(dst, a_lo + ks * 8, bhi, idesc, 1);
+                }
+                umma_commit(bars + 8 * (PB_A2_EMPTY + sg));
+                if (!static_w) umma_commit(bars + 8 * (PB_W_EMPTY + slot));
+                if (j == npos - 1) umma_commit(bars + 8 * PB_D2_FULL);
+                if (j == npos + 1) umma_commit(bars + 8 * PB_D3_FULL);
+            }
+            __syncwarp();
+            if (kProf) pw[PW_ISSUE_FC] += clock64() - tf0;
+            if (++slot >= Reff) slot = 0, ++wround;
+        }
+    }
+}
+
+template <bool kProf, class Out>
+__device__ __forceinline__ void single_epilogue_role(long long* pw, const PolicyParams& prm, int t0, int t1, const BlobLayout L,
+                                                     uint32_t tmem, const uint8_t* s_head, uint32_t bars, Out&& out) {
+    const int warp = threadIdx.x >> 5, g = warp >> 2, trow_id = (warp & 3) * 32 + (threadIdx.x & 31);
+    const int npos = prm.npos;
+    const int net = prm.single == 2 ? 1 : 0;  // head layout / outputs: 0 = actor (6 logits), 1 = critic (value)
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint8_t* rest = s_head + kPRestOff - L.bias1;  // the network's bias1 .. bh at their blob offsets
+    const float* s_bias1 = reinterpret_cast<const float*>(rest + L.bias1);
+    const float* s_b1 = reinterpret_cast<const float*>(rest + L.b1);
+    const float* s_b2 = reinterpret_cast<const float*>(rest + L.b2);
+    const float* s_wh = reinterpret_cast<const float*>(rest + L.wh);
+    const float* s_bh = reinterpret_cast<const float*>(rest + L.bh);
+    uint32_t u = 0, head_gen = 0, pubs = 0, d1_uses = 0;
+    auto publish = [&](float (&v)[32], const float* bias) {
+        const uint32_t a2 = trow + kPColA2 + g * kA2Cols;
+        const float4* b4 = reinterpret_cast<const float4*>(bias);
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 b = b4[q];
+            split2(fmaxf(v[4 * q] + b.x, 0.0f), fmaxf(v[4 * q + 1] + b.y, 0.0f), hi[2 * q], lo[2 * q]);
+            split2(fmaxf(v[4 * q + 2] + b.z, 0.0f), fmaxf(v[4 * q + 3] + b.w, 0.0f), hi[2 * q + 1], lo[2 * q + 1]);
+        }
+        if (pubs >= 1) {  // the group's previous item has been consumed
+            mbar_wait_p<kProf>(bars + 8 * (PB_A2_EMPTY + g), (pubs - 1) & 1, pw[PW_A2_EMPTY]);
+            tc_fence_after();
+        }
+        tmem_st16(a2, hi);
+        tmem_st16(a2 + 16, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bars + 8 * (PB_A2_FULL + g));
+        ++pubs;
+    };
+    for (int t = t0; t < t1; ++t, ++u) {
+        if (blob_changed(prm, t, t0)) {
+            mbar_wait_p<kProf>(bars + 8 * PB_HEAD_FULL, head_gen & 1, pw[PW_HEAD_FULL]);
+            ++head_gen;
+        }
+        for (int j = g; j < npos; j += 2, ++d1_uses) {  // positions of parity g sit in accumulator stage g
+            mbar_wait_p<kProf>(bars + 8 * (PBS_D1_FULL + g), d1_uses & 1, pw[PW_D1_FULL]);
+            tc_fence_after();
+            float v[32];
+            tmem_ld32(trow + kPColD1 + g * kCo, v);
+            tc_fence_before();
+            mbar_arrive(bars + 8 * (PBS_D1_EMPTY + g));
+            publish(v, s_bias1 + j * kCo);
+        }
+        mbar_wait_p<kProf>(bars + 8 * PB_D2_FULL, u & 1, pw[PW_D2_FULL]);
+        tc_fence_after();
+        {
+            float v[32];
+            tmem_ld32(trow + kPColD2 + g * 32, v);
+            publish(v, s_b1 + g * 32);
+        }
+        if (g != kSHeadGroup) {
+            mbar_arrive(bars + 8 * (PB_HEAD_EMPTY + (u & 1)));  // this group is done with the tile's biases
+            continue;
+        }
+        const uint32_t drawn = net == 0 ? out.draw(t, trow_id) : 0u;
+        mbar_wait_p<kProf>(bars + 8 * PB_D3_FULL, u & 1, pw[PW_D3_FULL]);
+        tc_fence_after();
+        float head[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) head[a] = s_bh[a];
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tmem_ld32(trow + kSColD3 + half * 32, v);
+            if (half == 1) {
+                tc_fence_before();
+                mbar_arrive(bars + 8 * PB_D3_EMPTY);
+            }
+            head_accumulate(net, v, s_b2 + half * 32, s_wh, half * 32, head);
+        }
+        mbar_arrive(bars + 8 * (PB_HEAD_EMPTY + (u & 1)));
+        out(t, trow_id, net, head, drawn);
+    }
+}
+
 // output stage of the plain forward: rows are tile-major
 struct PairForwardOut {
     const PolicyParams& prm;
@@ -1255,7 +1405,7 @@ __global__ void __launch_bounds__(kPThreads, 1) policy_pair_kernel(const PolicyP
                 (i >= PB_D3_EMPTY && i < PB_D3_EMPTY + 2))
                 count = 128;
             if (i >= PB_COL_EMPTY && i < PB_COL_EMPTY + 4) count = 2;  // both conv issuers are done with the column
-            if (i >= PB_HEAD_EMPTY && i < PB_HEAD_EMPTY + 2) count = (prm.single ? 128 : 32 * kEpiWarps) + 2;
+            if (i >= PB_HEAD_EMPTY && i < PB_HEAD_EMPTY + 2) count = 32 * kEpiWarps + 2;
             if (i >= PB_D1_EMPTY && i < PB_D1_EMPTY + 2) count = 32 * kEpiWarps;
             if (i >= PBS_D1_EMPTY && i < PBS_D1_EMPTY + 4) count = 128;  // single mode runs the split-mode stream of "network 0"
             mbar_init(bars + 8 * i, count);
@@ -1274,19 +1424,17 @@ __global__ void __launch_bounds__(kPThreads, 1) policy_pair_kernel(const PolicyP
 
     long long pw[kProf ? PW_COUNT : 1] = {};
     const long long t_begin = kProf ? clock64() : 0;
-    if (prm.single) {
-        // ONE network per tile (ocb_policy_act / _value, cross-play evaluation): the split-mode stream of "network 0" — N = 32
-        // conv from two issuers, one FC issuer, epilogue group 0; warps 4-7 and the second FC issuer have nothing to do
-        if (warp < 4) {
-            pair_epilogue_role<kProf, true>(pw, prm, ur.t0, ur.t1, L, tmem, s_head, bars, PairForwardOut(prm));
-        } else if (warp >= kEpiWarps && warp < kWarpMma) {
+    if (prm.single) {  // ONE network per tile (see single_epilogue_role)
+        if (warp < kEpiWarps) {
+            single_epilogue_role<kProf>(pw, prm, ur.t0, ur.t1, L, tmem, s_head, bars, PairForwardOut(prm));
+        } else if (warp < kWarpMma) {
             loader_role<kProf>(pw, prm, ur, tmem, s_stage, bars);
         } else if (warp == kWarpMma || warp == kWarpConv2) {
             pair_conv_role<kProf, 0>(pw, prm, ur.t0, ur.t1, L, tmem, smem_addr(s_head), bars, warp == kWarpMma ? 0 : 1, 2);
         } else if (warp == kPWarpProd) {
             pair_producer_role<kProf>(pw, prm, ur.t0, ur.t1, L, smem_addr(s_head), smem_addr(s_wring), bars);
         } else if (warp == kWarpFc) {
-            pair_fc_role<kProf, true>(pw, prm, 0, ur.t0, ur.t1, L, tmem, smem_addr(s_wring), bars);
+            single_fc_role<kProf>(pw, prm, ur.t0, ur.t1, L, tmem, smem_addr(s_wring), bars);
         }
     } else if (warp < kEpiWarps) {
         pair_epilogue_role<kProf, false>(pw, prm, ur.t0, ur.t1, L, tmem, s_head, bars, PairForwardOut(prm));
@@ -1299,8 +1447,9 @@ __global__ void __launch_bounds__(kPThreads, 1) policy_pair_kernel(const PolicyP
     } else {
         pair_fc_role<kProf, false>(pw, prm, warp - kWarpFc, ur.t0, ur.t1, L, tmem, smem_addr(s_wring), bars);
     }
-    if (kProf && prm.prof != nullptr &&
-        (tid == 0 || tid == 32 * kEpiWarps || tid == 32 * kWarpMma || tid == 32 * kPWarpProd)) {
+    // single mode reports its FC issuer in the producer's slot (the producer idles once the weights are resident)
+    const int tid_r3 = prm.single ? 32 * kWarpFc : 32 * kPWarpProd;
+    if (kProf && prm.prof != nullptr && (tid == 0 || tid == 32 * kEpiWarps || tid == 32 * kWarpMma || tid == tid_r3)) {
         pw[PW_TOTAL] = clock64() - t_begin;
         const int role = tid == 0 ? 0 : tid == 32 * kEpiWarps ? 1 : tid == 32 * kWarpMma ? 2 : 3;
         for (int i = 0; i < PW_COUNT; ++i) prm.prof[((size_t)blockIdx.x * 4 + role) * PW_COUNT + i] = pw[i];
@@ -1864,7 +2013,11 @@ extern "C" int ocb_policy_debug_profile(ocb_policy* p, const int8_t* obs, int M,
     if (err == cudaSuccess) err = cudaMemset(d_prof, 0, n * sizeof(long long));
     int ctas = 0;
     int rc = OCB_OK;
-    if (err == cudaSuccess) rc = policy_launch(p, 3, obs, M, tile_policy, nullptr, actions, nullptr, values, 1, 0, 0, nullptr, nullptr, d_prof, &ctas);
+    int mask = 3;  // OCB_PROFILE_MASK=1 / 2: the single-network mode (actor / critic)
+    if (const char* e = getenv("OCB_PROFILE_MASK")) mask = (e[0] == '1') ? 1 : (e[0] == '2') ? 2 : 3;
+    if (err == cudaSuccess)
+        rc = policy_launch(p, mask, obs, M, tile_policy, nullptr, mask == 2 ? nullptr : actions, nullptr, mask == 1 ? nullptr : values, 1, 0, 0,
+                           nullptr, nullptr, d_prof, &ctas);
     if (err == cudaSuccess && rc == OCB_OK) err = cudaMemcpy(h_prof, d_prof, n * sizeof(long long), cudaMemcpyDeviceToHost);
     cudaFree(d_prof);
     if (rc != OCB_OK) return rc;

@@ -193,7 +193,7 @@ __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s
         int32_t* done_ptr = fp.done ? fp.done + n : nullptr;
 
         World<P> w;
-        load_world<P, 1>(tb, c, fp.env, nl, 0, myobjs, w);
+        load_world<P, 1, 8>(tb, c, fp.env, nl, 0, myobjs, w);
         int cur_return = fp.env.cur_return[nl];
         long long ret_add = 0;
         int ep_add = 0;

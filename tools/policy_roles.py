@@ -15,7 +15,7 @@ from diverse_conventions_b200.overcooked_env import B200Overcooked  # noqa: E402
 from diverse_conventions_b200.policy import FusedPolicy, PolicyNet  # noqa: E402
 
 NAMES = ["total", "col_empty", "head_full", "col_full", "a2_full", "w_full", "d1_full", "d2_full", "a2_empty", "d3_full",
-         "head_empty", "w_empty", "issue_conv", "issue_fc", "ldg+stage"]
+         "head_empty", "w_empty", "issue_conv", "issue_fc", "ldg+stage", "cvt+tmem_st"]
 NWAIT = 12  # entries [1, NWAIT) are barrier stalls; the rest are sub-intervals of the busy time
 ROLES = ["epilogue", "loader", "mma", "producer"]
 
