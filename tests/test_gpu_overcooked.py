@@ -100,6 +100,33 @@ def test_random_rollout_matches_oracle(name, N, horizon, G, tma):
     assert np.array_equal(env.get_state(), orc.state)
 
 
+@pytest.mark.parametrize("name,N,lanes", [("simple", 4100, 0), ("random1", 4133, 0), ("unident_s", 4096, 0), ("simple_single", 4099, 0),
+                                          ("random3", 300, 1), ("random0", 77, 2), ("multiplayer_schelling", 130, 4)])
+def test_single_steps_match_oracle_across_episode_ends(name, N, lanes):
+    """ONE env step per launch (n_step): from 4,096 worlds on the library serves a world with two lanes; the planes of a warp
+    tile are rebuilt by one bulk copy of the template tile per view and only counters / pots are moved between HBM and shared
+    memory.  Ragged world counts, an episode end inside the run (auto-reset + post-reset observation), every lane count."""
+    horizon = 4
+    lp = layouts.load_layout(name, horizon)
+    env = make_env(name, N, horizon)
+    if lanes:
+        env.set_tuning(lanes, True)
+    P = lp.num_players
+    orc = COracle(lp, N)
+    rng = np.random.default_rng(3)
+    o0 = stack_obs(env.n_reset())
+    assert np.array_equal(o0, orc.observe())
+    for t in range(11):
+        a = rng.integers(0, 6, size=(P, N))
+        vobs, rew, done, _ = env.n_step(torch.from_numpy(a).reshape(P, N, 1))
+        o, r, d = orc.step(a)
+        assert np.array_equal(rew.cpu().numpy().astype(np.int64), r.astype(np.int64)), t
+        assert np.array_equal(done.cpu().numpy().astype(np.int64), d.astype(np.int64)), t
+        assert np.array_equal(stack_obs(vobs), o), t
+        assert bool(d[0]) == ((t + 1) % horizon == 0)
+    assert np.array_equal(env.get_state(), orc.state)
+
+
 def test_scripted_teams_all_branches_many_worlds():
     """scripted cooks (+noise) on every classic layout: every reward branch, N worlds diverging"""
     from test_kernel_logic_emulated import scripted_actions

@@ -89,6 +89,45 @@ def test_ragged_rows_many_policies_and_tile_selection():
     assert rel_err(val.cpu(), ref_v) < REL_TOL
 
 
+@pytest.mark.parametrize("layout", ["simple", "random1", "unident_s"])
+def test_single_network_mode_equals_the_pair_kernel_and_the_unit_kernel(monkeypatch, layout):
+    """ocb_policy_act / ocb_policy_value run the pair kernel's one-network mode (both epilogue groups on one stream): every
+    output element sums the same products in the same order as the two-network forward, so logits and values are
+    BIT-identical to ocb_policy_forward; policy_fwd_kernel (OCB_POLICY_SINGLE=0, the (tile, network)-unit kernel) splits the
+    head sum over two groups and agrees to rounding.  Several weight sets per launch (tile_policy), ragged row count."""
+    lp = layouts.load_layout(layout, 400)
+    n_pol, N = 3, 900
+    nets = [(PolicyNet("actor", lp.width, lp.height, lp.channels, 64).init_like_reference(3 + i, gain=1.0),
+             PolicyNet("critic", lp.width, lp.height, lp.channels, 64).init_like_reference(40 + i)) for i in range(n_pol)]
+    orc, rng = COracle(lp, N), np.random.default_rng(5)
+    for _ in range(60):
+        o, _, _ = orc.step(rng.choice(6, size=(2, N), p=[.15, .15, .15, .15, .05, .35]))
+    M = 2 * N - 61
+    obs = torch.from_numpy(o.reshape(2 * N, lp.width, lp.height, lp.channels)[:M].copy()).cuda()
+    tiles = (M + 127) // 128
+    tile_policy = torch.tensor([(2 * t + 1) % n_pol for t in range(tiles)], dtype=torch.int32, device="cuda")
+
+    def run():
+        pol = FusedPolicy(lp, 64, n_pol)
+        for i, (a, c) in enumerate(nets):
+            pol.set_weights(i, a, c)
+        act = pol.act(obs, tile_policy=tile_policy, seed=9, offset=4, want_logits=True)
+        val = pol.value(obs, tile_policy=tile_policy)
+        both = pol.forward(obs, tile_policy=tile_policy, seed=9, offset=4, want_logits=True)
+        torch.cuda.synchronize()
+        res = {k: v.cpu().clone() for k, v in act.items()}, val.cpu().clone(), {k: v.cpu().clone() for k, v in both.items()}
+        pol.close()
+        return res
+
+    act, val, both = run()
+    assert torch.equal(act["logits"], both["logits"]) and torch.equal(val, both["values"])
+    assert torch.equal(act["actions"], both["actions"]) and torch.equal(act["logp"], both["logp"])
+    monkeypatch.setenv("OCB_POLICY_SINGLE", "0")
+    act0, val0, _ = run()
+    assert rel_err(act0["logits"], act["logits"]) < 1e-6 and rel_err(val0, val) < 1e-6
+    assert float((act0["actions"] != act["actions"]).float().mean()) < 1e-3  # a draw on a boundary may flip
+
+
 def test_sampling_follows_the_softmax_and_is_reproducible():
     lp = layouts.load_layout("simple", 400)
     pol = FusedPolicy(lp, 64, 1)
