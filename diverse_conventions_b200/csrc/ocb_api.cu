@@ -602,8 +602,31 @@ extern "C" int ocb_rollout_policy_fused(ocb_env* e, ocb_policy* pol, int T, int 
     if (e->P != 2) return fail(OCB_ERR_UNSUPPORTED, "the policy rollout supports 2 players");
     DeviceGuard guard(e->device);
     RolloutParams p = base_params(e);
-    const int rc = ocb_policy_rollout_fused_launch(pol, policy_index, p, e->h_tables.W, e->h_tables.H, T, obs_slab, actions, logp,
+    const int rc = ocb_policy_rollout_fused_launch(pol, policy_index, nullptr, p, e->h_tables.W, e->h_tables.H, T, obs_slab, actions, logp,
                                                    values, reward, done, deterministic, seed,
+                                                   reinterpret_cast<const uint64_t*>(e->d_step_counter),
+                                                   reinterpret_cast<uint64_t*>(e->d_step_counter), stream);
+    if (rc != OCB_OK) return rc;
+    if (stream_capturing(stream))
+        e->count_stale = true;
+    else
+        e->step_count += (uint64_t)T;
+    return OCB_OK;
+}
+
+// Cross-play in one persistent launch: the rollout of ocb_rollout_policy(values = NULL) with a tile_policy table — seat-0 rows
+// act with the actor of tile_policy[seat-0 tile], seat-1 rows with that of tile_policy[seat-1 tile] — bit-identical actions
+// (same sampling counters).  Evaluation keeps no trajectory: every buffer is optional; the env's episode statistics
+// (ocb_episode_stats) carry the result.
+extern "C" int ocb_rollout_crossplay_fused(ocb_env* e, ocb_policy* pol, int T, const int32_t* tile_policy, int8_t* obs_slab,
+                                           int32_t* actions, float* logp, int32_t* reward, int32_t* done, int deterministic,
+                                           uint64_t seed, void* stream) {
+    if (e == nullptr || pol == nullptr || tile_policy == nullptr) return fail(OCB_ERR_INVALID_ARG, "NULL handle / tile_policy");
+    if (e->P != 2) return fail(OCB_ERR_UNSUPPORTED, "the policy rollout supports 2 players");
+    DeviceGuard guard(e->device);
+    RolloutParams p = base_params(e);
+    const int rc = ocb_policy_rollout_fused_launch(pol, 0, tile_policy, p, e->h_tables.W, e->h_tables.H, T, obs_slab, actions, logp,
+                                                   nullptr, reward, done, deterministic, seed,
                                                    reinterpret_cast<const uint64_t*>(e->d_step_counter),
                                                    reinterpret_cast<uint64_t*>(e->d_step_counter), stream);
     if (rc != OCB_OK) return rc;
@@ -632,7 +655,7 @@ extern "C" int ocb_rollout_fused_debug_trace(ocb_env* e, ocb_policy* pol, int T,
         return fail(OCB_ERR_CUDA, "ocb_rollout_fused_debug_trace: %s", cudaGetErrorString(err));
     }
     RolloutParams p = base_params(e);
-    const int rc = ocb_policy_rollout_fused_launch(pol, policy_index, p, e->h_tables.W, e->h_tables.H, T, obs_slab, actions, logp,
+    const int rc = ocb_policy_rollout_fused_launch(pol, policy_index, nullptr, p, e->h_tables.W, e->h_tables.H, T, obs_slab, actions, logp,
                                                    values, reward, done, 0, seed,
                                                    reinterpret_cast<const uint64_t*>(e->d_step_counter),
                                                    reinterpret_cast<uint64_t*>(e->d_step_counter), nullptr, d_trace, u0, n_steps);

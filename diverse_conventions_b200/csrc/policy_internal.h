@@ -5,12 +5,13 @@
 #include "oc_kernels.h"
 #include "ocb.h"
 
-// T-step self-play rollout of one policy in ONE persistent launch (rollout_fused.cuh): `envp`
-// carries the env's tables and state arrays.  Returns OCB_ERR_UNSUPPORTED (with the reason in
+// T-step rollout in ONE persistent launch (rollout_fused.cuh): `envp` carries the env's tables and state arrays.
+// tile_policy == nullptr: self-play of weight set `policy_index` (actor + critic); else cross-play with the per-step path's
+// seat-major tile table (actors only, every output buffer optional).  Returns OCB_ERR_UNSUPPORTED (with the reason in
 // ocb_last_error) when the layout / handle cannot run fused.
-int ocb_policy_rollout_fused_launch(ocb_policy* pol, int policy_index, const ocb::RolloutParams& envp, int env_w, int env_h, int T,
-                                    int8_t* obs_slab, int32_t* actions, float* logp, float* values, int32_t* reward,
-                                    int32_t* done, int deterministic, uint64_t seed, const uint64_t* d_offset,
+int ocb_policy_rollout_fused_launch(ocb_policy* pol, int policy_index, const int32_t* tile_policy, const ocb::RolloutParams& envp,
+                                    int env_w, int env_h, int T, int8_t* obs_slab, int32_t* actions, float* logp, float* values,
+                                    int32_t* reward, int32_t* done, int deterministic, uint64_t seed, const uint64_t* d_offset,
                                     uint64_t* d_counter, void* stream, long long* d_trace = nullptr, int trace_u0 = 0,
                                     int trace_n = 0);
 

@@ -132,6 +132,10 @@ struct PolicyParams {
     long long* trace;         // diagnostic build of the fused rollout: [trace_n steps][kTraceEvents] clock64 stamps of CTA 0
     int trace_u0, trace_n;    // first traced virtual tile (step) and number of traced steps
     int single;               // policy_pair_kernel: 0 = both networks of a tile, 1 = the actor only, 2 = the critic only (one stream)
+    // fused rollout (rollout_fused.cuh): a CTA's virtual tiles come in rounds of f_vt_round = slots * (T + 1); with
+    // tile_policy set (cross-play) the round's world tiles 2 c, 2 c + 1 play seat 0 / seat 1 with the actors of
+    // tile_policy[kt / 2] / tile_policy[f_seat1_tiles + kt / 2] (the per-step path's seat-major 128-row tile table)
+    int f_vt_round, f_slots, f_seat1_tiles;
 };
 
 // shared-memory carve-up (byte offsets from a 128-byte aligned base)
@@ -329,10 +333,21 @@ __device__ __forceinline__ UnitRange my_units(const PolicyParams& prm) {
     u.t1 = (int)(((long long)(c + 1) * prm.tiles) / g);
     return u;
 }
-__device__ __forceinline__ int tile_pol(const PolicyParams& prm, int t) { return prm.tile_policy ? prm.tile_policy[t] : 0; }
+// fused cross-play rollout: (seat-0 policy | seat-1 policy << 16) of the round virtual tile t belongs to
+__device__ __forceinline__ uint32_t fused_pair(const PolicyParams& prm, int t) {
+    const int kt0 = prm.f_slots * ((int)blockIdx.x + (t / prm.f_vt_round) * (int)gridDim.x);
+    return (uint32_t)prm.tile_policy[kt0 >> 1] | ((uint32_t)prm.tile_policy[prm.f_seat1_tiles + (kt0 >> 1)] << 16);
+}
+__device__ __forceinline__ int tile_pol(const PolicyParams& prm, int t) {
+    if (prm.tile_policy == nullptr) return 0;
+    return prm.f_vt_round ? (int)fused_pair(prm, t) : prm.tile_policy[t];
+}
 // does tile t need another weight set than the previous tile of this CTA
 __device__ __forceinline__ bool blob_changed(const PolicyParams& prm, int t, int t0) {
-    return t == t0 || (prm.tile_policy != nullptr && prm.tile_policy[t] != prm.tile_policy[t - 1]);
+    if (t == t0) return true;
+    if (prm.tile_policy == nullptr) return false;
+    if (prm.f_vt_round) return (t % prm.f_vt_round) == 0 && fused_pair(prm, t) != fused_pair(prm, t - 1);
+    return prm.tile_policy[t] != prm.tile_policy[t - 1];
 }
 
 // ---------------------------------------------------------------- roles
@@ -902,8 +917,10 @@ __device__ __forceinline__ void pair_producer_role(long long* pw, const PolicyPa
     for (int t = t0; t < t1; ++t, ++u) {
         if (static_w && u > 0) break;
         const bool chg = blob_changed(prm, t, t0);
-        const uint8_t* blob_a = prm.blobs + ((size_t)tile_pol(prm, t) * 2 + (prm.single == 2 ? 1 : 0)) * prm.blob_stride;
-        const uint8_t* blob_c = blob_a + prm.blob_stride;
+        const int tp = tile_pol(prm, t);
+        const bool cross = prm.f_vt_round != 0 && prm.tile_policy != nullptr;  // both streams are actors (of two policies)
+        const uint8_t* blob_a = prm.blobs + ((size_t)(cross ? (tp & 0xFFFF) : tp) * 2 + (prm.single == 2 ? 1 : 0)) * prm.blob_stride;
+        const uint8_t* blob_c = cross ? prm.blobs + (size_t)(tp >> 16) * 2 * prm.blob_stride : blob_a + prm.blob_stride;
         if (chg) {
             if (u > 0) mbar_wait_p<kProf>(bars + 8 * (PB_HEAD_EMPTY + ((u - 1) & 1)), ((u - 1) >> 1) & 1, pw[PW_HEAD_EMPTY]);
             if (elect_one()) {
@@ -1125,7 +1142,8 @@ __device__ __forceinline__ void pair_epilogue_role(long long* pw, const PolicyPa
     const float* s_wh = reinterpret_cast<const float*>(rest + L.wh);
     const float* s_bh = reinterpret_cast<const float*>(rest + L.bh);
     const uint32_t a2 = trow + kPColA2 + g * kA2Cols;
-    const int net = prm.single == 2 ? 1 : g;  // head layout / outputs: 0 = actor (6 logits), 1 = critic (value)
+    // head layout / outputs: 0 = actor (6 logits), 1 = critic (value); fused cross-play: two actors
+    const int net = (prm.f_vt_round != 0 && prm.tile_policy != nullptr) ? 0 : (prm.single == 2 ? 1 : g);
 
     uint32_t u = 0, head_gen = 0, item = 0, d1_par = 0;  // d1_par: phase parity bit per conv accumulator stage
     int trace_vt = 0, trace_item = 0;
@@ -1221,8 +1239,9 @@ constexpr int kSColD3 = kPColD2 + kHid;
 constexpr int kSHeadGroup = 1;
 // Measured and dropped (524,288 rows of coordination_ring, 206 us): a second A-operand stage per group in the conv
 // accumulator columns of the absent second network (218 us), a nanosleep back-off in the loaders' ring-slot wait (209 us:
-// try_wait polls are 14 % of the issued instructions, but not what the working warps wait for).  ncu: 47.7 k warp
-// instructions per tile at ~79 % issue utilisation — the kernel is bound by instruction issue (loads, conversions, splits).
+// try_wait polls are a third of the issued instructions, but not what the working warps wait for), suspend-time hints on
+// every wait of this mode (211 us).  ncu: 47.7 k warp instructions per tile; the roles wait on each other in turn (role
+// profile, tools/policy_roles.py with OCB_PROFILE_MASK=1): loaders 60 % busy, conv issuers 60 %, epilogue groups 40 %.
 
 template <bool kProf>
 __device__ __forceinline__ void single_fc_role(long long* pw, const PolicyParams& prm, int t0, int t1, const BlobLayout L, uint32_t tmem,
@@ -1638,10 +1657,12 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
     if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(policy_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<false, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(conv512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(gemm512_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(gemm512_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
@@ -2028,19 +2049,37 @@ extern "C" int ocb_policy_debug_profile(ocb_policy* p, const int8_t* obs, int M,
     return ctas;
 }
 
-// ---------------------------------------------------------------- fused self-play rollout (rollout_fused.cuh)
-int ocb_policy_rollout_fused_launch(ocb_policy* p, int policy_index, const RolloutParams& envp, int env_w, int env_h, int T,
-                                    int8_t* obs_slab, int32_t* actions, float* logp, float* values, int32_t* reward,
+// ---------------------------------------------------------------- fused rollout (rollout_fused.cuh)
+// tile_policy == nullptr: self-play of weight set `policy_index` with its critic (obs_slab, actions and values required).
+// tile_policy != nullptr: cross-play, the per-step path's seat-major table (int32 [2 N / 128], device); actors only, every
+// output buffer optional.
+int ocb_policy_rollout_fused_launch(ocb_policy* p, int policy_index, const int32_t* tile_policy, const RolloutParams& envp, int env_w,
+                                    int env_h, int T, int8_t* obs_slab, int32_t* actions, float* logp, float* values, int32_t* reward,
                                     int32_t* done, int deterministic, uint64_t seed, const uint64_t* d_offset,
                                     uint64_t* d_counter, void* stream, long long* d_trace, int trace_u0, int trace_n) {
     if (p == nullptr) return fail(OCB_ERR_INVALID_ARG, "policy is NULL");
     if (p->generic) return fail(OCB_ERR_UNSUPPORTED, "the fused rollout kernel needs the tensor-core policy path (2 players, grids up to %d rows)", kMaxH);
     if (p->hidden != kHid) return fail(OCB_ERR_UNSUPPORTED, "the fused rollout kernel exists for hidden_size 64 only");
-    if (policy_index < 0 || policy_index >= p->n_policies) return fail(OCB_ERR_INVALID_ARG, "policy index out of range");
+    const bool cross = tile_policy != nullptr;
+    if (!cross && (policy_index < 0 || policy_index >= p->n_policies)) return fail(OCB_ERR_INVALID_ARG, "policy index out of range");
     if (env_w != p->W || env_h != p->H) return fail(OCB_ERR_INVALID_ARG, "env and policy were built for different layouts");
-    if (T < 1 || obs_slab == nullptr || actions == nullptr || values == nullptr)
-        return fail(OCB_ERR_INVALID_ARG, "T >= 1, obs_slab, actions and values are required");
-    const int fixed = fused_smem_layout(p->npos, 0, p->S, p->SC).total;
+    if (T < 1) return fail(OCB_ERR_INVALID_ARG, "T must be >= 1");
+    if (!cross && (obs_slab == nullptr || actions == nullptr || values == nullptr))
+        return fail(OCB_ERR_INVALID_ARG, "obs_slab, actions and values are required");
+    if (cross && (envp.N % kRows) != 0)
+        return fail(OCB_ERR_INVALID_ARG, "cross-play needs a multiple of %d worlds (one weight set per 128-row tile of a seat), got %d", kRows, envp.N);
+    if (cross && values != nullptr) return fail(OCB_ERR_INVALID_ARG, "the cross-play rollout runs no critic: values must be NULL");
+    const int wtiles = (envp.N + kFWorlds - 1) / kFWorlds;
+    // two tiles in flight when there are more tiles than SMs and the second tile's planes leave a usable weight ring
+    int slots = 1;
+    {
+        const int fixed2 = fused_smem_layout(p->npos, 0, p->S, p->SC, 2).total;
+        const bool fits2 = fixed2 <= kSmemBudget && (kSmemBudget - fixed2) / kChunk >= 4;
+        const char* e = getenv("OCB_FUSED_SLOTS");
+        const bool want2 = e != nullptr ? (e[0] == '2') : (wtiles > p->sm_count);
+        if (want2 && fits2) slots = 2;
+    }
+    const int fixed = fused_smem_layout(p->npos, 0, p->S, p->SC, slots).total;
     int ring = (kSmemBudget - fixed) / kChunk;
     if (ring > kPMaxRing) ring = kPMaxRing;
     if (ring > 2 * p->L.chunks) ring = 2 * p->L.chunks;
@@ -2049,41 +2088,53 @@ int ocb_policy_rollout_fused_launch(ocb_policy* p, int policy_index, const Rollo
     DeviceGuard guard(p->device);
     FusedParams fp;
     memset(&fp, 0, sizeof(fp));
-    fp.pol.blobs = p->d_blobs + (size_t)policy_index * 2 * (size_t)p->L.total, fp.pol.blob_stride = (size_t)p->L.total;
+    fp.pol.blobs = cross ? p->d_blobs : p->d_blobs + (size_t)policy_index * 2 * (size_t)p->L.total;
+    fp.pol.blob_stride = (size_t)p->L.total;
     fp.pol.W = p->W, fp.pol.H = p->H, fp.pol.S = p->S, fp.pol.SC = p->SC, fp.pol.npos = p->npos;
     fp.pol.M = kRows, fp.pol.tiles = 1;
     fp.pol.deterministic = deterministic, fp.pol.seed = seed, fp.pol.offset = 0;
     fp.pol.rng_rows_per_seat = p->rng_rows_per_seat, fp.pol.rng_add0 = p->rng_add0, fp.pol.rng_add1 = p->rng_add1;
     fp.pol.d_offset = reinterpret_cast<const unsigned long long*>(d_offset);
     fp.pol.net_mask = 3, fp.pol.pair_ring = ring, fp.pol.stage_stride = p->stage_stride;
+    fp.pol.tile_policy = tile_policy, fp.pol.f_vt_round = slots * (T + 1), fp.pol.f_slots = slots, fp.pol.f_seat1_tiles = envp.N / kRows;
     fp.env = envp;
-    fp.T = T, fp.wtiles = (envp.N + kFWorlds - 1) / kFWorlds;
+    fp.T = T, fp.wtiles = wtiles, fp.slots = slots, fp.cross = cross ? 1 : 0;
     fp.obs_slab = obs_slab, fp.actions = actions, fp.logp = logp, fp.values = values, fp.reward = reward, fp.done = done;
-    const int ctas = fp.wtiles < p->sm_count ? fp.wtiles : p->sm_count;
-    const size_t smem = (size_t)fused_smem_layout(p->npos, ring, p->S, p->SC).total;
+    const int groups = (wtiles + slots - 1) / slots;
+    const int ctas = groups < p->sm_count ? groups : p->sm_count;
+    const size_t smem = (size_t)fused_smem_layout(p->npos, ring, p->S, p->SC, slots).total;
     fp.pol.trace = d_trace, fp.pol.trace_u0 = trace_u0, fp.pol.trace_n = trace_n;
     {   // 16-byte plane reads pay when the rows are 16-byte aligned (cramped_room, counter_circuit); OCB_FUSED_VEC_LOADER overrides
         const char* e = getenv("OCB_FUSED_VEC_LOADER");
         fp.vec_loader = e != nullptr ? (e[0] != '0') : (p->SC % 16 == 0);
     }
-    {   // split mode (the critic's conv stream deferred behind the actor's FC2): needs every grid column of a tile resident
-        const int slots = 192 / (kCellCols * p->H);
+    {   // split mode (the critic's conv stream deferred behind the actor's): needs every grid column of a tile resident, one
+        // tile in flight and a critic
+        const int cols = 192 / (kCellCols * p->H);
         const char* e = getenv("OCB_FUSED_SPLIT");
         const bool want = e != nullptr ? (e[0] != '0') : true;
-        fp.col_ring = (want && slots >= p->W) ? (p->W < kFMaxColRing ? p->W : kFMaxColRing) : 0;
+        fp.col_ring = (want && slots == 1 && !cross && cols >= p->W) ? (p->W < kFMaxColRing ? p->W : kFMaxColRing) : 0;
         if (fp.col_ring < p->W) fp.col_ring = 0;
     }
+    const cudaStream_t st = (cudaStream_t)stream;
     if (fp.col_ring > 0) {
         if (d_trace != nullptr)
-            rollout_fused_kernel<true, true><<<ctas, kFThreads, smem, (cudaStream_t)stream>>>(fp);
+            rollout_fused_kernel<true, true, 1><<<ctas, kFThreads, smem, st>>>(fp);
         else
-            rollout_fused_kernel<false, true><<<ctas, kFThreads, smem, (cudaStream_t)stream>>>(fp);
+            rollout_fused_kernel<false, true, 1><<<ctas, kFThreads, smem, st>>>(fp);
     } else {
         fp.col_ring = kColRing;
-        if (d_trace != nullptr)
-            rollout_fused_kernel<true, false><<<ctas, kFThreads, smem, (cudaStream_t)stream>>>(fp);
-        else
-            rollout_fused_kernel<false, false><<<ctas, kFThreads, smem, (cudaStream_t)stream>>>(fp);
+        if (slots == 2) {
+            if (d_trace != nullptr)
+                rollout_fused_kernel<true, false, 2><<<ctas, kFThreads, smem, st>>>(fp);
+            else
+                rollout_fused_kernel<false, false, 2><<<ctas, kFThreads, smem, st>>>(fp);
+        } else {
+            if (d_trace != nullptr)
+                rollout_fused_kernel<true, false, 1><<<ctas, kFThreads, smem, st>>>(fp);
+            else
+                rollout_fused_kernel<false, false, 1><<<ctas, kFThreads, smem, st>>>(fp);
+        }
     }
     if (d_counter != nullptr)
         counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(d_counter), (unsigned long long)T);

@@ -24,14 +24,25 @@ struct FusedParams {
     RolloutParams env;   // tables, template, world state arrays, N, use_tma
     int T;
     int wtiles;          // ceil(N / 64) world tiles
-    int8_t* obs_slab;    // [T+1][2][N][SC]
-    int32_t* actions;    // [T][2][N]
+    int8_t* obs_slab;    // [T+1][2][N][SC] or nullptr (evaluation rollouts keep no trajectory)
+    int32_t* actions;    // [T][2][N] or nullptr
     float* logp;         // [T][2][N] or nullptr
-    float* values;       // [T+1][2][N]
+    float* values;       // [T+1][2][N] or nullptr (cross-play: no critic)
     int32_t* reward;     // [T][2][N] or nullptr
     int32_t* done;       // [T][N] or nullptr
     int vec_loader;      // loaders read the planes as 16-byte vectors (conflict-free) instead of 4-byte words
     int col_ring;        // grid columns resident in the cell region: W in split mode (whole grid), else kColRing
+    // Two world tiles in flight (slots = 2): the CTA owns tiles (2c, 2c + 1), (2c + 2 gridDim, ...) and the policy pipeline
+    // runs over the interleaved stream (A, u), (B, u), (A, u + 1), (B, u + 1), ... — every role works on tile B while tile A's
+    // env step runs and vice versa.  One env step of one tile is a dependent chain of ~20 k cycles in which each role is busy
+    // a third of the time; a second tile fills the other two thirds.  No extra tensor memory: the stream reuses every TMEM
+    // region in order exactly as consecutive steps of one tile do; it costs the second tile's planes in shared memory (the FC
+    // weights then stream through a smaller ring) and only pays when there are more tiles than SMs.
+    int slots;
+    // Cross-play (pol.tile_policy set, xd_player.py:190-207 / partner_agents.py:97-111): seat-0 rows act with the actor of
+    // policy tile_policy[seat-0 tile], seat-1 rows with the actor of tile_policy[seat-1 tile]; both actors run over all 128
+    // rows of the tile as the pipeline's "two networks" and each epilogue group emits the rows of its seat.  No critic.
+    int cross;
 };
 
 constexpr int kFEnvWarps = 2;
@@ -41,36 +52,61 @@ constexpr int kFThreads = 32 * (kFWarpEnv + kFEnvWarps);    // 768
 constexpr int kFWorlds = 32 * kFEnvWarps;                   // worlds per CTA tile
 constexpr int kFMaxColRing = 6;  // 192 cell columns / (8 columns x H = 4)
 enum : int {
-    FB_OBS_FULL = PB_COUNT,      // env warps (64 arrivals) -> loaders: planes of virtual tile vt are complete
-    FB_OBS_EMPTY = PB_COUNT + 1, // loaders (256 arrivals) -> env warps: planes of vt have been consumed
-    FB_ACT_FULL = PB_COUNT + 2,  // actor epilogue group (128 arrivals) -> env warps
-    FB_COL_FULL = PB_COUNT + 3,  // [6] split mode: loader -> both conv issuers (128 arrivals)
+    FB_OBS_FULL = PB_COUNT,      // [2 slots] env warps (64 arrivals) -> loaders: planes of the slot's next virtual tile are complete
+    FB_OBS_EMPTY = PB_COUNT + 2, // [2] loaders (256 arrivals) -> env warps: the slot's planes have been consumed
+    FB_ACT_FULL = PB_COUNT + 4,  // [2] the epilogue threads that sample the tile's 128 actions (128 arrivals) -> env warps
+    FB_COL_FULL = PB_COUNT + 6,  // [6] split mode: loader -> both conv issuers (128 arrivals)
     FB_COL_EMPTY = FB_COL_FULL + kFMaxColRing,  // [6] split mode: both conv issuers' commits (2) -> loader
     FB_COUNT = FB_COL_EMPTY + kFMaxColRing
 };
-constexpr int kFActSlot = 100;  // 8-byte slots 100..115 of the barrier block hold the tile's 128 sampled actions (bytes)
-static_assert((int)FB_COUNT <= kFActSlot && kFActSlot + 16 <= (int)PB_TMEM_SLOT, "barrier block overflow");
+static_assert((int)FB_COUNT <= (int)PB_TMEM_SLOT, "barrier block overflow");
 
 struct FusedSmemLayout {
     int head, wring, bars, act, tables, tmpl, envw;
-    int view_stride, env_warp_bytes, total;
+    int view_stride, env_warp_bytes, slot_bytes, total;
 };
-__host__ __device__ inline FusedSmemLayout fused_smem_layout(int npos, int ring, int S, int SC) {
+__host__ __device__ inline FusedSmemLayout fused_smem_layout(int npos, int ring, int S, int SC, int slots) {
     FusedSmemLayout s;
     const BlobLayout L = blob_layout(npos);
     int o = 0;
     s.head = o, o += kPRestOff + 2 * (L.head_bytes - L.bias1);
     s.wring = o, o += ring * kChunk;
     s.bars = o, o += 1024;
-    s.act = s.bars + 8 * kFActSlot;  // 128 action bytes inside the barrier block
+    s.act = o, o += 2 * 128;  // the sampled actions of a slot's tile, one byte per agent row
     s.tables = o, o += (int)align16(sizeof(Tables));
     s.tmpl = o, o += (int)align16((size_t)SC);
     s.envw = o;
     s.view_stride = (int)align16((size_t)32 * SC);
     s.env_warp_bytes = 2 * s.view_stride + (int)align16((size_t)S * 32 * 2);
-    o += kFEnvWarps * s.env_warp_bytes;
+    s.slot_bytes = kFEnvWarps * s.env_warp_bytes;
+    o += slots * s.slot_bytes;
     s.total = o + 128;
     return s;
+}
+
+// The CTA's stream of virtual tiles: rounds of `slots` world tiles, T + 1 steps each, the tiles of a round interleaved step by
+// step.  Every role walks the same cursor (a slot without a tile — only possible in the last round — is skipped).
+struct FusedCursor {
+    int kt0, u, s, T, wtiles, stride, slots;
+    bool two;
+    __device__ __forceinline__ FusedCursor(const FusedParams& fp)
+        : kt0((int)blockIdx.x * fp.slots), u(0), s(0), T(fp.T), wtiles(fp.wtiles), stride((int)gridDim.x * fp.slots), slots(fp.slots) {
+        two = slots == 2 && kt0 + 1 < wtiles;
+    }
+    __device__ __forceinline__ int kt() const { return kt0 + s; }
+    __device__ __forceinline__ void next() {
+        if (two && s == 0) {
+            s = 1;
+            return;
+        }
+        s = 0;
+        if (++u > T) u = 0, kt0 += stride, two = slots == 2 && kt0 + 1 < wtiles;
+    }
+};
+__host__ __device__ inline int fused_virtual_tiles(int wtiles, int slots, int grid, int cta, int T) {
+    int n = 0;
+    for (int kt0 = cta * slots; kt0 < wtiles; kt0 += grid * slots) n += ((slots == 2 && kt0 + 1 < wtiles) ? 2 : 1) * (T + 1);
+    return n;
 }
 
 // loaders: shared-memory planes -> bf16 cell blocks in TMEM.  Thread (lw, lane) owns row 32 lw + lane
@@ -80,16 +116,20 @@ __device__ __forceinline__ void fused_loader_role(const FusedParams& fp, uint32_
                                                   const FusedSmemLayout& sl, uint32_t bars) {
     const int lwarp = (threadIdx.x >> 5) - kEpiWarps, lg = lwarp >> 2, lw = lwarp & 3, lane = threadIdx.x & 31;
     const int W = fp.pol.W, H = fp.pol.H, seg = 5 * H;
-    const uint32_t* myrow = reinterpret_cast<const uint32_t*>(s_env + (lw & 1) * sl.env_warp_bytes + (lw >> 1) * sl.view_stride +
-                                                              lane * fp.pol.SC);
+    const uint32_t* myrow0 = reinterpret_cast<const uint32_t*>(s_env + (lw & 1) * sl.env_warp_bytes + (lw >> 1) * sl.view_stride +
+                                                               lane * fp.pol.SC);
+    const uint32_t* myrow = myrow0;
     const uint32_t tcells = tmem + ((uint32_t)(lw * 32) << 16) + kColCells;
     const uint32_t ncols = nvt * (uint32_t)W;
     uint32_t lt = 0;  // virtual tile of the column
     int lx = lg;      // grid column inside it
     bool fresh = true;  // first column of this group in tile lt
+    FusedCursor cur(fp);
+    uint32_t seen[2] = {0, 0};  // virtual tiles of each slot consumed so far (phase of the slot's barriers)
     for (uint32_t gc = lg; gc < ncols; gc += 2) {
         if (fresh) {
-            mbar_wait(bars + 8 * FB_OBS_FULL, lt & 1);
+            myrow = myrow0 + cur.s * (sl.slot_bytes >> 2);
+            mbar_wait(bars + 8 * (FB_OBS_FULL + cur.s), (cur.s ? seen[1] : seen[0]) & 1);
             if (kProf && lwarp == 0) trace_ev<kProf>(fp.pol, (int)lt, 8);
         }
         const bool first_col = fresh;
@@ -156,15 +196,33 @@ __device__ __forceinline__ void fused_loader_role(const FusedParams& fp, uint32_
         if (kProf && lwarp == 0 && first_col) trace_ev<kProf>(fp.pol, (int)lt, 9);
         lx += 2;
         if (lx >= W) {  // this group's last column of the tile: its plane reads are done
-            mbar_arrive(bars + 8 * FB_OBS_EMPTY);
+            mbar_arrive(bars + 8 * (FB_OBS_EMPTY + cur.s));
             if (kProf && lwarp == 0) trace_ev<kProf>(fp.pol, (int)lt, 10);
+            if (cur.s) ++seen[1]; else ++seen[0];
+            cur.next();
             lx -= W, ++lt, fresh = true;
         }
     }
 }
 
-// env warps: one world per lane, state in registers / shared memory across the T steps
-template <bool kProf>
+// env warps: one world per lane and slot, state in registers / shared memory across the T steps.  With two tiles in flight the
+// same two warps serve both slots in stream order (A, u), (B, u), (A, u + 1), ...: a slot's env step takes a sixth of its
+// policy pass, so the warps are idle most of the time either way.
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+template <int P>
+struct FusedSlot {
+    World<P> w;
+    int cur_return, ep_add;
+    long long ret_add;
+    int n, nbytes;
+    bool valid, tma_ok, tma_pending;
+    int8_t* obs_ptr;
+    int32_t *rew_ptr, *done_ptr;
+    uint32_t vts, acts;  // virtual tiles / action hand-offs of this slot so far (barrier phases); never reset
+};
+
+template <bool kProf, int kSlots>
 __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s_env, const FusedSmemLayout& sl, const Tables& tb,
                                                const uint8_t* tmpl, const uint8_t* s_act, uint32_t bars) {
     constexpr int P = 2;
@@ -172,154 +230,186 @@ __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s
     const Consts c = load_consts(tb);
     const int SC = tb.SC, N = fp.env.N, T = fp.T;
     const int view_stride = sl.view_stride;
-    uint8_t* planes = s_env + ew * sl.env_warp_bytes;                                          // [P][32][SC]
-    uint16_t* myobjs = reinterpret_cast<uint16_t*>(planes + (size_t)P * view_stride) + lane;  // [S][32]
-    uint8_t* myplanes = planes + lane * SC;
-    const uint32_t planes_s = smem_addr(planes);
     const size_t PN = (size_t)P * N, obs_view_stride = (size_t)N * SC, obs_step_stride = PN * SC;
-    uint32_t vt = 0, acts = 0;
-    bool tma_pending = false;
+    const bool store_obs = fp.obs_slab != nullptr;
 
-    for (int kt = blockIdx.x; kt < fp.wtiles; kt += gridDim.x) {
-        const int n0 = kt * kFWorlds + ew * 32, n = n0 + lane;
-        const bool valid = n < N;
-        const int nl = valid ? n : N - 1;
-        const int nvalid = max(0, min(32, N - n0));
-        const int nbytes = nvalid * SC;
-        int8_t* obs_ptr = fp.obs_slab + (size_t)n0 * SC;
-        const bool tma_ok = fp.env.use_tma && nbytes > 0 && ((nbytes & 15) == 0) && ((reinterpret_cast<uintptr_t>(obs_ptr) & 15u) == 0) &&
-                            ((obs_view_stride & 15u) == 0);
-        int32_t* rew_ptr = fp.reward ? fp.reward + n : nullptr;
-        int32_t* done_ptr = fp.done ? fp.done + n : nullptr;
+    FusedSlot<P> sa, sb;  // slot 0 / slot 1 (two named objects: an array of them ends up in local memory)
+    sa.vts = sa.acts = sb.vts = sb.acts = 0;
+    sa.tma_pending = sb.tma_pending = false;
 
-        World<P> w;
-        load_world<P, 1, 8>(tb, c, fp.env, nl, 0, myobjs, w);
-        int cur_return = fp.env.cur_return[nl];
-        long long ret_add = 0;
-        int ep_add = 0;
+    // `slot` is a literal at both call sites
+    auto planes_of = [&](int slot) { return s_env + slot * sl.slot_bytes + ew * sl.env_warp_bytes; };  // [P][32][SC]
+    auto objs_of = [&](int slot) { return reinterpret_cast<uint16_t*>(planes_of(slot) + (size_t)P * view_stride) + lane; };  // [S][32]
 
-        for (int u = 0; u <= T; ++u, ++vt) {
-            bool full = true;
-            int oldslot[P] = {0, 0};
-            uint32_t dirty[P] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-            // the planes still hold virtual tile vt - 1: its loaders and its bulk store must be done with them (both finish
-            // long before the actions arrive, so these waits sit before the action wait, off the critical path)
-            if (vt > 0) mbar_wait(bars + 8 * FB_OBS_EMPTY, (vt - 1) & 1);
-            if (tma_pending) {
-                if (lane == 0) bulk_wait_read_all();
-                tma_pending = false;
+    auto begin_tile = [&](FusedSlot<P>& q, int slot, int kt) {
+        const int n0 = kt * kFWorlds + ew * 32;
+        q.n = n0 + lane;
+        q.valid = q.n < N;
+        const int nl = q.valid ? q.n : N - 1;
+        q.nbytes = max(0, min(32, N - n0)) * SC;
+        q.obs_ptr = store_obs ? fp.obs_slab + (size_t)n0 * SC : nullptr;
+        q.tma_ok = store_obs && fp.env.use_tma && q.nbytes > 0 && ((q.nbytes & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(q.obs_ptr) & 15u) == 0) && ((obs_view_stride & 15u) == 0);
+        q.rew_ptr = fp.reward ? fp.reward + q.n : nullptr;
+        q.done_ptr = fp.done ? fp.done + q.n : nullptr;
+        load_world<P, 1, 8>(tb, c, fp.env, nl, 0, objs_of(slot), q.w);
+        q.cur_return = fp.env.cur_return[nl];
+        q.ret_add = 0, q.ep_add = 0;
+    };
+
+    // `other_pending`: the other slot has a bulk store in flight that was committed AFTER this slot's last one
+    auto step_tile = [&](FusedSlot<P>& q, int slot, int u, bool other_pending) {
+        uint8_t* planes = planes_of(slot);
+        uint16_t* myobjs = objs_of(slot);
+        uint8_t* myplanes = planes + lane * SC;
+        bool full = true;
+        int oldslot[P] = {0, 0};
+        uint32_t dirty[P] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+        // the planes still hold the slot's previous virtual tile: its loaders and its bulk store must be done with them (both
+        // finish long before the actions arrive, so these waits sit before the action wait, off the critical path)
+        if (q.vts > 0) mbar_wait(bars + 8 * (FB_OBS_EMPTY + slot), (q.vts - 1) & 1);
+        if (q.tma_pending) {
+            if (lane == 0) {
+                if (other_pending)
+                    bulk_wait_read_1();  // all but the newest group: the other slot's store may go on reading ITS planes
+                else
+                    bulk_wait_read_all();
             }
-            if (u > 0) {
-                mbar_wait(bars + 8 * FB_ACT_FULL, acts & 1);
-                if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)vt, 0);
-                ++acts;
-                int act[P];
-                act[0] = s_act[ew * 32 + lane], act[1] = s_act[kFWorlds + ew * 32 + lane];
+            q.tma_pending = false;
+        }
+        if (u > 0) {
+            mbar_wait(bars + 8 * (FB_ACT_FULL + slot), q.acts & 1);
+            if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)q.vts, 0);
+            ++q.acts;
+            int act[P];
+            act[0] = s_act[slot * 128 + ew * 32 + lane], act[1] = s_act[slot * 128 + kFWorlds + ew * 32 + lane];
 #pragma unroll
-                for (int i = 0; i < P; ++i) oldslot[i] = w.slot[i];
-                const int r = step_world<P>(tb, c, w, myobjs, 32, act, dirty);
-                const bool done = w.timestep >= c.horizon;
-                cur_return += r;
-                if (done) {
-                    ret_add += cur_return;
-                    ep_add += 1;
-                    cur_return = 0;
-                    reset_world<P>(tb, w);
-                    for (int idx = 0; idx < c.n_objcells; ++idx) myobjs[(int)tb.objcells[idx] * 32] = 0;
-                }
-                if (rew_ptr != nullptr) {
-                    if (valid) rew_ptr[0] = r, rew_ptr[N] = r;
-                    rew_ptr += PN;
-                }
-                if (done_ptr != nullptr) {
-                    if (valid) *done_ptr = done ? 1 : 0;
-                    done_ptr += N;
-                }
-                full = done;
-                if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)vt, 1);
+            for (int i = 0; i < P; ++i) oldslot[i] = q.w.slot[i];
+            const int r = step_world<P>(tb, c, q.w, myobjs, 32, act, dirty);
+            const bool done = q.w.timestep >= c.horizon;
+            q.cur_return += r;
+            if (done) {
+                q.ret_add += q.cur_return;
+                q.ep_add += 1;
+                q.cur_return = 0;
+                reset_world<P>(tb, q.w);
+                for (int idx = 0; idx < c.n_objcells; ++idx) myobjs[(int)tb.objcells[idx] * 32] = 0;
             }
-            __syncwarp();
-            if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)vt, 2);
-            obs_phase1<P, 1>(tb, myplanes, view_stride, tmpl, full, 0, oldslot);
-            obs_phase2<P, 1>(tb, c, myplanes, view_stride, myobjs, 32, full, 0, w, dirty);
-            mbar_arrive(bars + 8 * FB_OBS_FULL);  // release: the loaders may read this lane's planes
-            if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)vt, 3);
-            int8_t* dst = obs_ptr + (size_t)u * obs_step_stride;
-            if (tma_ok) {
+            if (q.rew_ptr != nullptr) {
+                if (q.valid) q.rew_ptr[0] = r, q.rew_ptr[N] = r;
+                q.rew_ptr += PN;
+            }
+            if (q.done_ptr != nullptr) {
+                if (q.valid) *q.done_ptr = done ? 1 : 0;
+                q.done_ptr += N;
+            }
+            full = done;
+            if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)q.vts, 1);
+        }
+        __syncwarp();
+        if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)q.vts, 2);
+        obs_phase1<P, 1>(tb, myplanes, view_stride, tmpl, full, 0, oldslot);
+        obs_phase2<P, 1>(tb, c, myplanes, view_stride, myobjs, 32, full, 0, q.w, dirty);
+        mbar_arrive(bars + 8 * (FB_OBS_FULL + slot));  // release: the loaders may read this lane's planes
+        if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)q.vts, 3);
+        ++q.vts;
+        if (store_obs) {
+            int8_t* dst = q.obs_ptr + (size_t)u * obs_step_stride;
+            if (q.tma_ok) {
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
 #pragma unroll
-                    for (int v = 0; v < P; ++v) bulk_store_s2g(dst + v * obs_view_stride, planes_s + v * view_stride, (uint32_t)nbytes);
+                    for (int v = 0; v < P; ++v)
+                        bulk_store_s2g(dst + v * obs_view_stride, smem_addr(planes) + v * view_stride, (uint32_t)q.nbytes);
                     bulk_commit();
                 }
-                tma_pending = true;
-            } else if (nbytes > 0) {
+                q.tma_pending = true;
+            } else if (q.nbytes > 0) {
                 __syncwarp();
 #pragma unroll
-                for (int v = 0; v < P; ++v) warp_copy_out(dst + v * obs_view_stride, planes + v * view_stride, nbytes, lane);
+                for (int v = 0; v < P; ++v) warp_copy_out(dst + v * obs_view_stride, planes + v * view_stride, q.nbytes, lane);
             }
         }
-        // world state back to HBM (the next launch, or ocb_get_state, continues from it)
-        if (valid) {
-            fp.env.players[n] = player_pack(w.pos[0], w.orient[0], w.held[0]);
-            fp.env.players[(size_t)N + n] = player_pack(w.pos[1], w.orient[1], w.held[1]);
-            store_world_objs<1>(tb, c, fp.env, n, 0, myobjs);
-            fp.env.timestep[n] = w.timestep;
-            fp.env.cur_return[n] = cur_return;
-            if (ep_add) {
-                fp.env.ret_sum[n] += ret_add;
-                fp.env.episodes[n] += ep_add;
+    };
+
+    // world state back to HBM (the next launch, or ocb_get_state, continues from it)
+    auto end_tile = [&](FusedSlot<P>& q, int slot) {
+        if (q.valid) {
+            fp.env.players[q.n] = player_pack(q.w.pos[0], q.w.orient[0], q.w.held[0]);
+            fp.env.players[(size_t)N + q.n] = player_pack(q.w.pos[1], q.w.orient[1], q.w.held[1]);
+            store_world_objs<1>(tb, c, fp.env, q.n, 0, objs_of(slot));
+            fp.env.timestep[q.n] = q.w.timestep;
+            fp.env.cur_return[q.n] = q.cur_return;
+            if (q.ep_add) {
+                fp.env.ret_sum[q.n] += q.ret_add;
+                fp.env.episodes[q.n] += q.ep_add;
             }
         }
         __syncwarp();
+    };
+
+    for (int kt0 = (int)blockIdx.x * kSlots; kt0 < fp.wtiles; kt0 += (int)gridDim.x * kSlots) {
+        const bool two = kSlots == 2 && kt0 + 1 < fp.wtiles;
+        begin_tile(sa, 0, kt0);
+        if (kSlots == 2 && two) begin_tile(sb, 1, kt0 + 1);
+        for (int u = 0; u <= T; ++u) {
+            step_tile(sa, 0, u, kSlots == 2 && two && sb.tma_pending);
+            if (kSlots == 2 && two) step_tile(sb, 1, u, sa.tma_pending);
+        }
+        end_tile(sa, 0);
+        if (kSlots == 2 && two) end_tile(sb, 1);
     }
-    if (tma_pending && lane == 0) bulk_wait_read_all();
+    if ((sa.tma_pending || (kSlots == 2 && sb.tma_pending)) && lane == 0) bulk_wait_read_all();
 }
 
-// output stage of the epilogue in the fused rollout
+// output stage of the epilogue in the fused rollout.  `net` = 0: six logits of the tile's rows, 1: head[0] = value.
+// Cross-play: both pipeline networks are actors; group 0 (net 0) owns the rows of seat 0, group 1 those of seat 1.
 struct FusedOut {
     const FusedParams& fp;
     uint8_t* s_act;
     uint32_t bars;
     unsigned long long base;
-    int u, kt;
-    __device__ __forceinline__ FusedOut(const FusedParams& f, uint8_t* sa, uint32_t b) : fp(f), s_act(sa), bars(b), u(0), kt(blockIdx.x) {
+    FusedCursor cur;
+    int g;
+    __device__ __forceinline__ FusedOut(const FusedParams& f, uint8_t* sa, uint32_t b) : fp(f), s_act(sa), bars(b), cur(f) {
         base = f.pol.offset;
         if (f.pol.d_offset != nullptr) base += *f.pol.d_offset;
+        g = (int)(threadIdx.x >> 7);  // epilogue group of this thread
     }
+    __device__ __forceinline__ bool mine(int trow_id) const { return !fp.cross || (trow_id >> 6) == g; }
     __device__ __forceinline__ uint32_t draw(int, int trow_id) const {
-        if (fp.pol.deterministic || u >= fp.T) return 0u;
+        if (fp.pol.deterministic || cur.u >= fp.T || !mine(trow_id)) return 0u;
         const int wl = trow_id & (kFWorlds - 1), seat = trow_id >> 6;
-        const long long row = (long long)seat * fp.env.N + (kt * kFWorlds + wl);
-        return policy_draw(fp.pol, (uint32_t)row, base + (unsigned long long)u);
+        const long long row = (long long)seat * fp.env.N + (cur.kt() * kFWorlds + wl);
+        return policy_draw(fp.pol, (uint32_t)row, base + (unsigned long long)cur.u);
     }
-    __device__ __forceinline__ void operator()(int, int trow_id, int g, const float (&head)[6], uint32_t drawn) {
-        const int N = fp.env.N, wl = trow_id & (kFWorlds - 1), seat = trow_id >> 6;
-        const int n = kt * kFWorlds + wl;
+    __device__ __forceinline__ void operator()(int, int trow_id, int net, const float (&head)[6], uint32_t drawn) {
+        const int N = fp.env.N, wl = trow_id & (kFWorlds - 1), seat = trow_id >> 6, u = cur.u;
+        const int n = cur.kt() * kFWorlds + wl;
         const long long row = (long long)seat * N + n;               // row of one step's [2][N] block
         const long long store = (long long)u * 2 * N + row;
-        if (g == 1) {
-            if (n < N) fp.values[store] = head[0];
-        } else if (u < fp.T) {
+        if (net == 1) {
+            if (n < N && fp.values != nullptr) fp.values[store] = head[0];
+        } else if (u < fp.T && mine(trow_id)) {
             PolicyParams op = fp.pol;  // output pointers of this step; rows past N sample but store nothing
             const bool valid = n < N;
             op.actions = valid ? fp.actions : nullptr, op.logp = valid ? fp.logp : nullptr, op.logits = nullptr;
-            emit_actor_row(op, store, (uint32_t)row, head, base + (unsigned long long)u, true, &drawn, s_act + trow_id,
-                           bars + 8 * FB_ACT_FULL);
+            emit_actor_row(op, store, (uint32_t)row, head, base + (unsigned long long)u, true, &drawn, s_act + cur.s * 128 + trow_id,
+                           bars + 8 * (FB_ACT_FULL + cur.s));
         }
-        if (++u > fp.T) u = 0, kt += gridDim.x;
+        cur.next();
     }
 };
 
-template <bool kProf, bool kSplit>
+template <bool kProf, bool kSplit, int kSlots>
 __global__ void __launch_bounds__(kFThreads, 1) rollout_fused_kernel(const FusedParams fp) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
     const int tid = threadIdx.x, warp = tid >> 5;
     const PolicyParams& prm = fp.pol;
     const BlobLayout L = blob_layout(prm.npos);
-    const FusedSmemLayout sl = fused_smem_layout(prm.npos, prm.pair_ring, prm.S, prm.SC);
+    const FusedSmemLayout sl = fused_smem_layout(prm.npos, prm.pair_ring, prm.S, prm.SC, fp.slots);
     uint8_t* s_head = smem + sl.head;
     uint8_t* s_wring = smem + sl.wring;
     uint64_t* s_bars = reinterpret_cast<uint64_t*>(smem + sl.bars);
@@ -348,9 +438,9 @@ __global__ void __launch_bounds__(kFThreads, 1) rollout_fused_kernel(const Fused
             if (i >= PBS_D1_EMPTY && i < PBS_D1_EMPTY + 4) count = 128;
             if (i >= FB_COL_FULL && i < FB_COL_FULL + kFMaxColRing) count = 128;
             if (i >= FB_COL_EMPTY && i < FB_COL_EMPTY + kFMaxColRing) count = 3;  // the actor's two issuers and the critic's one
-            if (i == FB_OBS_FULL) count = 32 * kFEnvWarps;
-            if (i == FB_OBS_EMPTY) count = 32 * kLoadWarps;
-            if (i == FB_ACT_FULL) count = 128;
+            if (i >= FB_OBS_FULL && i < FB_OBS_FULL + 2) count = 32 * kFEnvWarps;
+            if (i >= FB_OBS_EMPTY && i < FB_OBS_EMPTY + 2) count = 32 * kLoadWarps;
+            if (i >= FB_ACT_FULL && i < FB_ACT_FULL + 2) count = 128;
             mbar_init(bars + 8 * i, count);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -365,9 +455,8 @@ __global__ void __launch_bounds__(kFThreads, 1) rollout_fused_kernel(const Fused
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    // virtual tiles of this CTA: (world tile k, step u), u = 0..T, world tiles blockIdx.x, + gridDim.x, ...
-    const int nk = ((int)blockIdx.x < fp.wtiles) ? (fp.wtiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int nvt = nk * (fp.T + 1);
+    // virtual tiles of this CTA: (world tile, step u), u = 0..T, the tiles of a round interleaved (FusedCursor)
+    const int nvt = fused_virtual_tiles(fp.wtiles, fp.slots, (int)gridDim.x, (int)blockIdx.x, fp.T);
 
     long long pw[kProf ? PW_COUNT : 1] = {};
     if (warp < kEpiWarps) {
@@ -390,7 +479,7 @@ __global__ void __launch_bounds__(kFThreads, 1) rollout_fused_kernel(const Fused
             pair_conv_role<kProf, 1>(pw, prm, 0, nvt, L, tmem, smem_addr(s_head), bars, 0, 1, (uint32_t)fp.col_ring, FB_COL_FULL,
                                      FB_COL_EMPTY);
     } else {
-        fused_env_role<kProf>(fp, s_env, sl, *s_tables, s_tmpl, s_act, bars);
+        fused_env_role<kProf, kSlots>(fp, s_env, sl, *s_tables, s_tmpl, s_act, bars);
     }
     __syncwarp();
     tc_fence_before();

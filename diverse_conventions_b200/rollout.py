@@ -157,9 +157,13 @@ class PolicyRollout:
         self.policy_index = policy_index
         # one persistent launch needs the tensor-core policy path: 2 players, grids up to 6 rows (else per-step launches,
         # which run any shape — the generic policy kernel covers schelling / corridor / multiplayer_schelling ...)
-        can_fuse = tile_policy is None and with_critic and policy.hidden == 64 and env.num_players == 2
+        # (self-play of one policy with its critic, or cross-play slices without a critic: ocb_rollout_crossplay_fused)
+        small = policy.hidden == 64 and env.num_players == 2
+        can_fuse = small and ((tile_policy is None and with_critic) or
+                              (tile_policy is not None and not with_critic and env.num_envs % TILE == 0))
         if fused and not can_fuse:
-            raise ValueError("the fused rollout needs self-play of one policy (no tile_policy), hidden 64 and the critic")
+            raise ValueError("the fused rollout needs hidden 64, two players and either self-play of one policy with its critic "
+                             "or cross-play slices (tile_policy, a multiple of %d worlds) without one" % TILE)
         self.fused = can_fuse if fused is None else bool(fused)
         self._fused_required = bool(fused)
         if tile_policy is None and policy_index != 0 and not self.fused:
@@ -181,9 +185,14 @@ class PolicyRollout:
         # handle-level state, set per issue: several rollouts may share one policy handle
         _native.check(self._lib.ocb_policy_set_sampling_rows(self.policy._h, *self._sampling_rows))
         if self.fused:
-            rc = self._lib.ocb_rollout_policy_fused(
-                env._h, self.policy._h, self.T, self.policy_index, _ptr(b.obs), _ptr(b.actions), _ptr(b.action_log_probs),
-                _ptr(b.value_preds), _ptr(b.rewards), _ptr(b.dones), int(deterministic), self.seed, stream)
+            if self.tile_policy is not None:
+                rc = self._lib.ocb_rollout_crossplay_fused(
+                    env._h, self.policy._h, self.T, _ptr(self.tile_policy), _ptr(b.obs), _ptr(b.actions),
+                    _ptr(b.action_log_probs), _ptr(b.rewards), _ptr(b.dones), int(deterministic), self.seed, stream)
+            else:
+                rc = self._lib.ocb_rollout_policy_fused(
+                    env._h, self.policy._h, self.T, self.policy_index, _ptr(b.obs), _ptr(b.actions), _ptr(b.action_log_probs),
+                    _ptr(b.value_preds), _ptr(b.rewards), _ptr(b.dones), int(deterministic), self.seed, stream)
             if rc != _native.OCB_ERR_UNSUPPORTED or self._fused_required:
                 _native.check(rc)
                 return
@@ -264,7 +273,7 @@ class CrossPlayEvaluator:
 
     def __init__(self, layout: str, policy: FusedPolicy, pairs, worlds_per_pair: int = 1024, horizon: int = 400,
                  gpu_id: int = 0, seed: int = 0, world_offset: int = 0, chunk_steps: int = 50, use_graph: bool = True,
-                 deterministic: bool = False, total_worlds: Optional[int] = None):
+                 deterministic: bool = False, total_worlds: Optional[int] = None, fused: Optional[bool] = None):
         self.pairs = [tuple(int(v) for v in p) for p in pairs]
         if not self.pairs:
             raise ValueError("no pairs on this rank")
@@ -277,18 +286,42 @@ class CrossPlayEvaluator:
         N = len(self.pairs) * worlds_per_pair
         self.env = B200Overcooked(layout, N, gpu_id, horizon=horizon, seed=seed, world_offset=world_offset)
         table = pair_tile_policy(self.pairs, worlds_per_pair, self.env.sim_device)
+        self.table, self.policy, self.seed = table, policy, seed
+        self._sampling_rows = (0, 0, 0) if total_worlds is None else (N, world_offset, total_worlds - N + world_offset)
+        # The whole episode as ONE persistent launch without any trajectory buffer (ocb_rollout_crossplay_fused) when the
+        # fused kernel takes the shape; ``fused=False`` (or a layout it does not fit) runs chunked per-step launches.
+        self.fused = (fused if fused is not None else True) and policy.hidden == 64 and self.env.num_players == 2 and N % TILE == 0
         # the slab holds chunk_steps observations, not the whole episode: evaluation keeps no trajectory
         # total_worlds = worlds of the whole pair list over all ranks: the matrix then does not depend on the sharding
-        self.rollout = PolicyRollout(self.env, policy, chunk_steps, table, with_critic=False, with_logp=False, seed=seed,
-                                     use_graph=use_graph, world_offset=world_offset, total_worlds=total_worlds)
+        self._rollout_args = dict(T=chunk_steps, tile_policy=table, with_critic=False, with_logp=False, seed=seed,
+                                  use_graph=use_graph, fused=False, world_offset=world_offset, total_worlds=total_worlds)
+        # the chunked per-step rollout (and its observation slab) is only built when it is needed
+        self.rollout = None if self.fused else PolicyRollout(self.env, policy, **self._rollout_args)
+
+    def _run_fused(self) -> bool:
+        lib, env = _native.lib(), self.env
+        with torch.cuda.device(env.sim_device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(env.sim_device).cuda_stream)
+            _native.check(lib.ocb_policy_set_sampling_rows(self.policy._h, *self._sampling_rows))
+            rc = lib.ocb_rollout_crossplay_fused(env._h, self.policy._h, self.horizon, _ptr(self.table), None, None, None, None,
+                                                 None, int(self.deterministic), self.seed, stream)
+        if rc == _native.OCB_ERR_UNSUPPORTED:
+            return False
+        _native.check(rc)
+        return True
 
     def run(self):
         """one full episode per world -> (return_sum int64 [pairs], episodes int64 [pairs]) on the device"""
         self.env.n_reset()
         self.env.clear_episode_stats()
-        self.rollout._primed = False
-        for _ in range(self.horizon // self.chunk_steps):
-            self.rollout.collect(self.deterministic)
+        if self.fused and not self._run_fused():
+            self.fused = False
+        if not self.fused:
+            if self.rollout is None:
+                self.rollout = PolicyRollout(self.env, self.policy, **self._rollout_args)
+            self.rollout._primed = False
+            for _ in range(self.horizon // self.chunk_steps):
+                self.rollout.collect(self.deterministic)
         rs, ep = self.env.episode_stats()
         n = len(self.pairs)
         return rs.view(n, self.worlds_per_pair).sum(1), ep.view(n, self.worlds_per_pair).sum(1, dtype=torch.int64)

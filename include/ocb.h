@@ -276,6 +276,15 @@ int ocb_rollout_policy_fused(ocb_env* env, ocb_policy* pol, int T, int policy_in
                              float* logp, float* values, int32_t* reward, int32_t* done, int deterministic,
                              uint64_t seed, void* stream);
 
+/* Cross-play evaluation in ONE persistent launch (the slices of XDPlayer / CentralizedMultiAgent, train/XD/xd_player.py:177-230,
+ * train/partner_agents.py:87-137, generalised to arbitrary pairs): the rollout of ocb_rollout_policy(values = NULL) with
+ * `tile_policy` (DEVICE int32 [2 N / 128], seat-major: tile t of seat 0 rows, then of seat 1 rows) — same sampled actions, same
+ * env transitions.  N must be a multiple of 128.  Every output buffer is optional (NULL): evaluation keeps no trajectory,
+ * ocb_episode_stats carries the returns.  OCB_ERR_UNSUPPORTED when the layout does not fit the kernel. */
+int ocb_rollout_crossplay_fused(ocb_env* env, ocb_policy* pol, int T, const int32_t* tile_policy, int8_t* obs_slab,
+                                int32_t* actions, float* logp, int32_t* reward, int32_t* done, int deterministic,
+                                uint64_t seed, void* stream);
+
 /* Diagnostic: ocb_rollout_policy_fused through the instrumented build of the kernel (synchronous, sampled
  * actions).  h_trace (HOST int64 [n_steps][64]) receives clock64 stamps of CTA 0 for steps u0 .. u0+n_steps-1;
  * event indices are listed at trace_ev in csrc/policy_kernels.cu (env / loader / MMA issue / epilogue hand-offs).

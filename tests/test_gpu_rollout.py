@@ -222,10 +222,12 @@ def test_sampled_graph_replays_draw_fresh_actions_and_stay_exact(fused):
     ("unident_s", 300, 21, 10, 0),        # 9 x 5 grid: weights streamed through the ring
     ("random3", 130, 17, 400, 0),         # 8 x 5 grid, no reset inside the rollout
 ])
-def test_fused_rollout_is_bit_identical_to_the_per_step_launches(layout, N, T, horizon, index):
+@pytest.mark.parametrize("slots", ["1", "2"])
+def test_fused_rollout_is_bit_identical_to_the_per_step_launches(monkeypatch, layout, N, T, horizon, index, slots):
     """the single persistent launch (ocb_rollout_policy_fused) and the 2T+1 launches of ocb_rollout_policy fill the
     same buffers: same observations / rewards / dones, same sampled actions, same log-probs and values (bitwise),
     same final state and episode statistics, over two consecutive rollouts"""
+    monkeypatch.setenv("OCB_FUSED_SLOTS", slots)  # world tiles in flight per CTA (2 falls back to 1 where the planes do not fit)
     lp = layouts.load_layout(layout, horizon)
     pol, _, _ = make_policies(lp, 2)
     res = []
@@ -274,7 +276,7 @@ def test_crossplay_slices_use_the_named_policies_and_return_matrix_matches_oracl
     assert table.tolist() == [p[0] for p in pairs] + [p[1] for p in pairs]
 
     ev = CrossPlayEvaluator(layout, pol, pairs, worlds_per_pair=wpp, horizon=horizon, seed=3, chunk_steps=20,
-                            use_graph=True)
+                            use_graph=True, fused=False)  # chunked per-step launches: the trajectory is recorded below
     N = ev.env.num_envs
     # record the whole episode by chunks to replay it
     ev.env.n_reset()
@@ -314,6 +316,47 @@ def test_crossplay_slices_use_the_named_policies_and_return_matrix_matches_oracl
     assert mean.shape == (n_pol, n_pol) and int(eps.sum()) == N
     assert torch.isfinite(mean).all()
     ev.close()
+
+    # (4) the whole episode as ONE persistent launch without a trajectory buffer: a fresh env draws the same streams as the
+    # recorded first episode above (sampling is keyed by seed, row and the env's step counter), hence the same returns
+    ev1 = CrossPlayEvaluator(layout, pol, pairs, worlds_per_pair=wpp, horizon=horizon, seed=3, chunk_steps=20)
+    rs3, ep3 = ev1.run()
+    torch.cuda.synchronize()
+    assert ev1.fused and ev1.rollout is None
+    assert torch.equal(rs3, rs) and torch.equal(ep3, ep)
+    ev1.close()
+
+
+@pytest.mark.parametrize("slots", ["1", "2"])
+@pytest.mark.parametrize("layout,n_pol,wpp,T,horizon", [("random1", 3, 128, 26, 11), ("simple", 2, 256, 19, 400),
+                                                         ("random0", 4, 128, 13, 6)])
+def test_fused_crossplay_is_bit_identical_to_the_per_step_launches(monkeypatch, layout, n_pol, wpp, T, horizon, slots):
+    """ocb_rollout_crossplay_fused (one persistent launch; OCB_FUSED_SLOTS forces one or two world tiles in flight per CTA)
+    against ocb_rollout_policy with the same tile_policy table: same sampled actions and log-probs (bitwise), same
+    observations / rewards / dones, same final state and episode statistics, over two consecutive rollouts"""
+    monkeypatch.setenv("OCB_FUSED_SLOTS", slots)
+    lp = layouts.load_layout(layout, horizon)
+    pol, _, _ = make_policies(lp, n_pol, gain=2.0)
+    pairs = sharding.all_pairs(n_pol)
+    N = len(pairs) * wpp
+    res = []
+    for fused in (False, True):
+        env = B200Overcooked(layout, N, 0, horizon=horizon, seed=4)
+        ro = PolicyRollout(env, pol, T, pair_tile_policy(pairs, wpp, env.sim_device), with_critic=False, seed=77, fused=fused)
+        out = []
+        for _ in range(2):
+            b = ro.collect()
+            torch.cuda.synchronize()
+            out.append([x.clone() for x in (b.obs, b.actions, b.action_log_probs, b.rewards, b.dones)])
+        assert ro.fused == fused
+        rs, ep = env.episode_stats()
+        res.append((out, env.get_state(), rs.clone(), ep.clone(), env.step_count))
+        env.close()
+    for k in range(2):
+        for name, x, y in zip(("obs", "actions", "logp", "rewards", "dones"), res[0][0][k], res[1][0][k]):
+            assert torch.equal(x, y), (k, name)
+    assert np.array_equal(res[0][1], res[1][1])
+    assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3]) and res[0][4] == res[1][4] == 2 * T
 
 
 def test_actor_only_rollout_and_argument_checks():
