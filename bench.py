@@ -613,8 +613,28 @@ def run_ours(args):
     launch_ms = statistics.mean(per_launch[1:] if len(per_launch) > 1 else per_launch)
     achieved = bytes_ws * N * spl / (launch_ms * 1e-3) / 1e9
     tuning = env.get_tuning()
-    traffic = ncu_traffic_bytes("oc_rollout_kernel<%d, %d>" % (P, tuning["lanes_per_world"])) \
+    # (kernel name without the closing bracket: the K-step instance carries a third template argument since round 2)
+    traffic = ncu_traffic_bytes("oc_rollout_kernel<%d, %d" % (P, tuning["lanes_per_world"])) \
         if (N, spl, args.layout) == (WORLDS_PER_GPU, 100, LAYOUT) else None
+    # The GPUs of the pool differ: the same binary streams 0.206-0.226 ms per launch from box to box.  A plain device copy
+    # on THIS GPU (1 GiB read + 1 GiB written per iteration, CUDA events) says how much of that is the box.
+    box_copy = None
+    try:
+        src = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        dst = torch.empty_like(src)
+        for _ in range(3):
+            dst.copy_(src)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(10):
+            dst.copy_(src)
+        c1.record()
+        torch.cuda.synchronize()
+        box_copy = 2 * 10 * float(1 << 30) / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        del src, dst
+        torch.cuda.empty_cache()
+    except Exception:
+        box_copy = None
 
     # ---- end-to-end: the reference-facing single-step call with host buffers
     E = max(args.e2e_steps, 10)
@@ -688,7 +708,10 @@ def run_ours(args):
                              "kernel": "oc_rollout_kernel<%d,%d>" % (P, tuning["lanes_per_world"]), "tuning": tuning,
                              "bytes_per_world_step": bytes_ws, "world_steps_per_launch": N * spl,
                              "launch_ms": launch_ms, "launches_timed": max(len(per_launch) - 1, 1),
-                             "launch_ms_first": per_launch[0], "peak_source": peaks["source"]},
+                             "launch_ms_first": per_launch[0], "peak_source": peaks["source"],
+                             "box_copy_gbs": box_copy, "frac_of_box_copy": (achieved / box_copy) if box_copy else None,
+                             "box_copy_note": "torch device-to-device copy of 1 GiB on this GPU (read + written bytes / time): "
+                                              "the box's own streaming rate beside the pool-wide peak"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "call": "ocb_step_host_async + ocb_step_host_wait (two steps in flight: D2H of step t under the H2D + "
                                 "kernel of step t + 1); 1 launch / step, obs + reward + done to pinned host memory every step",

@@ -3,7 +3,7 @@
 set -u
 cp diverse_conventions_b200/libocb.so /tmp/libocb_keep.so
 for rep in 1 2; do
-for f in ab/libocb_*.so; do
+for f in ab/libocb_*.so; do  # build the variants into ab/ first (git-ignored; they travel with gpurun)
   cp $f diverse_conventions_b200/libocb.so; touch diverse_conventions_b200/libocb.so
   echo "== $f"; python bench.py --no-config4 --no-config5 --no-cpu-baseline --steps 200 --warmup 10 2>&1 | tail -1 | python -c "
 import json,sys
