@@ -42,9 +42,15 @@ __host__ __device__ inline void bb_unpack(uint32_t s, BBWorld& w) {
     w.hist[1][0] = (s >> 16) & 15, w.hist[1][1] = (s >> 20) & 15;
 }
 
-__device__ inline void bb_reset_world(BBWorld& w, uint64_t seed, uint32_t world) {  // B:141-149
-    ActionRng<2> r;
-    r.refill(seed ^ kResetStream, world, (uint64_t)w.episode);
+// `r` / `r_block`: the reset stream's current Philox block, kept by the caller — one block serves kStepsPerBlock (4)
+// consecutive episodes, and episodes last two or three steps, so recomputing it on every reset was a fifth of the kernel's
+// instructions and its longest dependent chain
+__device__ inline void bb_reset_world(BBWorld& w, uint64_t seed, uint32_t world, ActionRng<2>& r, uint32_t& r_block) {  // B:141-149
+    const uint32_t block = w.episode / ActionRng<2>::kStepsPerBlock;
+    if (block != r_block) {
+        r.refill(seed ^ kResetStream, world, (uint64_t)w.episode);
+        r_block = block;
+    }
     w.loc[0] = r.action((uint64_t)w.episode, 0, kSpaces);
     w.loc[1] = r.action((uint64_t)w.episode, 1, kSpaces);
     w.time = kTime - 1;
@@ -108,9 +114,11 @@ __global__ void __launch_bounds__(256) bb_kernel(const BBParams prm) {
     bb_unpack(prm.state[nl], w);
     w.episode = prm.episode[nl];
     const uint32_t gworld = prm.world0 + (uint32_t)nl;
+    ActionRng<2> reset_rng;
+    uint32_t reset_block = 0xFFFFFFFFu;  // no block cached (episode counters stay far below 2^34)
 
     if (prm.mode != 0) {
-        if (prm.mode == 2) bb_reset_world(w, prm.seed, gworld);
+        if (prm.mode == 2) bb_reset_world(w, prm.seed, gworld, reset_rng, reset_block);
         if (prm.obs != nullptr) {
             bb_write_obs(w, tile, lane);
             __syncwarp();
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(256) bb_kernel(const BBParams prm) {
                 d = true;
                 r = (double)(-kSpaces * (w.time + 1)) * 0.2;
             }
-            if (d) bb_reset_world(w, prm.seed, gworld);  // pantheonrl_extension/vectorenv.py:369-370
+            if (d) bb_reset_world(w, prm.seed, gworld, reset_rng, reset_block);  // pantheonrl_extension/vectorenv.py:369-370
             if (valid) {
                 if (prm.rew != nullptr) {
                     prm.rew[((size_t)k * 2 + 0) * N + n] = (float)r;
