@@ -359,6 +359,69 @@ def test_fused_crossplay_is_bit_identical_to_the_per_step_launches(monkeypatch, 
     assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3]) and res[0][4] == res[1][4] == 2 * T
 
 
+def test_config5_at_full_size_replays_through_the_oracle():
+    """BASELINE config 5 at its stated size — 16 x 16 policy pairs x 1,024 worlds of coordination_ring, one 400-step episode
+    per world — as ONE fused launch with two tiles in flight per SM: the sampled actions are recorded, replayed through the
+    CPU oracle, and every reward, every done and the per-pair returns the device accumulated must come out identical.
+    (Size-independent property of the measured configuration; the policy side is pinned by the bit-identity test against the
+    per-step launches at small sizes.)"""
+    layout, horizon, wpp, n_pol = "random1", 400, 1024, 16
+    lp = layouts.load_layout(layout, horizon)
+    pol, _, _ = make_policies(lp, n_pol, gain=2.0)
+    pairs = sharding.all_pairs(n_pol)
+    N = len(pairs) * wpp
+    env = B200Overcooked(layout, N, 0, horizon=horizon, seed=6)
+    import ctypes
+    from diverse_conventions_b200 import _native
+    from diverse_conventions_b200.overcooked_env import _ptr
+    lib = _native.lib()
+    table = pair_tile_policy(pairs, wpp, env.sim_device)
+    actions = torch.empty((horizon, 2, N), dtype=torch.int32, device=env.sim_device)
+    rewards = torch.empty((horizon, 2, N), dtype=torch.int32, device=env.sim_device)
+    dones = torch.empty((horizon, N), dtype=torch.int32, device=env.sim_device)
+    env.n_reset()
+    env.clear_episode_stats()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(env.sim_device).cuda_stream)
+    _native.check(lib.ocb_rollout_crossplay_fused(env._h, pol._h, horizon, _ptr(table), None, _ptr(actions), None, _ptr(rewards),
+                                                  _ptr(dones), 0, 17, stream))
+    torch.cuda.synchronize()
+    rs, ep = env.episode_stats()
+    orc = COracle(lp, N)
+    _, rew, done = orc.rollout(actions.cpu().numpy().astype(np.uint8), with_obs=False)
+    assert np.array_equal(rewards.cpu().numpy(), rew) and np.array_equal(dones.cpu().numpy(), done)
+    assert done[-1].all() and done[:-1].sum() == 0
+    assert np.array_equal(env.get_state(), orc.state)
+    ref = rew[:, 0].astype(np.int64).sum(0)
+    assert np.array_equal(rs.cpu().numpy(), ref) and (ep.cpu().numpy() == 1).all()
+    per_pair = ref.reshape(len(pairs), wpp).sum(1)
+    assert per_pair.min() > 0  # random-init policies with gain 2 do cook on coordination_ring
+    env.close()
+
+
+def test_two_tiles_in_flight_at_a_large_batch_replay_through_the_oracle():
+    """32,768 worlds of cramped_room (512 tiles on 148 SMs: the launch keeps two tiles in flight per CTA): every observation,
+    reward and done of the self-play rollout is what the oracle produces for the sampled actions"""
+    layout, N, T, horizon = "simple", 32768, 24, 11
+    lp = layouts.load_layout(layout, horizon)
+    pol, actors, critics = make_policies(lp, 1)
+    env = B200Overcooked(layout, N, 0, horizon=horizon, seed=2)
+    ro = PolicyRollout(env, pol, T, seed=9, fused=True)
+    buf = ro.collect()
+    torch.cuda.synchronize()
+    obs, rew, done, orc = replay_through_oracle(lp, N, buf)
+    assert np.array_equal(buf.rewards.cpu().numpy(), rew) and np.array_equal(buf.dones.cpu().numpy(), done)
+    assert np.array_equal(buf.obs.cpu().numpy(), obs)
+    assert np.array_equal(env.get_state(), orc.state)
+    rows = torch.from_numpy(obs).reshape(T + 1, 2 * N, lp.width, lp.height, lp.channels)
+    sub = slice(0, 2 * N, 257)
+    for t in (0, T - 1):
+        ref_lp = log_softmax_sample(actors[0].forward(rows[t, sub]), buf.actions[t].cpu().reshape(-1)[sub])
+        assert torch.allclose(buf.action_log_probs[t].cpu().reshape(-1)[sub], ref_lp, atol=ATOL_LOGP), t
+    ref_v = critics[0].forward(rows[T, sub])[:, 0]
+    assert float((buf.value_preds[T].cpu().reshape(-1)[sub] - ref_v).abs().max() / ref_v.abs().max()) < REL_TOL
+    env.close()
+
+
 def test_actor_only_rollout_and_argument_checks():
     lp = layouts.load_layout("simple", 400)
     pol, _, _ = make_policies(lp, 2)
