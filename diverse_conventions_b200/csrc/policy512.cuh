@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv512_kernel(const P5Params q) 
 }
 
 // ---------------------------------------------------------------- gemm512_kernel
-enum : int { G5_FULL = 0, G5_EMPTY = 2, G5_D_FULL = 4, G5_D_EMPTY = 5, G5_COUNT = 6, G5_TMEM_SLOT = 8 };
+// Barrier slots (8 bytes each): operand ring FULL / EMPTY [3 each], accumulator FULL / EMPTY per N half [2 each]
+enum : int { G5_FULL = 0, G5_EMPTY = 3, G5_D_FULL = 6, G5_D_EMPTY = 8, G5_COUNT = 10, G5_TMEM_SLOT = 12 };
 struct G5Smem {
     int stages, xbuf, bias, wh, bars, total;
 };
@@ -264,16 +265,28 @@ __host__ __device__ inline G5Smem g5_smem_layout() {
     s.stages = o, o += kGStages * (kABlk + kWBlk);
     s.xbuf = o, o += kRows * 8 * 4;
     s.bias = o, o += kH5 * 4;
-    s.wh = o, o += 8 * kH5 * 4 + 128;  // head weights [8][512] + head bias
+    s.wh = o, o += 8 * kH5 * 4 + 128;  // head weights (FC2: hidden-major [512][8], see below) + head bias
     s.bars = o, o += 128;
     s.total = o + 128;
     return s;
 }
 
-// kHead = false: FC1 (A = q.a1, K blocks = kc1, W = w1, bias b1) -> q.a2 in the packed layout
-// kHead = true : FC2 (A = q.a2, 16 K blocks, W = w2, bias b2) -> head, sampling, outputs
-template <bool kHead>
+// kHead = false: FC1 (A = q.a1, K blocks = kc1, W = w1, bias b1) -> q.a2 in the packed layout.
+// kHead = true : FC2 (A = q.a2, 16 K blocks, W = w2, bias b2) -> head, sampling, outputs.
+// kTwo  = false: one pass over K with the whole 512-column accumulator; both epilogue groups drain it afterwards (FC1).
+// kTwo  = true : TWO passes over K, one per N half (FC2, round 2): the head makes that epilogue long (512 x 6 FMAs per row),
+//                and with one pass the tensor pipe idled under it (26 % of the burst peak against FC1's 62 %).  Now epilogue
+//                group h drains half h while the K loop of the other half — or of the next tile's half — runs; the A block
+//                is fetched twice (16 KB of the 48 KB per step), which also makes the ring three stages deep in the same
+//                shared memory.  Measured: hidden-512 forward of cramped_room 0.492 -> 0.405 ms per 32,768 rows.  FC1 streams
+//                three times the weights and sits near the L2 bound: two passes cost it 2-4 %, it keeps one.
+template <bool kHead, bool kTwo>
 __global__ void __launch_bounds__(kGThreads, 1) gemm512_kernel(const P5Params q) {
+    constexpr int kPasses = kTwo ? 2 : 1;                           // N halves computed one after the other
+    constexpr int kWPass = kWBlk / kPasses;                         // weight bytes per K step and pass (hi | lo)
+    constexpr int kStageBytes = kABlk + kWPass;
+    constexpr int kStages = kTwo ? 3 : kGStages;
+    static_assert(kStages * kStageBytes <= kGStages * (kABlk + kWBlk), "operand ring exceeds its shared memory");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
     const PolicyParams& prm = q.base;
@@ -297,7 +310,9 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm512_kernel(const P5Params q)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 32) {
-        for (int i = 0; i < G5_COUNT; ++i) mbar_init(bars + 8 * i, i == G5_D_EMPTY ? 32 * kEpiWarps : 1);
+        // accumulator EMPTY: one pass -> both groups (256 threads) on slot 0; two passes -> group h (128 threads) on slot h
+        for (int i = 0; i < G5_COUNT; ++i)
+            mbar_init(bars + 8 * i, (i >= G5_D_EMPTY && i < G5_D_EMPTY + 2) ? (kTwo ? 128 : 32 * kEpiWarps) : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
@@ -320,12 +335,19 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm512_kernel(const P5Params q)
                 const float* gb = reinterpret_cast<const float*>(blob + (kHead ? L.b2 : L.b1));
                 for (int i = et; i < kH5; i += 256) s_bias[i] = gb[i];
                 if (kHead) {
+                    // blob: wh [8][512] (a-major) then bh [8].  Staged hidden-major [512][8] for the actor (two 16-byte
+                    // broadcast loads per hidden unit instead of six scalar ones), as it is ([512]) for the critic.
                     const float* gw = reinterpret_cast<const float*>(blob + L.wh);
-                    for (int i = et; i < 8 * kH5 + 8; i += 256) s_wh[i] = gw[i];  // wh [8][512] then bh (contiguous in the blob)
+                    if (ur.net == 0) {
+                        for (int i = et; i < 8 * kH5; i += 256) s_wh[(i & (kH5 - 1)) * 8 + (i >> 9)] = gw[i];
+                    } else {
+                        for (int i = et; i < kH5; i += 256) s_wh[i] = gw[i];
+                    }
+                    for (int i = et; i < 8; i += 256) s_wh[8 * kH5 + i] = gw[8 * kH5 + i];
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
             }
-            mbar_wait(bars + 8 * G5_D_FULL, u & 1);
+            mbar_wait(bars + 8 * (G5_D_FULL + (kTwo ? g : 0)), u & 1);
             tc_fence_after();
             float head[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             uint8_t* blk0 = q.a2 + ((size_t)ur.net * prm.tiles + t) * kKc2 * kABlk;
@@ -333,9 +355,9 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm512_kernel(const P5Params q)
             for (int b = 0; b < 8; ++b) {
                 float v[32];
                 tmem_ld32(trow + g * 256 + b * 32, v);
-                if (b == 7) {  // the accumulator is in registers: the MMA may start the next unit
+                if (b == 7) {  // the accumulator (half) is in registers: the MMA may overwrite it
                     tc_fence_before();
-                    mbar_arrive(bars + 8 * G5_D_EMPTY);
+                    mbar_arrive(bars + 8 * (G5_D_EMPTY + (kTwo ? g : 0)));
                 }
                 const int n0 = g * 256 + b * 32;
                 if (!kHead) {
@@ -344,21 +366,37 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm512_kernel(const P5Params q)
                     for (int i = 0; i < 16; ++i)
                         split2(fmaxf(v[2 * i] + s_bias[n0 + 2 * i], 0.0f), fmaxf(v[2 * i + 1] + s_bias[n0 + 2 * i + 1], 0.0f), hi[i], lo[i]);
                     store_packed32(blk0 + (size_t)(n0 / kKc) * kABlk, r, hi, lo);
-                } else {
+                } else if (ur.net == 0) {
+                    const float4* w4 = reinterpret_cast<const float4*>(s_wh) + 2 * n0;
+                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + n0);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float h = fmaxf(v[i] + s_bias[n0 + i], 0.0f);
-                        if (ur.net == 0) {
+                    for (int qd = 0; qd < 8; ++qd) {
+                        const float4 bb = b4[qd];
+                        const float bq[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                            for (int a = 0; a < 6; ++a) head[a] = fmaf(h, s_wh[a * kH5 + n0 + i], head[a]);
-                        } else {
-                            head[0] = fmaf(h, s_wh[n0 + i], head[0]);
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = 4 * qd + k;
+                            const float h = fmaxf(v[i] + bq[k], 0.0f);
+                            const float4 wa = w4[2 * i], wb = w4[2 * i + 1];
+                            head[0] = fmaf(h, wa.x, head[0]), head[1] = fmaf(h, wa.y, head[1]), head[2] = fmaf(h, wa.z, head[2]);
+                            head[3] = fmaf(h, wa.w, head[3]), head[4] = fmaf(h, wb.x, head[4]), head[5] = fmaf(h, wb.y, head[5]);
                         }
+                    }
+                } else {
+                    const float4* w4 = reinterpret_cast<const float4*>(s_wh + n0);
+                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + n0);
+#pragma unroll
+                    for (int qd = 0; qd < 8; ++qd) {
+                        const float4 bb = b4[qd], w = w4[qd];
+                        head[0] = fmaf(fmaxf(v[4 * qd + 0] + bb.x, 0.0f), w.x, head[0]);
+                        head[0] = fmaf(fmaxf(v[4 * qd + 1] + bb.y, 0.0f), w.y, head[0]);
+                        head[0] = fmaf(fmaxf(v[4 * qd + 2] + bb.z, 0.0f), w.z, head[0]);
+                        head[0] = fmaf(fmaxf(v[4 * qd + 3] + bb.w, 0.0f), w.w, head[0]);
                     }
                 }
             }
             if (kHead) {
-                // group 1 hands its partial sums to group 0 (same rows: warps w and w + 4), double-buffered by unit parity
+                // group 1 hands its partial sums to group 0 (same rows: warps w and w + 4)
                 float* xrow = s_xbuf + (size_t)r * 8;
                 if (g == 1) {
                     *reinterpret_cast<float4*>(xrow) = make_float4(head[0], head[1], head[2], head[3]);
@@ -388,53 +426,65 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm512_kernel(const P5Params q)
         const uint32_t idesc = make_idesc(kRows, 256);
         uint32_t it = 0, u = 0;
         for (int t = ur.t0; t < ur.t1; ++t, ++u) {
-            if (u > 0) mbar_wait(bars + 8 * G5_D_EMPTY, (u - 1) & 1);
-            for (int kc = 0; kc < KC; ++kc, ++it) {
-                const uint32_t s = it % kGStages;
-                mbar_wait(bars + 8 * (G5_FULL + s), (it / kGStages) & 1);
-                tc_fence_after();
-                const uint32_t a_hi = s_stage0 + s * (kABlk + kWBlk), a_lo = a_hi + kABlk / 2;
-                const uint32_t b_hi = a_hi + kABlk, b_lo = b_hi + kWBlk / 2;
-                if (elect_one()) {
+#pragma unroll 1
+            for (int pass = 0; pass < kPasses; ++pass) {
+                // the accumulator columns of this pass have been drained by their epilogue group(s)
+                if (u > 0) mbar_wait(bars + 8 * (G5_D_EMPTY + pass), (u - 1) & 1);
+                for (int kc = 0; kc < KC; ++kc, ++it) {
+                    const uint32_t s = it % kStages;
+                    mbar_wait(bars + 8 * (G5_FULL + s), (it / kStages) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = s_stage0 + s * kStageBytes, a_lo = a_hi + kABlk / 2;
+                    const uint32_t b_hi = a_hi + kABlk, b_lo = b_hi + kWPass / 2;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const uint64_t dahi = make_desc(a_hi + ks * 256, 128, 512), dalo = make_desc(a_lo + ks * 256, 128, 512);
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const uint64_t dahi = make_desc(a_hi + ks * 256, 128, 512), dalo = make_desc(a_lo + ks * 256, 128, 512);
 #pragma unroll
-                        for (int nh = 0; nh < 2; ++nh) {
-                            const uint32_t dst = tmem + nh * 256;
-                            const uint32_t boff = (uint32_t)nh * (256 / 8) * 512 + ks * 256;  // 32 row groups per N half
-                            const uint64_t dbhi = make_desc(b_hi + boff, 128, 512), dblo = make_desc(b_lo + boff, 128, 512);
-                            umma_bf16_ss(dst, dahi, dbhi, idesc, (kc | ks) != 0 ? 1u : 0u);
-                            umma_bf16_ss(dst, dahi, dblo, idesc, 1);
-                            umma_bf16_ss(dst, dalo, dbhi, idesc, 1);
+                            for (int nh = 0; nh < 2 / kPasses; ++nh) {  // one pass: both N halves from one 64 KB block
+                                const uint32_t dst = tmem + (kPasses == 2 ? pass : nh) * 256;
+                                const uint32_t boff = (uint32_t)nh * (256 / 8) * 512 + ks * 256;  // 32 row groups per N half
+                                const uint64_t dbhi = make_desc(b_hi + boff, 128, 512), dblo = make_desc(b_lo + boff, 128, 512);
+                                umma_bf16_ss(dst, dahi, dbhi, idesc, (kc | ks) != 0 ? 1u : 0u);
+                                umma_bf16_ss(dst, dahi, dblo, idesc, 1);
+                                umma_bf16_ss(dst, dalo, dbhi, idesc, 1);
+                            }
                         }
+                        umma_commit(bars + 8 * (G5_EMPTY + s));
+                        if (kc + 1 == KC) umma_commit(bars + 8 * (G5_D_FULL + pass));
                     }
-                    umma_commit(bars + 8 * (G5_EMPTY + s));
-                    if (kc + 1 == KC) umma_commit(bars + 8 * G5_D_FULL);
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else {
-        // ---- producer: one activation block and one weight block per K step
+        // ---- producer: one activation block and one weight block (one pass: 64 KB; two passes: the pass's N half, hi and lo)
         const uint8_t* A = kHead ? q.a2 : q.a1;
         uint32_t it = 0;
         for (int t = ur.t0; t < ur.t1; ++t) {
             const uint8_t* blob = prm.blobs + ((size_t)tile_pol(prm, t) * 2 + ur.net) * prm.blob_stride;
             const uint8_t* a_src = A + ((size_t)ur.net * prm.tiles + t) * KC * kABlk;
-            for (int kc = 0; kc < KC; ++kc, ++it) {
-                const uint32_t s = it % kGStages;
-                if (it >= kGStages) mbar_wait(bars + 8 * (G5_EMPTY + s), ((it / kGStages) - 1) & 1);
-                if (elect_one()) {
-                    const uint32_t fb = bars + 8 * (G5_FULL + s);
-                    const uint32_t dst = s_stage0 + s * (kABlk + kWBlk);
-                    mbar_arrive_expect_tx(fb, kABlk + kWBlk);
-                    bulk_g2s(dst, a_src + (size_t)kc * kABlk, kABlk, fb);
-                    const uint8_t* w_src = blob + w_off + (size_t)kc * kWBlk;
+#pragma unroll 1
+            for (int pass = 0; pass < kPasses; ++pass) {
+                for (int kc = 0; kc < KC; ++kc, ++it) {
+                    const uint32_t s = it % kStages;
+                    if (it >= kStages) mbar_wait(bars + 8 * (G5_EMPTY + s), ((it / kStages) - 1) & 1);
+                    if (elect_one()) {
+                        const uint32_t fb = bars + 8 * (G5_FULL + s);
+                        const uint32_t dst = s_stage0 + s * kStageBytes;
+                        mbar_arrive_expect_tx(fb, kStageBytes);
+                        bulk_g2s(dst, a_src + (size_t)kc * kABlk, kABlk, fb);
+                        const uint8_t* w_src = blob + w_off + (size_t)kc * kWBlk;
+                        if (kPasses == 2) {  // rows 256 pass .. of the hi block and of the lo block (16 KB each, contiguous)
+                            bulk_g2s(dst + kABlk, w_src + (size_t)pass * (kWBlk / 4), kWBlk / 4, fb);
+                            bulk_g2s(dst + kABlk + kWBlk / 4, w_src + kWBlk / 2 + (size_t)pass * (kWBlk / 4), kWBlk / 4, fb);
+                        } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) bulk_g2s(dst + kABlk + i * (kWBlk / 4), w_src + (size_t)i * (kWBlk / 4), kWBlk / 4, fb);
+                            for (int i = 0; i < 4; ++i) bulk_g2s(dst + kABlk + i * (kWBlk / 4), w_src + (size_t)i * (kWBlk / 4), kWBlk / 4, fb);
+                        }
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     }

@@ -1664,8 +1664,8 @@ extern "C" int ocb_policy_create(const ocb_config* cfg, int device, int hidden, 
     if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(rollout_fused_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(conv512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(gemm512_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(gemm512_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(gemm512_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(gemm512_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (err != cudaSuccess) {
         cudaGetLastError();
         ocb_policy_destroy(p);
@@ -1770,8 +1770,10 @@ static int policy_launch512(ocb_policy* p, PolicyParams& prm, cudaStream_t strea
         ctas = prm.tiles < p->sm_count ? prm.tiles : p->sm_count;
     }
     conv512_kernel<<<ctas, kThreads, c5_smem_layout(p->npos, p->stage_stride).total, stream>>>(q);
-    gemm512_kernel<false><<<ctas, kGThreads, g5_smem_layout().total, stream>>>(q);
-    gemm512_kernel<true><<<ctas, kGThreads, g5_smem_layout().total, stream>>>(q);
+    // FC1 in one pass over K (two passes measured 2-4 % slower there: it streams 3 x the weights of FC2 and sits near the L2
+    // bound), FC2 + head in two (policy512.cuh)
+    gemm512_kernel<false, false><<<ctas, kGThreads, g5_smem_layout().total, stream>>>(q);
+    gemm512_kernel<true, true><<<ctas, kGThreads, g5_smem_layout().total, stream>>>(q);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(OCB_ERR_CUDA, "hidden-512 policy launch failed: %s", cudaGetErrorString(err));
     p->calls += 1;
