@@ -10,9 +10,9 @@
 //   conv512_kernel : loader_role (shared with the h=64 kernels) -> per-cell bf16 blocks in TMEM -> per
 //                    position two N=128 accumulates (A from TMEM, B = resident conv weights, 147 KB of shared
 //                    memory) -> bias/ReLU -> hi/lo split -> stores in the packed operand layout of FC1;
-//   gemm512_kernel : C[128 x 512] = A[128 x K] W^T; A and W arrive as pre-packed [rows x 32] canonical
-//                    K-major blocks (hi | lo), one 16 KB + one 64 KB cp.async.bulk per K step into a 2-stage
-//                    ring, 12 tcgen05.mma (SS mode, M128 N256 K16; 3 products hi.hi + hi.lo + lo.hi) per step,
+//   gemm512_kernel : C[128 x 512] = A[128 x K] W^T; A and W arrive as pre-packed [rows x 16] canonical
+//                    K-major blocks (hi | lo), 8 KB + 32 KB of cp.async.bulk per K step into a 4-stage
+//                    ring, 6 tcgen05.mma (SS mode, M128 N256 K16; 3 products hi.hi + hi.lo + lo.hi) per step,
 //                    the whole 512-column accumulator in TMEM; epilogue = bias/ReLU/split -> packed stores
 //                    (FC1) or the head, sampling and outputs (FC2).
 // Every operand block is stored in HBM exactly as the MMA reads it from shared memory (8-row x 16-byte
@@ -22,11 +22,15 @@
 constexpr int kH5 = 512;                       // hidden size
 constexpr int kCo5 = 256;                      // conv output channels
 constexpr int kCw5 = kCo5 * kK1 * 2;           // 73,728 B: conv weights [256 x 144] bf16 canonical, hi (or lo)
-constexpr int kKc = 32;                        // K extent of one packed block
-constexpr int kABlk = 2 * kRows * kKc * 2;     // 16 KB: activations [128 x 32] bf16 canonical, hi | lo
-constexpr int kWBlk = 2 * kH5 * kKc * 2;       // 64 KB: weights [512 x 32] bf16 canonical, hi | lo
-constexpr int kKc2 = kH5 / kKc;                // 16 K blocks of FC2
-constexpr int kGStages = 2;                    // operand ring of gemm512_kernel
+// K extent of one packed block = one MMA step.  (32 until round 2: with 80 KB per ring stage only two stages fit, and FC1 —
+// whose K loop is 48-126 blocks long — ran at 5.5 TB/s of L2 reads where the three-stage FC2 reached 8.9: it was bound by the
+// depth of its ring, not by L2 bandwidth.  Halving the block doubles the stages in the same shared memory.)
+constexpr int kKc = 16;
+constexpr int kKSbo = kKc / 8 * 128;           // bytes between 8-row groups of a packed block
+constexpr int kABlk = 2 * kRows * kKc * 2;     // 8 KB: activations [128 x 16] bf16 canonical, hi | lo
+constexpr int kWBlk = 2 * kH5 * kKc * 2;       // 32 KB: weights [512 x 16] bf16 canonical, hi | lo
+constexpr int kKc2 = kH5 / kKc;                // 32 K blocks of FC2
+constexpr int kGStages = 5;                    // operand ring of gemm512_kernel (one pass: 5 x 40 KB; two passes: six stages of 24 KB)
 constexpr int kGWarpMma = kEpiWarps, kGWarpProd = kEpiWarps + 1;
 constexpr int kGThreads = 32 * (kEpiWarps + 2);  // 320
 constexpr int kC5ColD1 = 192;                  // conv accumulators: half h at + 128 h
@@ -34,7 +38,7 @@ constexpr int kC5ColD1 = 192;                  // conv accumulators: half h at +
 // packed weight blob of one network (device): all offsets are multiples of 128
 struct Blob5 {
     size_t wc_hi, wc_lo, bias1, w1, b1, w2, b2, wh, bh, total;
-    int kc1;  // K blocks of FC1 = 256 npos / 32
+    int kc1;  // K blocks of FC1 = 256 npos / kKc
 };
 __host__ __device__ inline Blob5 blob5_layout(int npos) {
     Blob5 L;
@@ -69,14 +73,16 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t da, uint6
         : "memory");
 }
 
-// thread `r` (tile row) stores 32 consecutive K values (hi/lo packed pairs) into block `blk` of the packed
-// operand layout: [r/8][k8][r%8][8 x bf16]; a warp writes full 128-byte segments
+// thread `r` (tile row) stores 32 consecutive K values (hi/lo packed pairs) into the two consecutive blocks at `blk` of the
+// packed operand layout: per block [r/8][k8][r%8][8 x bf16] (hi half, then lo half); a warp writes full 128-byte segments
 __device__ __forceinline__ void store_packed32(uint8_t* blk, int r, const uint32_t (&hi)[16], const uint32_t (&lo)[16]) {
-    uint8_t* p = blk + (r >> 3) * (kKc / 8 * 128) + (r & 7) * 16;
+    static_assert(kKc == 16, "two blocks of 16 per call");
+    uint8_t* p = blk + (r >> 3) * kKSbo + (r & 7) * 16;
 #pragma unroll
     for (int k8 = 0; k8 < 4; ++k8) {
-        *reinterpret_cast<uint4*>(p + k8 * 128) = make_uint4(hi[4 * k8], hi[4 * k8 + 1], hi[4 * k8 + 2], hi[4 * k8 + 3]);
-        *reinterpret_cast<uint4*>(p + k8 * 128 + kABlk / 2) = make_uint4(lo[4 * k8], lo[4 * k8 + 1], lo[4 * k8 + 2], lo[4 * k8 + 3]);
+        uint8_t* d = p + (k8 >> 1) * kABlk + (k8 & 1) * 128;
+        *reinterpret_cast<uint4*>(d) = make_uint4(hi[4 * k8], hi[4 * k8 + 1], hi[4 * k8 + 2], hi[4 * k8 + 3]);
+        *reinterpret_cast<uint4*>(d + kABlk / 2) = make_uint4(lo[4 * k8], lo[4 * k8 + 1], lo[4 * k8 + 2], lo[4 * k8 + 3]);
     }
 }
 
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv512_kernel(const P5Params q) 
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         split2(fmaxf(v[2 * i] + bias[2 * i], 0.0f), fmaxf(v[2 * i + 1] + bias[2 * i + 1], 0.0f), hi[i], lo[i]);
-                    store_packed32(blk0 + (size_t)(p * 8 + g * 4 + b) * kABlk, r, hi, lo);
+                    store_packed32(blk0 + (size_t)(p * 8 + g * 4 + b) * 2 * kABlk, r, hi, lo);
                 }
             }
             mbar_arrive(bars + 8 * (C5_W_EMPTY + (u & 1)));  // done with bias1 of this unit
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv512_kernel(const P5Params q) 
 
 // ---------------------------------------------------------------- gemm512_kernel
 // Barrier slots (8 bytes each): operand ring FULL / EMPTY [3 each], accumulator FULL / EMPTY per N half [2 each]
-enum : int { G5_FULL = 0, G5_EMPTY = 3, G5_D_FULL = 6, G5_D_EMPTY = 8, G5_COUNT = 10, G5_TMEM_SLOT = 12 };
+enum : int { G5_FULL = 0, G5_EMPTY = 6, G5_D_FULL = 12, G5_D_EMPTY = 14, G5_COUNT = 16, G5_TMEM_SLOT = 20 };
 struct G5Smem {
     int stages, xbuf, bias, wh, bars, total;
 };
@@ -266,26 +272,25 @@ __host__ __device__ inline G5Smem g5_smem_layout() {
     s.xbuf = o, o += kRows * 8 * 4;
     s.bias = o, o += kH5 * 4;
     s.wh = o, o += 8 * kH5 * 4 + 128;  // head weights (FC2: hidden-major [512][8], see below) + head bias
-    s.bars = o, o += 128;
+    s.bars = o, o += 256;
     s.total = o + 128;
     return s;
 }
 
 // kHead = false: FC1 (A = q.a1, K blocks = kc1, W = w1, bias b1) -> q.a2 in the packed layout.
-// kHead = true : FC2 (A = q.a2, 16 K blocks, W = w2, bias b2) -> head, sampling, outputs.
+// kHead = true : FC2 (A = q.a2, 32 K blocks, W = w2, bias b2) -> head, sampling, outputs.
 // kTwo  = false: one pass over K with the whole 512-column accumulator; both epilogue groups drain it afterwards (FC1).
 // kTwo  = true : TWO passes over K, one per N half (FC2, round 2): the head makes that epilogue long (512 x 6 FMAs per row),
 //                and with one pass the tensor pipe idled under it (26 % of the burst peak against FC1's 62 %).  Now epilogue
 //                group h drains half h while the K loop of the other half — or of the next tile's half — runs; the A block
-//                is fetched twice (16 KB of the 48 KB per step), which also makes the ring three stages deep in the same
-//                shared memory.  Measured: hidden-512 forward of cramped_room 0.492 -> 0.405 ms per 32,768 rows.  FC1 streams
+//                is fetched twice (8 KB of the 24 KB per step), and the ring is six stages deep in the same shared memory.  Measured: hidden-512 forward of cramped_room 0.492 -> 0.405 ms per 32,768 rows.  FC1 streams
 //                three times the weights and sits near the L2 bound: two passes cost it 2-4 %, it keeps one.
 template <bool kHead, bool kTwo>
 __global__ void __launch_bounds__(kGThreads, 1) gemm512_kernel(const P5Params q) {
     constexpr int kPasses = kTwo ? 2 : 1;                           // N halves computed one after the other
     constexpr int kWPass = kWBlk / kPasses;                         // weight bytes per K step and pass (hi | lo)
     constexpr int kStageBytes = kABlk + kWPass;
-    constexpr int kStages = kTwo ? 3 : kGStages;
+    constexpr int kStages = kTwo ? 6 : kGStages;
     static_assert(kStages * kStageBytes <= kGStages * (kABlk + kWBlk), "operand ring exceeds its shared memory");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((128u - (smem_addr(smem_raw) & 127u)) & 127u);
@@ -365,7 +370,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm512_kernel(const P5Params q)
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         split2(fmaxf(v[2 * i] + s_bias[n0 + 2 * i], 0.0f), fmaxf(v[2 * i + 1] + s_bias[n0 + 2 * i + 1], 0.0f), hi[i], lo[i]);
-                    store_packed32(blk0 + (size_t)(n0 / kKc) * kABlk, r, hi, lo);
+                    store_packed32(blk0 + (size_t)(n0 / kKc) * kABlk, r, hi, lo);  // n0 is a multiple of 32: two blocks
                 } else if (ur.net == 0) {
                     const float4* w4 = reinterpret_cast<const float4*>(s_wh) + 2 * n0;
                     const float4* b4 = reinterpret_cast<const float4*>(s_bias + n0);
@@ -437,18 +442,15 @@ __global__ void __launch_bounds__(kGThreads, 1) gemm512_kernel(const P5Params q)
                     const uint32_t a_hi = s_stage0 + s * kStageBytes, a_lo = a_hi + kABlk / 2;
                     const uint32_t b_hi = a_hi + kABlk, b_lo = b_hi + kWPass / 2;
                     if (elect_one()) {
+                        const uint64_t dahi = make_desc(a_hi, 128, kKSbo), dalo = make_desc(a_lo, 128, kKSbo);
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            const uint64_t dahi = make_desc(a_hi + ks * 256, 128, 512), dalo = make_desc(a_lo + ks * 256, 128, 512);
-#pragma unroll
-                            for (int nh = 0; nh < 2 / kPasses; ++nh) {  // one pass: both N halves from one 64 KB block
-                                const uint32_t dst = tmem + (kPasses == 2 ? pass : nh) * 256;
-                                const uint32_t boff = (uint32_t)nh * (256 / 8) * 512 + ks * 256;  // 32 row groups per N half
-                                const uint64_t dbhi = make_desc(b_hi + boff, 128, 512), dblo = make_desc(b_lo + boff, 128, 512);
-                                umma_bf16_ss(dst, dahi, dbhi, idesc, (kc | ks) != 0 ? 1u : 0u);
-                                umma_bf16_ss(dst, dahi, dblo, idesc, 1);
-                                umma_bf16_ss(dst, dalo, dbhi, idesc, 1);
-                            }
+                        for (int nh = 0; nh < 2 / kPasses; ++nh) {  // one pass: both N halves from one weight block
+                            const uint32_t dst = tmem + (kPasses == 2 ? pass : nh) * 256;
+                            const uint32_t boff = (uint32_t)nh * (256 / 8) * kKSbo;  // 32 row groups per N half
+                            const uint64_t dbhi = make_desc(b_hi + boff, 128, kKSbo), dblo = make_desc(b_lo + boff, 128, kKSbo);
+                            umma_bf16_ss(dst, dahi, dbhi, idesc, kc != 0 ? 1u : 0u);
+                            umma_bf16_ss(dst, dahi, dblo, idesc, 1);
+                            umma_bf16_ss(dst, dalo, dbhi, idesc, 1);
                         }
                         umma_commit(bars + 8 * (G5_EMPTY + s));
                         if (kc + 1 == KC) umma_commit(bars + 8 * (G5_D_FULL + pass));
