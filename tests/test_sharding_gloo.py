@@ -57,7 +57,9 @@ def _worker(rank, world, port, n_pol, q):
         mean, eps = sharding.gather_pair_matrix(mine, rs, ep, n_pol)
         first, count = sharding.world_shard(1000, rank, world)
         s, n = sharding.reduce_episode_stats(torch.arange(first, first + count), torch.ones(count, dtype=torch.int32))
-        q.put((rank, mean, eps, int(s), int(n)))
+        # plain lists, not tensors: a tensor in an mp.Queue is rebuilt from a file descriptor the SENDER must still hold when the
+        # parent fetches it — a worker that had already exited made this test fail with EOFError on a loaded machine
+        q.put((rank, mean.tolist(), eps.tolist(), int(s), int(n)))
     finally:
         dist.destroy_process_group()
 
@@ -79,5 +81,5 @@ def test_gather_across_ranks_gloo(world):
                              dtype=torch.float64)
     want_eps = torch.tensor([[_stats_for((i, j))[1] for j in range(n_pol)] for i in range(n_pol)])
     for rank, mean, eps, s, n in results:  # every rank ends with the full matrix
-        assert torch.equal(mean, want_mean) and torch.equal(eps, want_eps)
+        assert torch.equal(torch.tensor(mean, dtype=torch.float64), want_mean) and torch.equal(torch.tensor(eps), want_eps)
         assert (s, n) == (sum(range(1000)), 1000)
