@@ -144,10 +144,13 @@ OCB_HD bool soup_ready(const Tables& tb, const Consts& c, uint32_t o) {
     return tp1 >= 1 && tp1 > cook_time(tb, c, o);
 }
 
-OCB_HD void tick_pot(const Tables& tb, const Consts& c, uint16_t* objs, int ostride, uint32_t pot_info) {
+// returns whether the pot's soup ticked (its plane bytes change)
+OCB_HD bool tick_pot(const Tables& tb, const Consts& c, uint16_t* objs, int ostride, uint32_t pot_info) {
     const int cell = info_cell(pot_info);
     const uint32_t o = objs[cell * ostride];
-    if (obj_name(o) == O_SOUP && soup_cooking(tb, c, o)) objs[cell * ostride] = (uint16_t)(o + 0x100u);
+    const bool cooking = obj_name(o) == O_SOUP && soup_cooking(tb, c, o);
+    if (cooking) objs[cell * ostride] = (uint16_t)(o + 0x100u);
+    return cooking;
 }
 
 // One world transition (R:381-385): resolve_interacts -> resolve_movement ->
@@ -155,9 +158,11 @@ OCB_HD void tick_pot(const Tables& tb, const Consts& c, uint16_t* objs, int ostr
 // dirty[i] receives the info word of the counter / pot cell touched by player i's
 // interact (or 0xFFFFFFFF).  Returns the team reward (sum over players;
 // envs/overcooked2_env.py:336).
+// `ticked` receives one bit per pot (index into pot0, pot1, pot_info[2..]) whose soup ticked in this step: together with
+// `dirty` these are the only cells whose dynamic plane bytes changed.
 template <int P>
 OCB_HD int step_world(const Tables& tb, const Consts& c, World<P>& w, uint16_t* objs, int ostride, const int (&act)[P],
-                      uint32_t (&dirty)[P]) {
+                      uint32_t (&dirty)[P], uint32_t& ticked) {
     int reward = 0;
     // pot snapshot "taken once before the player loop" (R:302): the running count as of step start
     const int pots_before = w.nonempty_pots;
@@ -253,9 +258,11 @@ OCB_HD int step_world(const Tables& tb, const Consts& c, World<P>& w, uint16_t* 
 
     // step_environment_effects R:373-379 (cooking soups only ever sit in pots)
     w.timestep += 1;
-    if (c.n_pots > 0) tick_pot(tb, c, objs, ostride, c.pot0);
-    if (c.n_pots > 1) tick_pot(tb, c, objs, ostride, c.pot1);
-    for (int q = 2; q < c.n_pots; ++q) tick_pot(tb, c, objs, ostride, tb.pot_info[q]);
+    uint32_t tk = 0;
+    if (c.n_pots > 0) tk |= tick_pot(tb, c, objs, ostride, c.pot0) ? 1u : 0u;
+    if (c.n_pots > 1) tk |= tick_pot(tb, c, objs, ostride, c.pot1) ? 2u : 0u;
+    for (int q = 2; q < c.n_pots; ++q) tk |= tick_pot(tb, c, objs, ostride, tb.pot_info[q]) ? (1u << (q & 31)) : 0u;
+    ticked = c.n_pots > 32 ? 0xFFFFFFFFu : tk;  // (more pots than bits: re-encode all of them)
     return reward;
 }
 
@@ -349,7 +356,7 @@ OCB_HD void obs_phase1(const Tables& tb, uint8_t* planes, int view_stride, const
 
 template <int P, int G>
 OCB_HD void obs_phase2(const Tables& tb, const Consts& c, uint8_t* planes, int view_stride, const uint16_t* objs,
-                       int ostride, bool full, int g, const World<P>& w, const uint32_t (&dirty)[P]) {
+                       int ostride, bool full, int g, const World<P>& w, const uint32_t (&dirty)[P], uint32_t ticked) {
     if (full) {
         for (int idx = g; idx < c.n_objcells; idx += G) {
             const uint32_t ci = tb.cell_info[tb.objcells[idx]];
@@ -367,8 +374,12 @@ OCB_HD void obs_phase2(const Tables& tb, const Consts& c, uint8_t* planes, int v
                 if (ci != 0xFFFFFFFFu) encode_cell<P>(planes + (j % P) * view_stride, ci, objs[info_cell(ci) * ostride]);
             }
         }
+        // pots whose soup ticked (a pot that was interacted with is among the dirty cells above; an idle, a full-but-unstarted
+        // or a finished pot keeps its bytes): with random actions pots rarely cook, and re-encoding every pot in every view
+        // every step was a tenth of the per-step dependent chain
         for (int j = g; j < c.n_pots * P; j += G) {
             const int q = j / P;
+            if (!((ticked >> (q & 31)) & 1u)) continue;
             const uint32_t ci = q == 0 ? c.pot0 : q == 1 ? c.pot1 : tb.pot_info[q];
             encode_cell<P>(planes + (j % P) * view_stride, ci, objs[info_cell(ci) * ostride]);
         }

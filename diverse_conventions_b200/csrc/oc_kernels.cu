@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, (G == 8 ? 6 : 4)) oc_rollout_k
         uint32_t dirty[P];
 #pragma unroll
         for (int i = 0; i < P; ++i) oldslot[i] = w.slot[i];
-        const int r = step_world<P>(tb, c, w, myobjs, 32, act, dirty);
+        uint32_t ticked;
+        const int r = step_world<P>(tb, c, w, myobjs, 32, act, dirty, ticked);
         const bool done = w.timestep >= c.horizon;  // envs/overcooked2_env.py:334
         cur_return += r;
         if (done) {  // auto-reset, pantheonrl_extension/vectorenv.py:369-370
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, (G == 8 ? 6 : 4)) oc_rollout_k
             obs_phase1<P, G>(tb, myplanes, view_stride, tmpl, rebuild1 || done, g, oldslot);
             rebuild1 = false;
             __syncwarp();
-            obs_phase2<P, G>(tb, c, myplanes, view_stride, myobjs, 32, full, g, w, dirty);
+            obs_phase2<P, G>(tb, c, myplanes, view_stride, myobjs, 32, full, g, w, dirty, ticked);
             if (tma_ok) {
                 fence_proxy_async_smem();  // generic-proxy pokes -> visible to the async proxy
                 __syncwarp();
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(kThreadsPerCta) oc_observe_kernel(const Rollou
     else
         obs_phase1<P, G>(tb, myplanes, view_stride, tmpl, true, g, noslot);
     __syncwarp();
-    obs_phase2<P, G>(tb, c, myplanes, view_stride, myobjs, 32, true, g, w, nodirty);
+    obs_phase2<P, G>(tb, c, myplanes, view_stride, myobjs, 32, true, g, w, nodirty, 0u);
     __syncwarp();
     const int nbytes = nvalid * SC;
 #pragma unroll

@@ -265,6 +265,7 @@ __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s
         bool full = true;
         int oldslot[P] = {0, 0};
         uint32_t dirty[P] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+        uint32_t ticked = 0;
         // the planes still hold the slot's previous virtual tile: its loaders and its bulk store must be done with them (both
         // finish long before the actions arrive, so these waits sit before the action wait, off the critical path)
         if (q.vts > 0) mbar_wait(bars + 8 * (FB_OBS_EMPTY + slot), (q.vts - 1) & 1);
@@ -285,7 +286,7 @@ __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s
             act[0] = s_act[slot * 128 + ew * 32 + lane], act[1] = s_act[slot * 128 + kFWorlds + ew * 32 + lane];
 #pragma unroll
             for (int i = 0; i < P; ++i) oldslot[i] = q.w.slot[i];
-            const int r = step_world<P>(tb, c, q.w, myobjs, 32, act, dirty);
+            const int r = step_world<P>(tb, c, q.w, myobjs, 32, act, dirty, ticked);
             const bool done = q.w.timestep >= c.horizon;
             q.cur_return += r;
             if (done) {
@@ -309,7 +310,7 @@ __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s
         __syncwarp();
         if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)q.vts, 2);
         obs_phase1<P, 1>(tb, myplanes, view_stride, tmpl, full, 0, oldslot);
-        obs_phase2<P, 1>(tb, c, myplanes, view_stride, myobjs, 32, full, 0, q.w, dirty);
+        obs_phase2<P, 1>(tb, c, myplanes, view_stride, myobjs, 32, full, 0, q.w, dirty, ticked);
         mbar_arrive(bars + 8 * (FB_OBS_FULL + slot));  // release: the loaders may read this lane's planes
         if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)q.vts, 3);
         ++q.vts;

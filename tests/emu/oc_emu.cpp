@@ -73,6 +73,7 @@ int rollout(const Tables& tb, const uint8_t* tmpl, int32_t* state, int N, int K,
         for (int k = 0; k < K; ++k, ++t) {
             int oldslot[32][P];
             uint32_t dirty[32][P];
+            uint32_t ticked[32] = {};
             bool full[32];
             // transition: the G lanes of a world run in lockstep -> emulate by letting only the
             // first lane of each world touch the shared object array and copying its registers
@@ -93,7 +94,7 @@ int rollout(const Tables& tb, const uint8_t* tmpl, int32_t* state, int N, int K,
                 if (actions_out && n < N)
                     for (int i = 0; i < P; ++i) actions_out[((size_t)k * P + i) * N + n] = (uint8_t)act[i];
                 for (int i = 0; i < P; ++i) oldslot[lane][i] = w[lane].slot[i];
-                const int r = step_world<P>(tb, c, w[lane], objs.data() + wi, WPW, act, dirty[lane]);
+                const int r = step_world<P>(tb, c, w[lane], objs.data() + wi, WPW, act, dirty[lane], ticked[lane]);
                 const bool d = w[lane].timestep >= c.horizon;
                 cur_ret[lane] += r;
                 if (d) {
@@ -107,6 +108,7 @@ int rollout(const Tables& tb, const uint8_t* tmpl, int32_t* state, int N, int K,
                     rng[lane + g] = rng[lane];
                     full[lane + g] = full[lane];
                     for (int i = 0; i < P; ++i) oldslot[lane + g][i] = oldslot[lane][i], dirty[lane + g][i] = dirty[lane][i];
+                    ticked[lane + g] = ticked[lane];
                 }
                 if (n < N) {
                     if (rew)
@@ -120,7 +122,7 @@ int rollout(const Tables& tb, const uint8_t* tmpl, int32_t* state, int N, int K,
                                      oldslot[lane]);
                 for (int lane = 0; lane < 32; ++lane)  // phase 2
                     obs_phase2<P, G>(tb, c, planes.data() + (lane / G) * SC, view_stride, objs.data() + lane / G, WPW,
-                                     full[lane], lane % G, w[lane], dirty[lane]);
+                                     full[lane], lane % G, w[lane], dirty[lane], ticked[lane]);
                 for (int v = 0; v < P; ++v)
                     memcpy(obs + (((size_t)k * P + v) * N + n0) * SC, planes.data() + (size_t)v * view_stride,
                            (size_t)nvalid * SC);
