@@ -1,5 +1,7 @@
-// rollout_fused.cuh — the whole T-step self-play rollout in ONE persistent launch (included by
+// rollout_fused.cuh — a whole T-step self-play or cross-play rollout in ONE persistent launch (included by
 // policy_kernels.cu inside its anonymous namespace, after the pair kernel whose roles it reuses).
+// Variants (FusedParams): one or two world tiles in flight per CTA (`slots`), split mode (the critic's conv stream deferred
+// behind the actor's; one tile in flight, whole grid resident in TMEM), cross-play (`cross`: two actors, seat-selected rows).
 //
 // The 2T+1-launch rollout (ocb_rollout_policy) is bound by its dependent launches: per env step a
 // policy launch and an env launch, each of which fills and drains the GPU for one tile per SM.
