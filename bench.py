@@ -614,8 +614,9 @@ def run_ours(args):
     achieved = bytes_ws * N * spl / (launch_ms * 1e-3) / 1e9
     tuning = env.get_tuning()
     # (kernel name without the closing bracket: the K-step instance carries a third template argument since round 2)
-    traffic = ncu_traffic_bytes("oc_rollout_kernel<%d, %d" % (P, tuning["lanes_per_world"])) \
-        if (N, spl, args.layout) == (WORLDS_PER_GPU, 100, LAYOUT) else None
+    kernel_name = "oc_rollout_split_kernel" if tuning["lanes_per_world"] == 16 else \
+        "oc_rollout_kernel<%d, %d" % (P, tuning["lanes_per_world"])  # 16 = the role-split kernel (ocb_set_tuning)
+    traffic = ncu_traffic_bytes(kernel_name) if (N, spl, args.layout) == (WORLDS_PER_GPU, 100, LAYOUT) else None
     # The GPUs of the pool differ: the same binary streams 0.206-0.226 ms per launch from box to box.  A plain device copy
     # on THIS GPU (1 GiB read + 1 GiB written per iteration, CUDA events) says how much of that is the box.
     box_copy = None
@@ -705,7 +706,7 @@ def run_ours(args):
                 "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
-                             "kernel": "oc_rollout_kernel<%d,%d>" % (P, tuning["lanes_per_world"]), "tuning": tuning,
+                             "kernel": kernel_name.replace(", ", ",") + (">" if "<" in kernel_name else ""), "tuning": tuning,
                              "bytes_per_world_step": bytes_ws, "world_steps_per_launch": N * spl,
                              "launch_ms": launch_ms, "launches_timed": max(len(per_launch) - 1, 1),
                              "launch_ms_first": per_launch[0], "peak_source": peaks["source"],

@@ -167,68 +167,68 @@ OCB_HD int step_world(const Tables& tb, const Consts& c, World<P>& w, uint16_t* 
     // pot snapshot "taken once before the player loop" (R:302): the running count as of step start
     const int pots_before = w.nonempty_pots;
 
-    // resolve_interacts: players in index order on live state (R:305-353)
+    // resolve_interacts: players in index order on live state (R:305-353).
+    // Written as straight-line selects, not as the reference's if / else tree: a warp holds 32 different worlds, so a
+    // branchy version executes every arm of the tree one after the other anyway (~1,200 cycles of a 2,200-cycle
+    // transition), while here the arms are independent dataflow the scheduler overlaps, and the dependent chain is the
+    // handful of operations from a player's target object to its new value.  Only the load / store of the target cell
+    // are predicated.  Arm by arm the values are those of the tree (each predicate below names its reference lines).
+    uint32_t fci[P];  // the cell each player faces, from the pose at step start (R:309-310: interacts never move anyone)
+#pragma unroll
+    for (int i = 0; i < P; ++i) fci[i] = tb.cell_info[w.pos[i] + dir_delta(w.orient[i], c.dpack)];
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-        dirty[i] = 0xFFFFFFFFu;
-        if (act[i] != A_INTERACT) continue;
-        const uint32_t ci = tb.cell_info[w.pos[i] + dir_delta(w.orient[i], c.dpack)];  // pre-move pose, R:309-310
+        const bool inter = act[i] == A_INTERACT;
+        const uint32_t ci = fci[i];
         const int t = info_terrain(ci);
         const int tgt = info_cell(ci);
         const uint32_t h = w.held[i];
-        if (t == T_COUNTER) {  // R:313-319
-            const uint32_t o = objs[tgt * ostride];
-            if (h != 0u && o == 0u) {
-                objs[tgt * ostride] = (uint16_t)h;
-                w.held[i] = 0u;
-                w.counter_dishes += (obj_name(h) == O_DISH);
-            } else if (h == 0u && o != 0u) {
-                w.held[i] = o;
-                objs[tgt * ostride] = 0;
-                w.counter_dishes -= (obj_name(o) == O_DISH);
-            }
-            dirty[i] = ci;
-        } else if (t == T_POT) {  // R:331-349
-            if (h != 0u) {
-                const uint32_t o0 = objs[tgt * ostride];
-                uint32_t o = o0;
-                const int hn = obj_name(h);
-                if (hn == O_DISH && o != 0u && soup_ready(tb, c, o)) {  // R:332-336
-                    w.held[i] = o;
-                    o = 0u;
-                    reward += c.rew_soup;
-                } else if (hn == O_ONION || hn == O_TOMATO) {  // R:337-349
-                    if (o == 0u) o = obj_make(O_SOUP, 0, 0, -1);
-                    if (!(obj_tickp1(o) >= 1 || obj_ingredients(o) == 3)) {
-                        o += (hn == O_ONION) ? (1u << 5) : (1u << 3);
-                        w.held[i] = 0u;
-                        reward += c.rew_place;
-                    }
-                    // soup_to_be_cooked_at_location (R:287-296) and full -> auto start
-                    if (obj_name(o) == O_SOUP && obj_tickp1(o) == 0 && obj_ingredients(o) == 3) o |= (1u << 8);
-                }
-                objs[tgt * ostride] = (uint16_t)o;
-                w.nonempty_pots += pot_counts(o) - pot_counts(o0);
-                dirty[i] = ci;
-            }
-        } else if (h == 0u) {  // the three dispensers only serve empty hands (R:320-327)
-            if (t == T_ONION_SRC) {
-                w.held[i] = obj_make(O_ONION, 0, 0, -1);
-            } else if (t == T_TOMATO_SRC) {
-                w.held[i] = obj_make(O_TOMATO, 0, 0, -1);
-            } else if (t == T_DISH_SRC) {  // is_dish_pickup_useful R:261-270
-                if (P == 2) {
-                    int held_dishes = 0;
+        const int hn = obj_name(h);
+        const bool is_counter = inter && t == T_COUNTER;        // R:313-319
+        const bool is_pot = inter && t == T_POT && h != 0u;     // R:331-349 (empty hands do nothing at a pot)
+        uint32_t o = 0u;
+        if (is_counter || is_pot) o = objs[tgt * ostride];
+        const int on = obj_name(o);
+        const bool c_place = is_counter && h != 0u && o == 0u;
+        const bool c_pick = is_counter && h == 0u && o != 0u;
+        const bool p_take = is_pot && hn == O_DISH && o != 0u && soup_ready(tb, c, o);        // R:332-336
+        const bool p_ingr = is_pot && (hn == O_ONION || hn == O_TOMATO);                      // R:337-349
+        uint32_t o2 = (o == 0u) ? obj_make(O_SOUP, 0, 0, -1) : o;
+        const bool p_add = p_ingr && !(obj_tickp1(o2) >= 1 || obj_ingredients(o2) == 3);
+        o2 += p_add ? ((hn == O_ONION) ? (1u << 5) : (1u << 3)) : 0u;
+        // soup_to_be_cooked_at_location (R:287-296) and full -> auto start
+        o2 |= (obj_name(o2) == O_SOUP && obj_tickp1(o2) == 0 && obj_ingredients(o2) == 3) ? (1u << 8) : 0u;
+        const bool free_hands = inter && h == 0u;  // the three dispensers only serve empty hands (R:320-327)
+        const bool d_onion = free_hands && t == T_ONION_SRC, d_tomato = free_hands && t == T_TOMATO_SRC;
+        const bool d_dish = free_hands && t == T_DISH_SRC;
+        const bool serve = inter && t == T_SERVING && hn == O_SOUP;  // R:350-353, deliver_soup R:283-285
+
+        uint32_t newo = c_place ? h : o;
+        newo = (c_pick || p_take) ? 0u : newo;
+        newo = p_ingr ? o2 : newo;
+        if (c_place || c_pick || is_pot) objs[tgt * ostride] = (uint16_t)newo;
+
+        reward += p_take ? c.rew_soup : 0;
+        reward += p_add ? c.rew_place : 0;
+        if (P == 2) {  // is_dish_pickup_useful R:261-270 (held objects as they are now: earlier players already acted)
+            int held_dishes = 0;
 #pragma unroll
-                    for (int j = 0; j < P; ++j) held_dishes += (obj_name(w.held[j]) == O_DISH);
-                    if (w.counter_dishes == 0 && held_dishes < pots_before) reward += c.rew_dish;
-                }
-                w.held[i] = obj_make(O_DISH, 0, 0, -1);
-            }
-        } else if (t == T_SERVING && obj_name(h) == O_SOUP) {  // R:350-353, deliver_soup R:283-285
-            reward += tb.rvalue[obj_recipe(h)];
-            w.held[i] = 0u;
+            for (int j = 0; j < P; ++j) held_dishes += (obj_name(w.held[j]) == O_DISH);
+            reward += (d_dish && w.counter_dishes == 0 && held_dishes < pots_before) ? c.rew_dish : 0;
         }
+        const int served = tb.rvalue[obj_recipe(h)];  // (index 0..15 whatever h is)
+        reward += serve ? served : 0;
+
+        uint32_t nh = (c_place || p_add || serve) ? 0u : h;
+        nh = (c_pick || p_take) ? o : nh;
+        nh = d_onion ? obj_make(O_ONION, 0, 0, -1) : nh;
+        nh = d_tomato ? obj_make(O_TOMATO, 0, 0, -1) : nh;
+        nh = d_dish ? obj_make(O_DISH, 0, 0, -1) : nh;
+        w.held[i] = nh;
+        w.counter_dishes += (c_place && hn == O_DISH) ? 1 : 0;
+        w.counter_dishes -= (c_pick && on == O_DISH) ? 1 : 0;
+        w.nonempty_pots += is_pot ? pot_counts(newo) - pot_counts(o) : 0;
+        dirty[i] = (is_counter || is_pot) ? ci : 0xFFFFFFFFu;
     }
 
     // resolve_movement R:368-371, _move_if_direction R:393-399

@@ -38,6 +38,8 @@ struct RolloutParams {
     int32_t* rew;          // [K][P][N] or nullptr
     int32_t* done;         // [K][N] or nullptr
     int use_tma;
+    int tile_worlds;  // worlds per warp tile (one-warp kernel: <= 32 / G) resp. per group (split kernel: <= 32); 0 = full
+                      // tiles.  Narrower tiles spread a launch evenly over all SMs (see ocb_api.cu: balanced_tile)
     unsigned long long* step_counter;  // device mirror of the global step counter (+= K per launch) or nullptr
 };
 
@@ -45,6 +47,9 @@ size_t rollout_smem_bytes(int P, int S, int C, int G, int warps_per_cta);
 
 cudaError_t launch_rollout(const RolloutParams& prm, int P, int G, int warps_per_cta, size_t smem_bytes,
                            bool observe_only, cudaStream_t stream);
+// role-split K-step kernel (P = 2, <= 2 pots, observations wanted): GE encoder warps per transition warp, TW groups per CTA
+size_t rollout_split_smem_bytes(int S, int C, int TW, int tile_worlds);
+cudaError_t launch_rollout_split(const RolloutParams& prm, int GE, int TW, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_counter_add(unsigned long long* counter, unsigned long long k, cudaStream_t stream);
 cudaError_t launch_reset(const Tables* tables, uint32_t* players, uint16_t* objs, int32_t* timestep, int32_t* cur_return,
                          int N, int rows, cudaStream_t stream);

@@ -41,6 +41,7 @@ struct ocb_env {
     int lanes_per_world;  // G of the fused K-step launches
     int step_lanes;       // G of single-step / observe launches (load + full rebuild dominate there)
     int use_tma;
+    int sm_count;
     Tables h_tables;
     // device
     Tables* d_tables;
@@ -81,6 +82,14 @@ static int default_lanes(int N, int SC) {
     if (N < 16384) return big ? 2 : 4;
     return big ? 2 : 1;
 }
+// ... unless the role-split kernel serves the env (two players, at most two pots): below 16,384 worlds a launch is bound
+// by the latency of a world's step, and the split kernel's step is the transition alone.  tools/gpu_split_defaults.sh
+// (profiles/r2g_split_defaults.jsonl), ms per 100 steps, split against the best one-warp shape: cramped_room 1,024 / 4,096
+// / 8,192 / 12,288 worlds 0.105 / 0.106 / 0.113 / 0.174 against 0.154 / 0.157 / 0.158 / 0.174; coordination_ring 0.109 /
+// 0.109 / 0.148 / 0.217 against 0.162 / 0.166 / 0.166 / 0.215; asymmetric_advantages (900-byte planes) 0.142 / 0.134
+// against 0.172 / 0.173 up to 4,096 worlds and a tie (0.257 / 0.253) at 8,192.  From 16,384 worlds on the one-warp shapes
+// stay (cramped_room 0.199 against 0.227-0.235).
+static bool split_is_default(int N, int SC) { return SC >= 800 ? N <= 4096 : N < 16384; }
 
 // lanes per world of single-step / observe launches.  The planes of a tile are rebuilt by one bulk copy per view
 // (tile_fill_begin), so what is left per world is the state load and the sequential transition: from a few thousand worlds
@@ -88,6 +97,41 @@ static int default_lanes(int N, int SC) {
 // 144 / 160 / 190 at 4 / 8 / 1; 32,768 worlds 21.1 against 23.3 / 27.4 / 23.4; 8,192 worlds of cramped_room 10.3 against
 // 10.9 / 11.4 / 13.0); below that the launch is latency-bound (10 us) and more lanes hide the transition better.
 static int default_step_lanes(int N) { return N >= 4096 ? 2 : 8; }
+
+// lanes_per_world == kLanesSplit selects the role-split K-step kernel (oc_rollout_split_kernel: a transition warp and GE
+// encoder warps per 32 worlds).  It serves two players and at most two pots and only launches that write observations;
+// every other launch of such an env falls back to the one-warp-does-all kernel with `fallback_lanes`.
+constexpr int kLanesSplit = 16;
+static bool split_supported(const ocb_env* e) { return e->P == 2 && e->h_tables.n_pots <= 2; }
+static int fallback_lanes(const ocb_env* e) { return default_lanes(e->N, e->SC); }
+static int default_lanes_env(const ocb_env* e) {
+    if (split_supported(e) && split_is_default(e->N, e->SC) && rollout_split_smem_bytes(e->S, e->C, 1, 32) <= 200 * 1024)
+        return kLanesSplit;
+    return default_lanes(e->N, e->SC);
+}
+// Worlds per tile of a K-step launch: full tiles (32 / G worlds per warp; 32 per group of the role-split kernel).
+// Narrower tiles would spread a launch more evenly over the SMs (16,384 worlds in 32-world groups are four CTAs on some
+// SMs and three on others) and the kernels take any width (`RolloutParams::tile_worlds`), but measured (tools/gpu_tile.sh,
+// profiles/r2g_tile_sweep.jsonl) they do not pay: widths whose planes are not a whole number of 128-byte lines lose 15 %
+// (a tile starting inside a line shares it with a neighbour that another SM writes at another time), 8-world groups halve
+// the throughput, and 16-world groups gain 3 % at 16,384 worlds while losing 1 % at 8,192.  OCB_TILE_WORLDS narrows the
+// tiles for the parity tests of that code path and for experiments.
+static int tile_worlds_for(int full) {
+    if (const char* ev = getenv("OCB_TILE_WORLDS")) {
+        const int v = atoi(ev);
+        if (v >= 1) return v < full ? v : full;
+    }
+    return full;
+}
+
+static void split_shape(const ocb_env* e, int* GE, int* TW) {
+    *GE = e->SC >= 800 ? 4 : 2, *TW = 1;  // encoder lanes per world (tools/gpu_split_defaults.sh)
+    if (const char* ev = getenv("OCB_SPLIT_GE")) {  // tuning experiments only
+        const int v = atoi(ev);
+        if (v == 2 || v == 4) *GE = v;
+    }
+    (void)e;
+}
 
 static int pick_launch_shape(const ocb_env* e, int G, int* warps, size_t* smem) {
     // 4 warps per CTA measured best on B200 even when that leaves some SMs without a CTA
@@ -172,9 +216,13 @@ extern "C" int ocb_create(const ocb_config* cfg, int device, uint32_t num_worlds
     e->P = e->h_tables.P, e->S = e->h_tables.S, e->C = e->h_tables.C, e->SC = e->h_tables.SC;
     e->L = 1 + 6 * e->P + 4 * e->S;
     e->seed = seed;
-    e->lanes_per_world = default_lanes(e->N, e->SC);
+    e->lanes_per_world = default_lanes_env(e);
     e->step_lanes = default_step_lanes(e->N);
     e->use_tma = 1;
+    if (cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || e->sm_count < 1) {
+        cudaGetLastError();
+        e->sm_count = 148;
+    }
 
     DeviceGuard guard(device);
     const size_t N = num_worlds;
@@ -212,7 +260,7 @@ extern "C" int ocb_create(const ocb_config* cfg, int device, uint32_t num_worlds
 #undef OCB_TRY
     int warps;
     size_t smem;
-    rc = pick_launch_shape(e, e->lanes_per_world, &warps, &smem);
+    rc = pick_launch_shape(e, e->lanes_per_world == kLanesSplit ? fallback_lanes(e) : e->lanes_per_world, &warps, &smem);
     if (rc != OCB_OK) {
         ocb_destroy(e);
         return rc;
@@ -259,15 +307,23 @@ extern "C" uint64_t ocb_step_count(const ocb_env* e) {
 extern "C" int ocb_set_tuning(ocb_env* e, int lanes_per_world, int use_tma) {
     if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "env is NULL");
     const bool explicit_lanes = lanes_per_world != 0;
-    if (lanes_per_world == 0) lanes_per_world = default_lanes(e->N, e->SC);
-    if (lanes_per_world != 1 && lanes_per_world != 2 && lanes_per_world != 4 && lanes_per_world != 8)
-        return fail(OCB_ERR_INVALID_ARG, "lanes_per_world must be 1, 2, 4 or 8");
+    if (lanes_per_world == 0) lanes_per_world = default_lanes_env(e);
+    if (lanes_per_world != 1 && lanes_per_world != 2 && lanes_per_world != 4 && lanes_per_world != 8 &&
+        lanes_per_world != kLanesSplit)
+        return fail(OCB_ERR_INVALID_ARG, "lanes_per_world must be 1, 2, 4, 8 or 16 (role-split kernel)");
+    if (lanes_per_world == kLanesSplit) {
+        if (!split_supported(e))
+            return fail(OCB_ERR_UNSUPPORTED, "the role-split kernel serves 2 players and at most 2 pots (P=%d, pots=%d)", e->P,
+                        e->h_tables.n_pots);
+        if (rollout_split_smem_bytes(e->S, e->C, 1, 32) > 200 * 1024)
+            return fail(OCB_ERR_UNSUPPORTED, "layout needs more shared memory than one SM has (S=%d, role-split kernel)", e->S);
+    }
     int warps;
     size_t smem;
-    int rc = pick_launch_shape(e, lanes_per_world, &warps, &smem);
+    int rc = pick_launch_shape(e, lanes_per_world == kLanesSplit ? fallback_lanes(e) : lanes_per_world, &warps, &smem);
     if (rc != OCB_OK) return rc;
     e->lanes_per_world = lanes_per_world;
-    e->step_lanes = explicit_lanes ? lanes_per_world : default_step_lanes(e->N);
+    e->step_lanes = (explicit_lanes && lanes_per_world != kLanesSplit) ? lanes_per_world : default_step_lanes(e->N);
     e->use_tma = use_tma ? 1 : 0;
     return OCB_OK;
 }
@@ -276,8 +332,13 @@ extern "C" int ocb_get_tuning(const ocb_env* e, int* lanes_per_world, int* use_t
     if (e == nullptr) return fail(OCB_ERR_INVALID_ARG, "env is NULL");
     int warps = 0;
     size_t smem = 0;
-    int rc = pick_launch_shape(e, e->lanes_per_world, &warps, &smem);
+    int rc = pick_launch_shape(e, e->lanes_per_world == kLanesSplit ? fallback_lanes(e) : e->lanes_per_world, &warps, &smem);
     if (rc != OCB_OK) return rc;
+    if (e->lanes_per_world == kLanesSplit) {  // warps of one CTA of the split kernel
+        int GE, TW;
+        split_shape(e, &GE, &TW);
+        warps = TW * (1 + GE);
+    }
     if (lanes_per_world) *lanes_per_world = e->lanes_per_world;
     if (use_tma) *use_tma = e->use_tma;
     if (warps_per_cta) *warps_per_cta = warps;
@@ -327,10 +388,21 @@ static int run_rollout(ocb_env* e, int K, const void* actions, int act_dtype, in
     size_t smem;
     // single steps are dominated by the state load and the full plane rebuild: spread each world over
     // more lanes there (tools/step_latency.py); fused launches use the throughput-tuned shape
-    const int G = (observe_only || K <= 2) ? e->step_lanes : e->lanes_per_world;
-    int rc = pick_launch_shape(e, G, &warps, &smem);
-    if (rc != OCB_OK) return rc;
-    cudaError_t err = launch_rollout(p, e->P, G, warps, smem, observe_only, (cudaStream_t)stream);
+    int G = (observe_only || K <= 2) ? e->step_lanes : e->lanes_per_world;
+    const bool split = G == kLanesSplit && obs != nullptr;
+    if (G == kLanesSplit) G = fallback_lanes(e);
+    cudaError_t err;
+    if (split) {
+        int GE, TW;
+        split_shape(e, &GE, &TW);
+        p.tile_worlds = tile_worlds_for(32);
+        err = launch_rollout_split(p, GE, TW, rollout_split_smem_bytes(e->S, e->C, TW, p.tile_worlds), (cudaStream_t)stream);
+    } else {
+        int rc = pick_launch_shape(e, G, &warps, &smem);
+        if (rc != OCB_OK) return rc;
+        if (!observe_only && K > 2) p.tile_worlds = tile_worlds_for(32 / G);
+        err = launch_rollout(p, e->P, G, warps, smem, observe_only, (cudaStream_t)stream);
+    }
     if (err != cudaSuccess) {
         cudaGetLastError();
         return fail(OCB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(err));

@@ -112,8 +112,10 @@ int ocb_obs_channels(const ocb_env* env);         /* C = 5P + 10 */
 int ocb_obs_bytes_per_agent(const ocb_env* env);  /* W*H*C */
 int ocb_state_ints_per_world(const ocb_env* env); /* length of one packed world state */
 
-/* kernel tuning knobs: lanes_per_world in {1,2,4,8} (0 = default by world count),
- * use_tma in {0,1} (default 1: TMA bulk stores of the observation tiles) */
+/* kernel tuning knobs: lanes_per_world in {1,2,4,8} — lanes that serve one world in the one-warp kernel — or 16, the
+ * role-split kernel (a transition warp + encoder warps per 32 worlds; two players and at most two pots, else
+ * OCB_ERR_UNSUPPORTED; launches it does not serve — single steps, no observations — use the one-warp kernel);
+ * 0 = default by layout and world count.  use_tma in {0,1} (default 1: TMA bulk stores of the observation tiles) */
 int ocb_set_tuning(ocb_env* env, int lanes_per_world, int use_tma);
 /* the launch shape currently in effect (any out pointer may be NULL) */
 int ocb_get_tuning(const ocb_env* env, int* lanes_per_world, int* use_tma, int* warps_per_cta);

@@ -15,13 +15,18 @@ from test_random_layout_golden import load_case, seeds
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("G,tma", [(0, 1), (1, 0), (2, 1), (4, 1), (8, 0)])
+@pytest.mark.parametrize("G,tma", [(0, 1), (1, 0), (2, 1), (4, 1), (8, 0), (16, 1)])
 @pytest.mark.parametrize("seed", seeds())
 def test_fused_launches_replay_the_reference_on_random_layouts(golden_dir, seed, G, tma):
     g, k, d, horizon, lp = load_case(golden_dir, seed)
     N, P, K = 37, lp.num_players, g[k + "actions"].shape[0]
     env = B200Overcooked("random%d" % seed, N, 0, horizon=horizon, layout_params=lp)
-    env.set_tuning(G, bool(tma))
+    try:
+        env.set_tuning(G, bool(tma))
+    except RuntimeError as exc:  # 16 = role-split kernel: two players, at most two pots
+        if G == 16 and "role-split" in str(exc):
+            pytest.skip("role-split kernel does not serve this layout")
+        raise
     first = torch.stack([v.obs for v in env.n_reset()]).cpu().numpy()
     assert np.array_equal(first[:, 0], g[k + "reset_obs"]) and np.array_equal(first[:, N - 1], g[k + "reset_obs"])
     acts = torch.from_numpy(g[k + "actions"].astype(np.int32))[:, :, None].repeat(1, 1, N).cuda()

@@ -38,6 +38,9 @@ def main():
     ap.add_argument("--worlds", default="16384,65536,262144")
     ap.add_argument("--T", type=int, default=100)
     ap.add_argument("--passes", type=int, default=20)
+    ap.add_argument("--lanes", default="1,2,4,8,16", help="16 = role-split kernel (OCB_SPLIT_GE / OCB_SPLIT_TW pick its shape)")
+    ap.add_argument("--quick", action="store_true", help="TMA + observations only")
+    ap.add_argument("--tma", default="1,0")
     args = ap.parse_args()
     rows = []
     for layout in args.layouts.split(","):
@@ -45,15 +48,18 @@ def main():
         bws = layouts.io_bytes_per_world_step(lp)
         for N in [int(x) for x in args.worlds.split(",")]:
             T = args.T if N * lp.size * lp.channels * 2 * args.T < 8e9 else max(1, int(8e9 / (N * lp.size * lp.channels * 2)))
-            for G in (1, 2, 4, 8):
-                for tma in (1, 0):
+            for G in [int(x) for x in args.lanes.split(",")]:
+                for tma in [int(x) for x in args.tma.split(",")]:
                     for obs in (True, False):
                         if not obs and not tma:
+                            continue
+                        if args.quick and not obs:
                             continue
                         ms = time_config(layout, N, G, tma, T, args.passes, obs)
                         gsteps = 2 * N * T / (ms * 1e-3) / 1e9
                         gbs = bws * N * T / (ms * 1e-3) / 1e9 if obs else 0.0
                         row = dict(layout=layout, N=N, T=T, G=G, tma=tma, obs=obs, ms=round(ms, 4),
+                                   split_ge=os.environ.get("OCB_SPLIT_GE", ""), split_tw=os.environ.get("OCB_SPLIT_TW", ""),
                                    Gagent_steps_s=round(gsteps, 3), GBs=round(gbs, 1), frac=round(gbs / 6550.1, 3))
                         rows.append(row)
                         print(json.dumps(row), flush=True)
