@@ -619,7 +619,7 @@ def run_ours(args):
     traffic = ncu_traffic_bytes(kernel_name) if (N, spl, args.layout) == (WORLDS_PER_GPU, 100, LAYOUT) else None
     # The GPUs of the pool differ: the same binary streams 0.206-0.226 ms per launch from box to box.  A plain device copy
     # on THIS GPU (1 GiB read + 1 GiB written per iteration, CUDA events) says how much of that is the box.
-    box_copy = box_write = None
+    box_copy = None
     try:
         src = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
         dst = torch.empty_like(src)
@@ -632,19 +632,10 @@ def run_ours(args):
         c1.record()
         torch.cuda.synchronize()
         box_copy = 2 * 10 * float(1 << 30) / (c0.elapsed_time(c1) * 1e-3) / 1e9
-        # the hot kernel only WRITES: a write-only stream (cudaMemset-style fill of 1 GiB) of this GPU beside the copy figure
-        for _ in range(3):
-            dst.zero_()
-        c0.record()
-        for _ in range(10):
-            dst.zero_()
-        c1.record()
-        torch.cuda.synchronize()
-        box_write = 10 * float(1 << 30) / (c0.elapsed_time(c1) * 1e-3) / 1e9
         del src, dst
         torch.cuda.empty_cache()
     except Exception:
-        box_copy = box_write = None
+        box_copy = None
 
     # ---- end-to-end: the reference-facing single-step call with host buffers
     E = max(args.e2e_steps, 10)
@@ -722,10 +713,10 @@ def run_ours(args):
                              "box_copy_gbs": box_copy, "frac_of_box_copy": (achieved / box_copy) if box_copy else None,
                              "box_copy_note": "torch device-to-device copy of 1 GiB on this GPU (read + written bytes / time): "
                                               "the box's own streaming rate beside the pool-wide peak",
-                             "box_write_gbs": box_write, "frac_of_box_write": (achieved / box_write) if box_write else None,
-                             "box_write_note": "write-only fill of 1 GiB on this GPU: the kernel reads nothing, so it can (and "
-                                               "on fast boxes does) exceed the copy-derived peak; tools/probes/store_probe.cu: "
-                                               "128 SMs writing reach 7.2-7.3 TB/s on a fast box, 6.6 on a slow one"},
+                             "write_only_note": "the kernel reads nothing, so it can (and on fast boxes does) exceed the copy-derived "
+                                                "peak: tools/probes/store_probe.cu (profiles/r2g_store_probe.jsonl) measured "
+                                                "7.2-7.3 TB/s for 128 SMs writing on a fast box of the pool, 6.6 on a slow one, and "
+                                                "at most 62.7 GB/s (32 B/clk) per SM"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "call": "ocb_step_host_async + ocb_step_host_wait (two steps in flight: D2H of step t under the H2D + "
                                 "kernel of step t + 1); 1 launch / step, obs + reward + done to pinned host memory every step",
