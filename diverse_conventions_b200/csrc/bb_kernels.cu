@@ -58,7 +58,83 @@ __device__ inline void bb_reset_world(BBWorld& w, uint64_t seed, uint32_t world,
     w.episode += 1;
 }
 
-__device__ inline int bb_move(int a) { return a == 0 ? -2 : a == 1 ? -1 : a == 2 ? 1 : 2; }  // B:14
+// The reset stream inside the K-step loop.  Lanes end their (one- to three-step) episodes at different steps, so with the
+// cached block above some lane of the warp needed a new Philox block on nearly every step and the whole warp walked
+// through the ten rounds each time.  Here every lane keeps the block it draws from (`cur`) AND computes the next one a few
+// rounds per step (`advance`, the same straight-line code on every lane and step, independent of the transition's chain):
+// a block serves four episodes of one or two steps each (seven steps on average), two rounds per step complete the next
+// block within five, and the rare lane that gets there earlier (four one-step episodes in a row) runs the missing rounds
+// in `reset`.  Same words as ActionRng::refill.
+struct BBResetStream {
+    static constexpr int kRoundsPerStep = 2;
+    uint32_t cur[4], nxt[4];
+    uint32_t cur_block, k0, k1;  // block index of `cur` (`nxt` is cur_block + 1); Philox key of nxt's next round
+    int rounds;                  // rounds of `nxt` done so far
+
+    __device__ __forceinline__ void start_next(uint64_t seed, uint32_t world) {
+        const uint64_t s = seed ^ kResetStream;
+        const uint64_t block = (uint64_t)cur_block + 1;
+        nxt[0] = world, nxt[1] = (uint32_t)block, nxt[2] = (uint32_t)(block >> 32), nxt[3] = 0u;
+        k0 = (uint32_t)s, k1 = (uint32_t)(s >> 32);
+        rounds = 0;
+    }
+    __device__ __forceinline__ void round() {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, nxt[0]), lo0 = 0xD2511F53u * nxt[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, nxt[2]), lo1 = 0xCD9E8D57u * nxt[2];
+        const uint32_t n0 = hi1 ^ nxt[1] ^ k0, n2 = hi0 ^ nxt[3] ^ k1;
+        nxt[0] = n0, nxt[1] = lo1, nxt[2] = n2, nxt[3] = lo0;
+        k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+        ++rounds;
+    }
+    __device__ __forceinline__ void advance() {
+#pragma unroll
+        for (int q = 0; q < kRoundsPerStep; ++q)
+            if (rounds < 10) round();
+    }
+    __device__ __forceinline__ void init(uint64_t seed, uint32_t world, uint32_t episode) {
+        ActionRng<2> r;
+        r.refill(seed ^ kResetStream, world, (uint64_t)episode);
+        cur_block = episode / ActionRng<2>::kStepsPerBlock;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cur[q] = r.r[q];
+        start_next(seed, world);
+        while (rounds < 10) round();
+    }
+    // B:141-149, as bb_reset_world
+    __device__ __forceinline__ void reset(BBWorld& w, uint64_t seed, uint32_t world) {
+        const uint32_t block = w.episode / ActionRng<2>::kStepsPerBlock;
+        if (block != cur_block) {  // == cur_block + 1: episodes count up by one
+            while (rounds < 10) round();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
+            cur_block = block;
+            start_next(seed, world);
+        }
+        const int h = (int)(w.episode % ActionRng<2>::kStepsPerBlock) * 2;  // 16-bit slices h, h + 1 of the block
+        const uint32_t lo = (h & 2) ? cur[1] : cur[0], hi = (h & 2) ? cur[3] : cur[2];
+        const uint32_t word = (h & 4) ? hi : lo;
+        w.loc[0] = (int)(((word & 0xFFFFu) * (uint32_t)kSpaces) >> 16);
+        w.loc[1] = (int)(((word >> 16) * (uint32_t)kSpaces) >> 16);
+        w.time = kTime - 1;
+        w.hist[0][0] = w.hist[0][1] = w.hist[1][0] = w.hist[1][1] = 0;
+        w.episode += 1;
+    }
+};
+
+__device__ inline int bb_move(int a) { return a - 2 + (a >> 1); }  // B:14: [-2, -1, 1, 2][a], a in 0..3, without branches
+
+// Rewards (B:129-137) are Python floats (fp64) narrowed to float32 by the tensor they are written into.  For every value
+// the env can produce — |loc0 - loc1| in 0..8 and the out-of-bounds penalty -SPACES * (time + 1) * 0.2 — the float32
+// product is the same float, so the kernel multiplies in float32 (the fp64 multiply and its two conversions were 4 % of the
+// kernel's instructions); checked here at compile time.
+constexpr bool bb_rewards_match_fp64() {
+    for (int d = 1; d <= 8; ++d)
+        if ((float)(-(double)d * 0.2) != -(float)d * 0.2f) return false;
+    for (int t = 0; t <= kTime; ++t)
+        if ((float)((double)(-kSpaces * (t + 1)) * 0.2) != (float)(-kSpaces * (t + 1)) * 0.2f) return false;
+    return true;
+}
+static_assert(bb_rewards_match_fp64(), "float32 rewards differ from the reference's fp64-then-narrowed ones");
 
 struct BBParams {
     uint32_t* state;
@@ -85,10 +161,22 @@ __device__ inline void bb_write_obs(const BBWorld& w, int32_t* tile /* [2][32*7]
     }
 }
 
-__device__ inline void bb_flush_obs(const int32_t* tile, int32_t* obs, size_t k, int N, int n0, int nvalid, int lane) {
+// `vec`: full tile and 16-byte aligned rows (N % 4 == 0): the 224 ints of a view leave as 56 16-byte stores
+// `obs`: this tile's rows of view 0 of the step; view 1 follows N rows later
+__device__ inline void bb_flush_obs(const int32_t* tile, int32_t* obs, int N, int nvalid, int lane, bool vec) {
+    if (vec) {
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            uint4* dst = reinterpret_cast<uint4*>(obs + (size_t)v * N * 7);
+            const uint4* src = reinterpret_cast<const uint4*>(tile + v * 224);
+            __stcs(dst + lane, src[lane]);
+            if (lane < 24) __stcs(dst + 32 + lane, src[32 + lane]);
+        }
+        return;
+    }
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
-        int32_t* dst = obs + ((k * 2 + v) * (size_t)N + n0) * 7;
+        int32_t* dst = obs + (size_t)v * N * 7;
         const int cnt = nvalid * 7;
 #pragma unroll
         for (int j = 0; j < 7; ++j) {
@@ -99,7 +187,7 @@ __device__ inline void bb_flush_obs(const int32_t* tile, int32_t* obs, size_t k,
 }
 
 __global__ void __launch_bounds__(256) bb_kernel(const BBParams prm) {
-    __shared__ int32_t tiles[8][2 * 224];
+    __shared__ __align__(16) int32_t tiles[8][2 * 224];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n0 = (blockIdx.x * 8 + warp) * 32;
     const int N = prm.N;
@@ -116,31 +204,42 @@ __global__ void __launch_bounds__(256) bb_kernel(const BBParams prm) {
     const uint32_t gworld = prm.world0 + (uint32_t)nl;
     ActionRng<2> reset_rng;
     uint32_t reset_block = 0xFFFFFFFFu;  // no block cached (episode counters stay far below 2^34)
+    const bool vec = nvalid == 32 && (N & 3) == 0 && (reinterpret_cast<uintptr_t>(prm.obs) & 15u) == 0;
 
     if (prm.mode != 0) {
         if (prm.mode == 2) bb_reset_world(w, prm.seed, gworld, reset_rng, reset_block);
         if (prm.obs != nullptr) {
             bb_write_obs(w, tile, lane);
             __syncwarp();
-            bb_flush_obs(tile, prm.obs, 0, N, n0, nvalid, lane);
+            bb_flush_obs(tile, prm.obs + (size_t)n0 * 7, N, nvalid, lane, vec);
         }
     } else {
         ActionRng<2> rng;
         unsigned long long t = prm.step0;
         const bool use_rng = prm.actions == nullptr;
         if (use_rng && (t % ActionRng<2>::kStepsPerBlock) != 0) rng.refill(prm.seed, gworld, t);
+        BBResetStream rs;
+        rs.init(prm.seed, gworld, w.episode);
+        // per-lane output cursors, advanced by one step's stride each iteration (no 64-bit multiplies in the loop)
+        const size_t PN = 2 * (size_t)N;
+        const int32_t* act_ptr = use_rng ? nullptr : prm.actions + nl;
+        uint8_t* aout_ptr = (prm.actions_out != nullptr && valid) ? prm.actions_out + n : nullptr;
+        float* rew_ptr = (prm.rew != nullptr && valid) ? prm.rew + n : nullptr;
+        int32_t* done_ptr = (prm.done != nullptr && valid) ? prm.done + n : nullptr;
+        int32_t* obs_ptr = prm.obs != nullptr ? prm.obs + (size_t)n0 * 7 : nullptr;
         for (int k = 0; k < prm.K; ++k, ++t) {
+            rs.advance();
             int a0, a1;
             if (use_rng) {
                 if ((t % ActionRng<2>::kStepsPerBlock) == 0) rng.refill(prm.seed, gworld, t);
                 a0 = rng.action(t, 0, 4), a1 = rng.action(t, 1, 4);
             } else {
-                a0 = prm.actions[((size_t)k * 2 + 0) * N + nl] & 3;
-                a1 = prm.actions[((size_t)k * 2 + 1) * N + nl] & 3;
+                a0 = act_ptr[0] & 3, a1 = act_ptr[N] & 3;
+                act_ptr += PN;
             }
-            if (prm.actions_out != nullptr && valid) {
-                prm.actions_out[((size_t)k * 2 + 0) * N + n] = (uint8_t)a0;
-                prm.actions_out[((size_t)k * 2 + 1) * N + n] = (uint8_t)a1;
+            if (aout_ptr != nullptr) {
+                aout_ptr[0] = (uint8_t)a0, aout_ptr[N] = (uint8_t)a1;
+                aout_ptr += PN;
             }
             // B:123-139
             w.hist[0][1] = w.hist[0][0], w.hist[0][0] = w.loc[0] + kBuffer;
@@ -148,26 +247,27 @@ __global__ void __launch_bounds__(256) bb_kernel(const BBParams prm) {
             w.loc[0] += bb_move(a0);
             w.loc[1] += bb_move(a1);
             w.time -= 1;
-            bool d = (w.time == 0);
             const int diff = abs(w.loc[0] - w.loc[1]);
-            double r = (diff == 0) ? 1.0 : -(double)diff * 0.2;  // fp64 then narrowed, as Python does
-            if (w.loc[0] < 0 || w.loc[0] >= kSpaces || w.loc[1] < 0 || w.loc[1] >= kSpaces) {
-                d = true;
-                r = (double)(-kSpaces * (w.time + 1)) * 0.2;
+            // (unsigned compare: loc < 0 wraps above SPACES)
+            const bool oob = (unsigned)w.loc[0] >= (unsigned)kSpaces || (unsigned)w.loc[1] >= (unsigned)kSpaces;
+            const bool d = (w.time == 0) || oob;
+            float r = (diff == 0) ? 1.0f : -(float)diff * 0.2f;  // == the reference's fp64 value narrowed (static_assert above)
+            r = oob ? (float)(-kSpaces * (w.time + 1)) * 0.2f : r;
+            if (d) rs.reset(w, prm.seed, gworld);  // pantheonrl_extension/vectorenv.py:369-370
+            if (rew_ptr != nullptr) {
+                rew_ptr[0] = r, rew_ptr[N] = r;
+                rew_ptr += PN;
             }
-            if (d) bb_reset_world(w, prm.seed, gworld, reset_rng, reset_block);  // pantheonrl_extension/vectorenv.py:369-370
-            if (valid) {
-                if (prm.rew != nullptr) {
-                    prm.rew[((size_t)k * 2 + 0) * N + n] = (float)r;
-                    prm.rew[((size_t)k * 2 + 1) * N + n] = (float)r;
-                }
-                if (prm.done != nullptr) prm.done[(size_t)k * N + n] = d ? 1 : 0;
+            if (done_ptr != nullptr) {
+                *done_ptr = d ? 1 : 0;
+                done_ptr += N;
             }
-            if (prm.obs != nullptr) {
+            if (obs_ptr != nullptr) {
                 bb_write_obs(w, tile, lane);
                 __syncwarp();
-                bb_flush_obs(tile, prm.obs, (size_t)k, N, n0, nvalid, lane);
+                bb_flush_obs(tile, obs_ptr, N, nvalid, lane, vec);
                 __syncwarp();
+                obs_ptr += PN * 7;
             }
         }
     }
