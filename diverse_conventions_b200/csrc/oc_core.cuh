@@ -298,6 +298,28 @@ OCB_HD void encode_cell(uint8_t* plane, uint32_t ci, uint32_t o) {
     px[4] = (name == O_ONION) ? 1 : 0;
 }
 
+// The same five bytes as two values: byte 0 (channel shift+5) and bytes 1..4 as one little-endian word.  They do not
+// depend on the viewer, so a caller that updates all views of a cell computes them once (`store_cell`).
+OCB_HD void cell_bytes(uint32_t ci, uint32_t o, uint32_t& b0, uint32_t& w14) {
+    const int name = obj_name(o);
+    const bool soup_in_pot = (name == O_SOUP) && (info_terrain(ci) == T_POT);
+    const int tp1 = obj_tickp1(o);
+    b0 = soup_in_pot ? (uint32_t)obj_onions(o) : 0u;
+    w14 = ((soup_in_pot && tp1 >= 1) ? (uint32_t)(tp1 - 1) : 0u) | ((name == O_SOUP && !soup_in_pot) ? (1u << 8) : 0u) |
+          ((name == O_DISH) ? (1u << 16) : 0u) | ((name == O_ONION) ? (1u << 24) : 0u);
+}
+// P == 2: the five channels are bytes 15..19 of the cell's 20 — the last byte of one aligned word and the whole next one
+template <int P>
+OCB_HD void store_cell(uint8_t* plane, uint32_t ci, uint32_t b0, uint32_t w14) {
+    uint8_t* px = plane + info_slot(ci) + 5 * P + 5;
+    px[0] = (uint8_t)b0;
+    if (P == 2) {
+        *reinterpret_cast<uint32_t*>(px + 1) = w14;
+    } else {
+        px[1] = (uint8_t)w14, px[2] = (uint8_t)(w14 >> 8), px[3] = (uint8_t)(w14 >> 16), px[4] = (uint8_t)(w14 >> 24);
+    }
+}
+
 // player i as seen by `viewer` (R:221-257): position one-hot, orientation one-hot of
 // the relative player index, held object drawn on the holder's cell
 template <int P>
@@ -363,6 +385,26 @@ OCB_HD void obs_phase2(const Tables& tb, const Consts& c, uint8_t* planes, int v
             const uint32_t o = objs[info_cell(ci) * ostride];
             if (o != 0u)
                 for (int v = 0; v < P; ++v) encode_cell<P>(planes + v * view_stride, ci, o);
+        }
+    } else if (G == 1) {
+        // one lane does all views of its world: the bytes of a touched cell are computed once and stored per view
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            const uint32_t ci = dirty[i];
+            if (ci != 0xFFFFFFFFu) {
+                uint32_t b0, w14;
+                cell_bytes(ci, objs[info_cell(ci) * ostride], b0, w14);
+#pragma unroll
+                for (int v = 0; v < P; ++v) store_cell<P>(planes + v * view_stride, ci, b0, w14);
+            }
+        }
+        for (int q = 0; q < c.n_pots; ++q) {
+            if (!((ticked >> (q & 31)) & 1u)) continue;
+            const uint32_t ci = q == 0 ? c.pot0 : q == 1 ? c.pot1 : tb.pot_info[q];
+            uint32_t b0, w14;
+            cell_bytes(ci, objs[info_cell(ci) * ostride], b0, w14);
+#pragma unroll
+            for (int v = 0; v < P; ++v) store_cell<P>(planes + v * view_stride, ci, b0, w14);
         }
     } else {
         // (interact targets + pots) x views

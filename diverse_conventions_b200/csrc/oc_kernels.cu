@@ -489,13 +489,23 @@ __global__ void __launch_bounds__(TW*(1 + GE) * 32) oc_rollout_split_kernel(cons
                 const int j = j0 + g;
                 if (j < P * P) {
                     const uint32_t d = selu<P>(dw, j / P);
-                    if (d != 0xFFFFFFFFu) encode_cell<P>(myplanes + (j % P) * view_stride, tb.cell_info[d & 0xFFu], d >> 16);
+                    if (d != 0xFFFFFFFFu) {
+                        const uint32_t ci = tb.cell_info[d & 0xFFu];
+                        uint32_t b0, w14;
+                        cell_bytes(ci, d >> 16, b0, w14);
+                        store_cell<P>(myplanes + (j % P) * view_stride, ci, b0, w14);
+                    }
                 }
             }
             for (int j = g; j < c.n_pots * P; j += GE) {
                 const int q = j / P;
                 const uint32_t o = q ? (pots >> 16) : (pots & 0xFFFFu);
-                if (o != 0u) encode_cell<P>(myplanes + (j % P) * view_stride, q ? c.pot1 : c.pot0, o);
+                if (o != 0u) {
+                    const uint32_t ci = q ? c.pot1 : c.pot0;
+                    uint32_t b0, w14;
+                    cell_bytes(ci, o, b0, w14);
+                    store_cell<P>(myplanes + (j % P) * view_stride, ci, b0, w14);
+                }
             }
         }
 #pragma unroll

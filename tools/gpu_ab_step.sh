@@ -1,14 +1,13 @@
 #!/bin/bash
-# branch-free transition + role-split kernel: parity, then same-box A/B of ab/libocb_old.so against ab/libocb_new.so
+# same-box A/B of ab/libocb_old.so against ab/libocb_new.so on the env launches and the fused rollout (parity of `new` first)
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_overcooked.py tests/test_gpu_random_layouts.py tests/test_gpu_rollout.py tests/test_gpu_mixed.py -x -q -m gpu 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_gpu_overcooked.py tests/test_gpu_random_layouts.py tests/test_gpu_rollout.py tests/test_gpu_mixed.py -x -q -m gpu 2>&1 | tail -2
 cp diverse_conventions_b200/libocb.so /tmp/libocb_keep.so
 for rep in 1 2; do for v in old new; do
   cp ab/libocb_$v.so diverse_conventions_b200/libocb.so; touch diverse_conventions_b200/libocb.so
-  L=1,4; [ $v = new ] && L=1,4,16
   echo "== $v"
-  timeout 300 python tools/sweep.py --layouts simple --worlds 8192,16384 --lanes $L --quick --tma 1 2>&1 | cut -c1-130
+  timeout 300 python tools/sweep.py --layouts simple --worlds 8192,16384 --lanes ${LANES:-1,16} --quick --tma 1 2>&1 | cut -c1-130
   timeout 300 python tools/rollout_bench.py --mode selfplay --layouts simple --worlds 8192 --T 100 --fused 1 2>&1 | tail -1 | cut -c1-260
 done; done 2>&1 | tee gpurun_out/ab_step.txt
 cp /tmp/libocb_keep.so diverse_conventions_b200/libocb.so
