@@ -374,12 +374,17 @@ def test_error_codes_through_the_abi():
 
 
 # --------------------------------------------------------------------------- full-size properties
-def test_full_size_properties_cramped_room():
-    """BASELINE config 3 size (16,384 worlds, horizon 400): size-independent properties +
+@pytest.mark.parametrize("N,lanes", [(16384, 0), (8192, 0), (16384, 16)])
+def test_full_size_properties_cramped_room(N, lanes):
+    """BASELINE config 3 size (16,384 worlds, horizon 400; default launch shape = the one-warp kernel) and config 4's
+    8,192 worlds (default = the role-split kernel), plus the split kernel forced at 16,384: size-independent properties +
     an oracle replay of a strided subset of worlds."""
-    N, H, K = 16384, 400, 100
+    H, K = 400, 100
     lp = layouts.load_layout("simple", H)
     env = make_env("simple", N, H, seed=7)
+    if lanes:
+        env.set_tuning(lanes, True)
+    assert env.get_tuning()["lanes_per_world"] == (16 if (lanes == 16 or N < 16384) else 1)
     sub = np.arange(0, N, 331)
     orc = COracle(lp, len(sub))
     total_rew = torch.zeros((), dtype=torch.int64, device="cuda")
