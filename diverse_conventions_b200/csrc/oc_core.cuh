@@ -266,6 +266,160 @@ OCB_HD int step_world(const Tables& tb, const Consts& c, World<P>& w, uint16_t* 
     return reward;
 }
 
+// ---------------------------------------------------------------- the transition in two halves (two players)
+// In the fused rollout the env warps wait most of a step for the sampled actions, and what follows the hand-off is on the
+// step's critical path.  Nearly all of step_world depends on the STATE only: which cell each player faces and what an
+// INTERACT would do there, where each of the four moves would lead, what the pots hold.  `step_pre` computes those
+// outcomes while the policy forward runs; `step_post` picks among them once the joint action is known, resolves the
+// collisions, applies the writes and ticks the pots — the same values as step_world (the emulated-kernel test and the
+// fused-vs-per-step bit-identity tests run both).
+struct InteractEval {  // what a player's INTERACT does on a given state
+    uint32_t held, newo, dirty;  // held object / faced cell's object afterwards, info word of the touched counter / pot cell
+    int reward, d_cd, d_np;      // reward, change of counter_dishes / nonempty_pots
+    bool wr;                     // the faced cell is written
+};
+// `h` = the player's held object, `o_cell` = the object on the faced cell `ci` (anything if ci is neither counter nor pot),
+// `held_dishes` / `counter_dishes` / `pots_before` as step_world sees them at this player's turn.  Same arms and
+// reference lines as the loop body of step_world.
+template <int P>
+OCB_HD InteractEval interact_eval(const Tables& tb, const Consts& c, uint32_t ci, uint32_t h, uint32_t o_cell, int held_dishes,
+                                  int counter_dishes, int pots_before) {
+    const int t = info_terrain(ci);
+    const int hn = obj_name(h);
+    const bool is_counter = t == T_COUNTER;
+    const bool is_pot = t == T_POT && h != 0u;
+    const uint32_t o = (is_counter || is_pot) ? o_cell : 0u;
+    const int on = obj_name(o);
+    const bool c_place = is_counter && h != 0u && o == 0u;
+    const bool c_pick = is_counter && h == 0u && o != 0u;
+    const bool p_take = is_pot && hn == O_DISH && o != 0u && soup_ready(tb, c, o);
+    const bool p_ingr = is_pot && (hn == O_ONION || hn == O_TOMATO);
+    uint32_t o2 = (o == 0u) ? obj_make(O_SOUP, 0, 0, -1) : o;
+    const bool p_add = p_ingr && !(obj_tickp1(o2) >= 1 || obj_ingredients(o2) == 3);
+    o2 += p_add ? ((hn == O_ONION) ? (1u << 5) : (1u << 3)) : 0u;
+    o2 |= (obj_name(o2) == O_SOUP && obj_tickp1(o2) == 0 && obj_ingredients(o2) == 3) ? (1u << 8) : 0u;
+    const bool free_hands = h == 0u;
+    const bool d_onion = free_hands && t == T_ONION_SRC, d_tomato = free_hands && t == T_TOMATO_SRC;
+    const bool d_dish = free_hands && t == T_DISH_SRC;
+    const bool serve = t == T_SERVING && hn == O_SOUP;
+    InteractEval e;
+    uint32_t newo = c_place ? h : o;
+    newo = (c_pick || p_take) ? 0u : newo;
+    newo = p_ingr ? o2 : newo;
+    e.newo = newo;
+    e.wr = c_place || c_pick || is_pot;
+    int reward = (p_take ? c.rew_soup : 0) + (p_add ? c.rew_place : 0);
+    if (P == 2) reward += (d_dish && counter_dishes == 0 && held_dishes < pots_before) ? c.rew_dish : 0;
+    const int served = tb.rvalue[obj_recipe(h)];
+    reward += serve ? served : 0;
+    e.reward = reward;
+    uint32_t nh = (c_place || p_add || serve) ? 0u : h;
+    nh = (c_pick || p_take) ? o : nh;
+    nh = d_onion ? obj_make(O_ONION, 0, 0, -1) : nh;
+    nh = d_tomato ? obj_make(O_TOMATO, 0, 0, -1) : nh;
+    nh = d_dish ? obj_make(O_DISH, 0, 0, -1) : nh;
+    e.held = nh;
+    e.d_cd = ((c_place && hn == O_DISH) ? 1 : 0) - ((c_pick && on == O_DISH) ? 1 : 0);
+    e.d_np = is_pot ? pot_counts(newo) - pot_counts(o) : 0;
+    e.dirty = (is_counter || is_pot) ? ci : 0xFFFFFFFFu;
+    return e;
+}
+
+struct StepPre2 {
+    InteractEval e0, e1a, e1b;  // player 0; player 1 if player 0 does not / does interact
+    int tgt0, tgt1;             // faced cells
+    uint32_t np[2];             // destination cell of moves NORTH..WEST, 8 bits each (own cell where the move is blocked)
+    uint32_t ns_lo[2], ns_hi[2];  // plane offsets of those cells, 16 bits each
+    uint32_t pot_o[2];          // objects in pot0 / pot1 at the start of the step
+};
+
+OCB_HD void step_pre(const Tables& tb, const Consts& c, const World<2>& w, const uint16_t* objs, int ostride, StepPre2& p) {
+    const uint32_t f0 = tb.cell_info[w.pos[0] + dir_delta(w.orient[0], c.dpack)];
+    const uint32_t f1 = tb.cell_info[w.pos[1] + dir_delta(w.orient[1], c.dpack)];
+    p.tgt0 = info_cell(f0), p.tgt1 = info_cell(f1);
+    const uint32_t o0 = objs[p.tgt0 * ostride], o1 = objs[p.tgt1 * ostride];
+    const int d0 = obj_name(w.held[0]) == O_DISH, d1 = obj_name(w.held[1]) == O_DISH;
+    p.e0 = interact_eval<2>(tb, c, f0, w.held[0], o0, d0 + d1, w.counter_dishes, w.nonempty_pots);
+    p.e1a = interact_eval<2>(tb, c, f1, w.held[1], o1, d0 + d1, w.counter_dishes, w.nonempty_pots);
+    const uint32_t o1b = (p.tgt1 == p.tgt0 && p.e0.wr) ? p.e0.newo : o1;
+    p.e1b = interact_eval<2>(tb, c, f1, w.held[1], o1b, (obj_name(p.e0.held) == O_DISH) + d1, w.counter_dishes + p.e0.d_cd,
+                             w.nonempty_pots);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        uint32_t cells = 0u, lo = 0u, hi = 0u;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const uint32_t ci = tb.cell_info[w.pos[i] + dir_delta(a, c.dpack)];
+            const bool walk = info_terrain(ci) == T_AIR;
+            const uint32_t cell = walk ? (uint32_t)info_cell(ci) : (uint32_t)w.pos[i];
+            const uint32_t slot = walk ? (uint32_t)info_slot(ci) : (uint32_t)w.slot[i];
+            cells |= cell << (8 * a);
+            if (a < 2) lo |= slot << (16 * a); else hi |= slot << (16 * (a - 2));
+        }
+        p.np[i] = cells, p.ns_lo[i] = lo, p.ns_hi[i] = hi;
+    }
+    p.pot_o[0] = c.n_pots > 0 ? (uint32_t)objs[info_cell(c.pot0) * ostride] : 0u;
+    p.pot_o[1] = c.n_pots > 1 ? (uint32_t)objs[info_cell(c.pot1) * ostride] : 0u;
+}
+
+// the second half: same results as step_world<2>(tb, c, w, objs, ostride, act, dirty, ticked) on the state `p` was computed from
+OCB_HD int step_post(const Tables& tb, const Consts& c, World<2>& w, uint16_t* objs, int ostride, const int (&act)[2],
+                     const StepPre2& p, uint32_t (&dirty)[2], uint32_t& ticked) {
+    const bool i0 = act[0] == A_INTERACT, i1 = act[1] == A_INTERACT;
+    InteractEval e1;  // (field by field: a reference picked at run time would put the outcomes in local memory)
+    e1.held = i0 ? p.e1b.held : p.e1a.held, e1.newo = i0 ? p.e1b.newo : p.e1a.newo, e1.dirty = i0 ? p.e1b.dirty : p.e1a.dirty;
+    e1.reward = i0 ? p.e1b.reward : p.e1a.reward, e1.d_cd = i0 ? p.e1b.d_cd : p.e1a.d_cd, e1.d_np = i0 ? p.e1b.d_np : p.e1a.d_np;
+    e1.wr = i0 ? p.e1b.wr : p.e1a.wr;
+    const bool w0 = i0 && p.e0.wr, w1 = i1 && e1.wr;
+    const uint32_t n0 = p.e0.newo, n1 = e1.newo;
+    if (w0) objs[p.tgt0 * ostride] = (uint16_t)n0;
+    if (w1) objs[p.tgt1 * ostride] = (uint16_t)n1;
+    const int reward = (i0 ? p.e0.reward : 0) + (i1 ? e1.reward : 0);
+    w.held[0] = i0 ? p.e0.held : w.held[0];
+    w.held[1] = i1 ? e1.held : w.held[1];
+    w.counter_dishes += (i0 ? p.e0.d_cd : 0) + (i1 ? e1.d_cd : 0);
+    w.nonempty_pots += (i0 ? p.e0.d_np : 0) + (i1 ? e1.d_np : 0);
+    dirty[0] = i0 ? p.e0.dirty : 0xFFFFFFFFu;
+    dirty[1] = i1 ? e1.dirty : 0xFFFFFFFFu;
+
+    // resolve_movement / _handle_collisions (R:356-371, 393-399) from the precomputed destinations
+    int np[2], ns[2], no[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int a = act[i];
+        const bool mv = a < A_STAY;
+        const uint32_t slots = (a & 2) ? p.ns_hi[i] : p.ns_lo[i];
+        np[i] = mv ? (int)((p.np[i] >> (8 * (a & 3))) & 0xFFu) : w.pos[i];
+        ns[i] = mv ? (int)((slots >> (16 * (a & 1))) & 0xFFFFu) : w.slot[i];
+        no[i] = mv ? a : w.orient[i];
+    }
+    const bool blocked = (np[0] == np[1]) || (np[0] == w.pos[1] && w.pos[0] == np[1]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        w.pos[i] = blocked ? w.pos[i] : np[i];
+        w.slot[i] = blocked ? w.slot[i] : ns[i];
+        w.orient[i] = no[i];
+    }
+
+    // step_environment_effects (R:373-379): the first two pots from the values read in step_pre, patched by this step's writes
+    w.timestep += 1;
+    uint32_t tk = 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (q >= c.n_pots) break;
+        const int cell = info_cell(q == 0 ? c.pot0 : c.pot1);
+        uint32_t o = p.pot_o[q];
+        o = (w0 && p.tgt0 == cell) ? n0 : o;
+        o = (w1 && p.tgt1 == cell) ? n1 : o;
+        const bool cooking = obj_name(o) == O_SOUP && soup_cooking(tb, c, o);
+        if (cooking) objs[cell * ostride] = (uint16_t)(o + 0x100u);
+        tk |= cooking ? (1u << q) : 0u;
+    }
+    for (int q = 2; q < c.n_pots; ++q) tk |= tick_pot(tb, c, objs, ostride, tb.pot_info[q]) ? (1u << (q & 31)) : 0u;
+    ticked = c.n_pots > 32 ? 0xFFFFFFFFu : tk;
+    return reward;
+}
+
 template <int P>
 OCB_HD void reset_world(const Tables& tb, World<P>& w) {  // R:387-391
 #pragma unroll

@@ -236,6 +236,11 @@ __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s
     const bool store_obs = fp.obs_slab != nullptr;
 
     FusedSlot<P> sa, sb;  // slot 0 / slot 1 (two named objects: an array of them ends up in local memory)
+    // One tile in flight: the step time IS the chain env -> loaders -> conv -> FC -> head -> sampling, so the env warps compute
+    // everything of the next transition that depends on the state only (step_pre, oc_core.cuh) while the policy forward
+    // runs, and only pick among those outcomes once the actions arrive (step_post).  With two tiles in flight the other
+    // tile's policy pass hides the transition, and the outcomes of two slots would have to stay in registers.
+    StepPre2 pre;
     sa.vts = sa.acts = sb.vts = sb.acts = 0;
     sa.tma_pending = sb.tma_pending = false;
 
@@ -281,14 +286,22 @@ __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s
             q.tma_pending = false;
         }
         if (u > 0) {
+            // the cells the players stand on are cleared now, while the actions are still being computed (one lane owns all
+            // views of its world, so nothing has to be ordered against other lanes); an episode end overwrites them anyway
+            __syncwarp();  // lane 0's wait for the bulk store above covers the warp
+#pragma unroll
+            for (int i = 0; i < P; ++i) oldslot[i] = q.w.slot[i];
+            obs_phase1<P, 1>(tb, myplanes, view_stride, tmpl, false, 0, oldslot);
             mbar_wait(bars + 8 * (FB_ACT_FULL + slot), q.acts & 1);
             if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)q.vts, 0);
             ++q.acts;
             int act[P];
             act[0] = s_act[slot * 128 + ew * 32 + lane], act[1] = s_act[slot * 128 + kFWorlds + ew * 32 + lane];
-#pragma unroll
-            for (int i = 0; i < P; ++i) oldslot[i] = q.w.slot[i];
-            const int r = step_world<P>(tb, c, q.w, myobjs, 32, act, dirty, ticked);
+            int r;
+            if constexpr (kSlots == 1)
+                r = step_post(tb, c, q.w, myobjs, 32, act, pre, dirty, ticked);
+            else
+                r = step_world<P>(tb, c, q.w, myobjs, 32, act, dirty, ticked);
             const bool done = q.w.timestep >= c.horizon;
             q.cur_return += r;
             if (done) {
@@ -311,7 +324,7 @@ __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s
         }
         __syncwarp();
         if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)q.vts, 2);
-        obs_phase1<P, 1>(tb, myplanes, view_stride, tmpl, full, 0, oldslot);
+        if (full) obs_phase1<P, 1>(tb, myplanes, view_stride, tmpl, true, 0, oldslot);  // (else: cleared before the action wait)
         obs_phase2<P, 1>(tb, c, myplanes, view_stride, myobjs, 32, full, 0, q.w, dirty, ticked);
         mbar_arrive(bars + 8 * (FB_OBS_FULL + slot));  // release: the loaders may read this lane's planes
         if (kProf && ew == 0) trace_ev<kProf>(fp.pol, (int)q.vts, 3);
@@ -334,6 +347,7 @@ __device__ __forceinline__ void fused_env_role(const FusedParams& fp, uint8_t* s
                 for (int v = 0; v < P; ++v) warp_copy_out(dst + v * obs_view_stride, planes + v * view_stride, q.nbytes, lane);
             }
         }
+        if constexpr (kSlots == 1) step_pre(tb, c, q.w, myobjs, 32, pre);  // for the next step, off the critical path
     };
 
     // world state back to HBM (the next launch, or ocb_get_state, continues from it)

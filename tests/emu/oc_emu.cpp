@@ -21,6 +21,8 @@ namespace {
 
 size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+bool g_two_halves = false;  // G code 101: one lane per world, transition as step_pre + step_post (two players)
+
 template <int P, int G>
 int rollout(const Tables& tb, const uint8_t* tmpl, int32_t* state, int N, int K, const uint8_t* actions, uint64_t seed,
             uint64_t step0, uint32_t world0, int8_t* obs, int32_t* rew, int32_t* done, uint8_t* actions_out) {
@@ -94,7 +96,18 @@ int rollout(const Tables& tb, const uint8_t* tmpl, int32_t* state, int N, int K,
                 if (actions_out && n < N)
                     for (int i = 0; i < P; ++i) actions_out[((size_t)k * P + i) * N + n] = (uint8_t)act[i];
                 for (int i = 0; i < P; ++i) oldslot[lane][i] = w[lane].slot[i];
-                const int r = step_world<P>(tb, c, w[lane], objs.data() + wi, WPW, act, dirty[lane], ticked[lane]);
+                int r;
+                if constexpr (P == 2) {
+                    if (g_two_halves) {  // the fused rollout's env warps: step_pre while the policy runs, step_post on the actions
+                        StepPre2 pre;
+                        step_pre(tb, c, w[lane], objs.data() + wi, WPW, pre);
+                        r = step_post(tb, c, w[lane], objs.data() + wi, WPW, act, pre, dirty[lane], ticked[lane]);
+                    } else {
+                        r = step_world<P>(tb, c, w[lane], objs.data() + wi, WPW, act, dirty[lane], ticked[lane]);
+                    }
+                } else {
+                    r = step_world<P>(tb, c, w[lane], objs.data() + wi, WPW, act, dirty[lane], ticked[lane]);
+                }
                 const bool d = w[lane].timestep >= c.horizon;
                 cur_ret[lane] += r;
                 if (d) {
@@ -153,6 +166,8 @@ template <int P>
 int rollout_p(int G, const Tables& tb, const uint8_t* tmpl, int32_t* state, int N, int K, const uint8_t* actions,
               uint64_t seed, uint64_t step0, uint32_t world0, int8_t* obs, int32_t* rew, int32_t* done,
               uint8_t* actions_out) {
+    g_two_halves = (G == 101);
+    if (G == 101) G = 1;
     switch (G) {
         case 1: return rollout<P, 1>(tb, tmpl, state, N, K, actions, seed, step0, world0, obs, rew, done, actions_out);
         case 2: return rollout<P, 2>(tb, tmpl, state, N, K, actions, seed, step0, world0, obs, rew, done, actions_out);

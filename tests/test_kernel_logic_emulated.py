@@ -29,7 +29,7 @@ def scripted_actions(lp, N, K, rng, noise=0.25):
 
 @pytest.mark.parametrize("name", ["simple", "random0", "random1", "random3", "unident_s", "simple_tomato",
                                   "multiplayer_schelling", "simple_single", "corridor"])
-@pytest.mark.parametrize("G", [1, 2, 4, 8])
+@pytest.mark.parametrize("G", [1, 2, 4, 8, 101])  # 101: one lane per world, the transition as step_pre + step_post
 def test_emulated_kernel_matches_oracle(name, G):
     rng = np.random.default_rng(hash((name, G)) % 2**32)
     lp = layouts.load_layout(name, 50)
@@ -66,6 +66,26 @@ def test_emulated_rng_stream_matches_oracle_stream():
     assert np.array_equal(ao, random_actions(77, 100, N, 5, K, 2))
     o, _, _ = orc.rollout(ao)
     assert np.array_equal(o, obs)
+
+
+@pytest.mark.parametrize("name", ["simple", "unident_s", "random0", "random1", "random3", "scenario2", "mdp_test"])
+def test_two_half_transition_matches_oracle_on_random_play(name):
+    """step_pre + step_post (what the fused rollout's env warps run) over long random play — both players facing the same
+    counter or pot, pots filling and cooking, episode ends — against the C oracle: observations, rewards, final states"""
+    lp = layouts.load_layout(name, 120)
+    if lp.num_players != 2:
+        pytest.skip("two players")
+    N, K = 96, 700
+    orc = COracle(lp, N)
+    st = orc.state.copy()
+    ao = np.zeros((K, 2, N), np.uint8)
+    obs = np.zeros((K, 2, N, lp.width, lp.height, lp.channels), np.int8)
+    rew = np.zeros((K, 2, N), np.int32)
+    done = np.zeros((K, N), np.int32)
+    assert emu_lib().ocemu_rollout(ctypes.byref(orc.cfg), 101, _p(st), N, K, None, 5, 0, 0, _p(obs), _p(rew), _p(done), _p(ao)) == 0
+    o, r, d = orc.rollout(ao)
+    assert np.array_equal(o, obs) and np.array_equal(r, rew) and np.array_equal(d, done)
+    assert np.array_equal(st, orc.state)
 
 
 def test_mixed_play_schedule_and_mask_stream_of_the_kernels_match_the_oracle():
