@@ -1042,6 +1042,7 @@ __device__ __forceinline__ void pair_conv_role(long long* pw, const PolicyParams
             const uint32_t cb0 = cellb + c_slot * colw, cb1 = cellb + s1 * colw, cb2 = cellb + s2 * colw;
             const long long ti0 = kProf ? clock64() : 0;
             if (cp == 3 && tracer) trace_ev<kProf>(prm, t - t0, 54);  // waits of conv 3 done, issue starts
+            if (cp < 2 && tracer) trace_ev<kProf>(prm, t - t0, 11 + cp);  // waits of conv 0 / 1 done
             if (elect_one()) {
 #pragma unroll
                 for (int j = 0; j < 9; ++j) {

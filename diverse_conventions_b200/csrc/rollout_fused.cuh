@@ -196,6 +196,7 @@ __device__ __forceinline__ void fused_loader_role(const FusedParams& fp, uint32_
         tc_fence_before();
         mbar_arrive(bars + 8 * ((kSplit ? FB_COL_FULL : PB_COL_FULL) + slot));
         if (kProf && lwarp == 0 && first_col) trace_ev<kProf>(fp.pol, (int)lt, 9);
+        if (kProf && lw == 0 && lx >= 1 && lx <= 4) trace_ev<kProf>(fp.pol, (int)lt, 3 + lx);  // grid columns 1..4 in tensor memory
         lx += 2;
         if (lx >= W) {  // this group's last column of the tile: its plane reads are done
             mbar_arrive(bars + 8 * (FB_OBS_EMPTY + cur.s));

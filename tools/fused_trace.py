@@ -29,6 +29,7 @@ NAMES = {0: "env_got_actions", 1: "env_stepped", 2: "env_planes_free", 3: "env_p
 NAMES.update({54: "conv3_issue_starts", 55: "FC2a_issue_starts", 56: "conv3_first_mma", 63: "conv3_mmas_issued", 57: "FC2a_critic_issue_starts",
               58: "FC2a_critic_issued", 59: "epi_conv2_in_regs", 60: "epi_conv2_split_done", 61: "epi_conv2_stored",
               62: "FC2a_operand_seen"})
+NAMES.update({4: "loader_col1", 5: "loader_col2", 6: "loader_col3", 7: "loader_col4", 11: "conv0_issue_starts", 12: "conv1_issue_starts"})
 for p in range(8):
     NAMES[16 + p] = "conv%d_issued" % p
     NAMES[24 + p] = "fc%d_issued" % p
