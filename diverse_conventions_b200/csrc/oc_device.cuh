@@ -54,28 +54,6 @@ __device__ __forceinline__ void tile_fill_wait(uint32_t bar) {  // every lane th
     }
 }
 
-// ---- mbarrier hand-offs between the roles of the split rollout kernel (CTA scope, generic proxy)
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t spins = 0;; ++spins) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) return;
-        if (spins > (1u << 26)) __trap();  // a lost hand-off must not hang the GPU
-    }
-}
-
 // ---- named-barrier hand-offs (bar.arrive by the producer, bar.sync by the consumer; whole warps, `threads` = all
 // participants of both sides).  A waiting warp is descheduled by the hardware: unlike an mbarrier poll loop it takes no
 // issue slots from the warps that are working, which is what the split rollout kernel's transition warp needs.
