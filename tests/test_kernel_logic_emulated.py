@@ -68,7 +68,7 @@ def test_emulated_rng_stream_matches_oracle_stream():
     assert np.array_equal(o, obs)
 
 
-@pytest.mark.parametrize("name", ["simple", "unident_s", "random0", "random1", "random3", "scenario2", "mdp_test"])
+@pytest.mark.parametrize("name", layouts.builtin_layout_names())
 def test_two_half_transition_matches_oracle_on_random_play(name):
     """step_pre + step_post (what the fused rollout's env warps run) over long random play — both players facing the same
     counter or pot, pots filling and cooking, episode ends — against the C oracle: observations, rewards, final states"""
