@@ -417,6 +417,31 @@ def test_full_size_properties_cramped_room(N, lanes):
     assert int(rs.sum()) <= int(total_rew)
 
 
+@pytest.mark.parametrize("name", CLASSIC)
+def test_config4_size_env_rollouts_match_oracle(name):
+    """the five classic layouts at BASELINE config 4's 8,192 worlds (default launch shape: the role-split kernel for the
+    small planes, the one-warp kernel for asymmetric_advantages / counter_circuit): 450 random steps across an episode end,
+    a strided subset of worlds replayed through the oracle, every world's done flags and the episode accounting checked"""
+    N, H, K = 8192, 400, 90
+    lp = layouts.load_layout(name, H)
+    env = make_env(name, N, H, seed=11)
+    sub = np.arange(3, N, 257)
+    orc = COracle(lp, len(sub))
+    out = env.alloc_rollout(K)
+    for it in range(5):
+        env.rollout_random(K, out)
+        steps = torch.arange(it * K + 1, (it + 1) * K + 1, device="cuda")
+        assert torch.equal(out["dones"].bool(), ((steps % H) == 0)[:, None].expand(K, N))
+        assert torch.equal(out["rewards"][:, 0], out["rewards"][:, 1])
+        a = out["actions"].cpu().numpy()
+        o, r, d = orc.rollout(np.ascontiguousarray(a[:, :, sub]))
+        assert np.array_equal(out["obs"][:, :, sub].cpu().numpy(), o)
+        assert np.array_equal(out["rewards"][:, :, sub].cpu().numpy(), r)
+    assert np.array_equal(env.get_state()[sub], orc.state)
+    rs, ep = env.episode_stats()
+    assert int(ep.sum()) == N
+
+
 def test_observe_matches_rollout_last_obs_and_reset_idempotent():
     env = make_env("unident_s", 300, horizon=400, seed=5)
     out = env.rollout_random(40)
