@@ -100,7 +100,36 @@ struct BBResetStream {
         start_next(seed, world);
         while (rounds < 10) round();
     }
-    // B:141-149, as bb_reset_world
+    // B:141-149 for the lanes with `d` set, written as selects: some lane of a warp ends an episode on nearly every step, so a
+    // branch would make the whole warp walk the reset code anyway, plus the divergence bookkeeping
+    __device__ __forceinline__ void reset_if(BBWorld& w, bool d, uint64_t seed, uint32_t world) {
+        const uint32_t block = w.episode / ActionRng<2>::kStepsPerBlock;
+        const bool swap = d && block != cur_block;  // == cur_block + 1: episodes count up by one
+        if (swap && rounds < 10) {  // rare (four one-step episodes in a row): the next block is not complete yet
+            while (rounds < 10) round();
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cur[q] = swap ? nxt[q] : cur[q];
+        cur_block = swap ? block : cur_block;
+        {   // start_next for the swapping lanes
+            const uint64_t s = seed ^ kResetStream;
+            const uint64_t nb = (uint64_t)cur_block + 1;
+            nxt[0] = swap ? world : nxt[0], nxt[1] = swap ? (uint32_t)nb : nxt[1], nxt[2] = swap ? (uint32_t)(nb >> 32) : nxt[2];
+            nxt[3] = swap ? 0u : nxt[3];
+            k0 = swap ? (uint32_t)s : k0, k1 = swap ? (uint32_t)(s >> 32) : k1;
+            rounds = swap ? 0 : rounds;
+        }
+        const int h = (int)(w.episode % ActionRng<2>::kStepsPerBlock) * 2;  // 16-bit slices h, h + 1 of the block
+        const uint32_t lo = (h & 2) ? cur[1] : cur[0], hi = (h & 2) ? cur[3] : cur[2];
+        const uint32_t word = (h & 4) ? hi : lo;
+        w.loc[0] = d ? (int)(((word & 0xFFFFu) * (uint32_t)kSpaces) >> 16) : w.loc[0];
+        w.loc[1] = d ? (int)(((word >> 16) * (uint32_t)kSpaces) >> 16) : w.loc[1];
+        w.time = d ? kTime - 1 : w.time;
+        w.hist[0][0] = d ? 0 : w.hist[0][0], w.hist[0][1] = d ? 0 : w.hist[0][1];
+        w.hist[1][0] = d ? 0 : w.hist[1][0], w.hist[1][1] = d ? 0 : w.hist[1][1];
+        w.episode += d ? 1u : 0u;
+    }
+    // the same with a branch (one-off resets outside the step loop)
     __device__ __forceinline__ void reset(BBWorld& w, uint64_t seed, uint32_t world) {
         const uint32_t block = w.episode / ActionRng<2>::kStepsPerBlock;
         if (block != cur_block) {  // == cur_block + 1: episodes count up by one
@@ -253,7 +282,7 @@ __global__ void __launch_bounds__(256) bb_kernel(const BBParams prm) {
             const bool d = (w.time == 0) || oob;
             float r = (diff == 0) ? 1.0f : -(float)diff * 0.2f;  // == the reference's fp64 value narrowed (static_assert above)
             r = oob ? (float)(-kSpaces * (w.time + 1)) * 0.2f : r;
-            if (d) rs.reset(w, prm.seed, gworld);  // pantheonrl_extension/vectorenv.py:369-370
+            rs.reset_if(w, d, prm.seed, gworld);  // pantheonrl_extension/vectorenv.py:369-370
             if (rew_ptr != nullptr) {
                 rew_ptr[0] = r, rew_ptr[N] = r;
                 rew_ptr += PN;

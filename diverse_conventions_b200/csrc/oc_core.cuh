@@ -624,8 +624,9 @@ struct ActionRng {
     // 16-bit slice number sub*kPad + player, mapped to 0..num_actions-1
     OCB_HDM int action(uint64_t step, int player, int num_actions) const {
         const int h = (int)(step % kStepsPerBlock) * kPad + player;
-        const int wsel = h >> 1;
-        const uint32_t word = wsel == 0 ? r[0] : wsel == 1 ? r[1] : wsel == 2 ? r[2] : r[3];
+        const int wsel = h >> 1;  // two-level select on its bits (a compare chain compiles to branches)
+        const uint32_t lo = (wsel & 1) ? r[1] : r[0], hi = (wsel & 1) ? r[3] : r[2];
+        const uint32_t word = (wsel & 2) ? hi : lo;
         const uint32_t half = (h & 1) ? (word >> 16) : (word & 0xFFFFu);
         return (int)((half * (uint32_t)num_actions) >> 16);
     }
